@@ -1,0 +1,148 @@
+/*
+ * dcn_b200.h — C ABI of libdcn_b200.so, the B200 (sm_100a) deformable-convolution engine
+ * that sits below the `DeformConv2d` / `TorchDeformConv2d` module boundary of
+ * x-y20/jittor-dcn.
+ *
+ * Everything the reference computes between "offsets are known" and "NCHW output is
+ * returned" — and the autograd backward of that span — is behind these entry points:
+ *
+ *   reference span replaced (forward)   deform_conv.py:62-81 (+ grid_sample_wrapper :30-54)
+ *                                       train.py:102-140
+ *   reference span replaced (backward)  the autograd of the above, triggered at
+ *                                       train.py:249 (loss.backward) / train.py:414
+ *                                       (optimizer.backward)
+ *
+ * The companion offset convolution (deform_conv.py:16-21,58 / train.py:80-85,98) stays a
+ * framework convolution: its output is the `offset` argument here and `grad_offset` is
+ * handed back to it.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name
+ *     says host; the caller owns every buffer including the workspace;
+ *   - every function returns a DcnStatus (0 = OK, negative = error) and never throws;
+ *     dcn_last_error() returns a thread-local human readable message for the last failure;
+ *   - all work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as
+ *     void*; NULL = legacy default stream); nothing synchronises the device;
+ *   - tensors are dense, contiguous, 16-byte aligned, NCHW, float32 (DCN_OPERAND_FP32) —
+ *     see DcnShape.operand for the bf16 storage mode.
+ */
+#ifndef DCN_B200_H_
+#define DCN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCN_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef enum DcnStatus {
+  DCN_OK = 0,
+  DCN_ERR_BAD_SHAPE = -1,      /* non-positive dims, empty output, index space > 2^31 */
+  DCN_ERR_NULL_POINTER = -2,   /* a required pointer is NULL */
+  DCN_ERR_MISALIGNED = -3,     /* a pointer is not 16-byte aligned */
+  DCN_ERR_WORKSPACE = -4,      /* workspace smaller than dcn_workspace_bytes() */
+  DCN_ERR_CUDA = -5,           /* a CUDA runtime call failed (see dcn_last_error) */
+  DCN_ERR_UNSUPPORTED = -6,    /* combination of variant / operand / flags not available */
+  DCN_ERR_NCCL = -7            /* NCCL could not be loaded or a collective failed */
+} DcnStatus;
+
+/* Which of the reference's two (mathematically different) operators to reproduce. */
+enum {
+  /* deform_conv.py:56-81 — coordinates normalised by (W_out-1,H_out-1) (:34-38), columns
+   * ordered (n, c) (:72-73). */
+  DCN_VARIANT_JITTOR = 0,
+  /* train.py:95-140 — coordinates normalised by (W_in-1,H_in-1) (:111-112), columns are the
+   * memory-reinterpreting reshape of the [B,C,Ho,Wo,N] sample tensor (:129-131). */
+  DCN_VARIANT_TORCH = 1
+};
+
+/* Storage / arithmetic mode of the dense contraction. */
+enum {
+  /* x, weight, out, grads: float32.  Tensor-core path uses a 3-term bf16 split
+   * (hi*hi + hi*lo + lo*hi, fp32 accumulate; |err| ~ 5e-6 relative). */
+  DCN_OPERAND_FP32 = 0,
+  /* x, weight, grad_out stored as bfloat16; out, all gradients float32; fp32 accumulate. */
+  DCN_OPERAND_BF16 = 1
+};
+
+/* DcnShape.flags */
+enum {
+  DCN_FLAG_ACCUM_GRAD_X = 1 << 0,  /* dcn_backward adds into grad_x instead of overwriting */
+  DCN_FLAG_FORCE_SIMT = 1 << 1,    /* use the generic CUDA-core kernels even when the
+                                      tcgen05 path supports the shape (A/B testing) */
+  DCN_FLAG_NO_GRAD_X = 1 << 2,     /* dcn_backward: skip grad_x (first layer of a net) */
+  DCN_FLAG_RELU_OUT = 1 << 3       /* reserved for the fused epilogue */
+};
+
+/* Problem description.  Constructor arguments of the reference modules
+ * (deform_conv.py:7-14, train.py:71-78) plus the input extent. */
+typedef struct DcnShape {
+  int32_t B, C, O;     /* batch, in_channels, out_channels */
+  int32_t H, W;        /* input height / width */
+  int32_t kh, kw;      /* kernel_size  (N = kh*kw taps) */
+  int32_t sh, sw;      /* stride   — only enters through H_out/W_out */
+  int32_t ph, pw;      /* padding  — idem */
+  int32_t variant;     /* DCN_VARIANT_* */
+  int32_t operand;     /* DCN_OPERAND_* */
+  int32_t flags;       /* DCN_FLAG_* */
+} DcnShape;
+
+/* phases for dcn_workspace_bytes */
+enum { DCN_PHASE_FORWARD = 0, DCN_PHASE_BACKWARD = 1, DCN_PHASE_CORNERS = 2 };
+
+/* ---- introspection ---------------------------------------------------------------- */
+int dcn_version(void);
+const char* dcn_last_error(void);
+const char* dcn_status_string(int status);
+/* H_out / W_out exactly as the offset conv produces them (deform_conv.py:34-35). */
+int dcn_output_hw(const DcnShape* s, int32_t* h_out, int32_t* w_out);
+/* Bytes of caller-owned scratch the given phase needs (16-byte aligned). */
+size_t dcn_workspace_bytes(const DcnShape* s, int phase);
+/* Name of the kernel family dcn_forward/dcn_backward will pick for this shape
+ * ("umma" = tcgen05 implicit GEMM, "simt" = generic CUDA-core kernels). */
+const char* dcn_path_name(const DcnShape* s, int phase);
+/* Number of kernel launches issued by this library on the calling thread since the
+ * last reset (bench.py's gpu_launches). */
+uint64_t dcn_launch_count(void);
+void dcn_launch_count_reset(void);
+
+/* ---- the hot path ------------------------------------------------------------------ */
+
+/* Forward: replaces deform_conv.py:62-81 / train.py:102-140.
+ *   x       [B,C,H,W]            offset [B,2N,Ho,Wo]  (planar: channels 0..N-1 "x", N..2N-1 "y")
+ *   weight  [O,C,kh,kw]          bias   [O] or NULL
+ *   out     [B,O,Ho,Wo]                                                                   */
+int dcn_forward(const DcnShape* s, const void* x, const void* offset, const void* weight,
+                const void* bias, void* out, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* Backward: replaces the autograd of the same span (train.py:249, train.py:414).
+ *   grad_out    [B,O,Ho,Wo]
+ *   grad_x      [B,C,H,W]      (overwritten, or accumulated with DCN_FLAG_ACCUM_GRAD_X;
+ *                               may be NULL with DCN_FLAG_NO_GRAD_X)
+ *   grad_offset [B,2N,Ho,Wo]   grad_weight [O,C,kh,kw]   grad_bias [O] or NULL            */
+int dcn_backward(const DcnShape* s, const void* x, const void* offset, const void* weight,
+                 const void* grad_out, void* grad_x, void* grad_offset, void* grad_weight,
+                 void* grad_bias, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Sampling geometry only (bit-exactness probe): for every (b, n, h, w)
+ *   y0,x0 [B,N,Ho,Wo] int32   floor'ed row / column of the north-west corner
+ *   w4    [B,N,Ho,Wo,4] f32   corner weights nw, ne, sw, se (unmasked)                     */
+int dcn_debug_corners(const DcnShape* s, const void* offset, int32_t* y0, int32_t* x0,
+                      float* w4, void* stream);
+
+/* ---- data-parallel helpers (one process per GPU; NCCL over NVLink) --------------------
+ * NCCL is dlopen'ed on first use; the core library has no link-time dependency on it.   */
+int dcn_comm_unique_id(void* out128_host);                     /* 128-byte ncclUniqueId  */
+int dcn_comm_init(int rank, int world, const void* unique_id128_host, void** comm);
+/* buf[i] = scale * sum_over_ranks(buf[i]), in place, float32 */
+int dcn_allreduce_sum_f32(void* comm, void* buf, size_t count, float scale, void* stream);
+int dcn_comm_destroy(void* comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCN_B200_H_ */
