@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""bench.py — DeformConv2d fwd+bwd images/sec on B200 (the metric of BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|det2|det5]
+                    [--variant torch|jittor] [--impl ours|reference]
+    torchrun ... bench.py --gpus N ...            (N > 1, one rank per GPU, NCCL)
+
+A "step" is one pass of the hot path (engine forward + backward through the C ABI,
+dcn_forward + dcn_backward, offsets supplied) over one batch of synthetic input.  At N > 1
+every rank works on its own batch of the same size (weak scaling along the batch dimension,
+the only natural sharding — SURVEY.md 8e) and the step ends with ONE all-reduce of the flat
+weight/bias/offset-conv gradient bucket.
+
+JSON keys (one line, rank 0): see the task contract; `value` = device-resident inputs,
+`e2e` = the same metric through the module API (`TorchDeformConv2d.forward/backward`) with
+HOST input buffers (pinned H2D of x every step, D2H of the parameter gradients),
+`roofline` = dominant kernel against MEASURED_PEAKS.json, `cpu_baseline` = the reference's op
+chain (oracle/torch_chain.py, same torch CPU kernels as the reference) on this host's cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (description, B per GPU, C, O, H, W, k, s, p)
+    "cfg2": ("DeformConv2d 64->64 3x3 s1 p1, 128x128, batch 256 per GPU (BASELINE configs[1] shape), fwd+bwd",
+             256, 64, 64, 128, 128, 3, 1, 1),
+    "cfg3": ("DeformConv2d 256->256 3x3 s1 p1, 28x28, batch 64 per GPU (BASELINE configs[2]), fwd+bwd",
+             64, 256, 256, 28, 28, 3, 1, 1),
+    "det2": ("detector conv2 16->32 3x3 s2 p1, 128x128, batch 1024 per GPU (BASELINE configs[4] layer), fwd+bwd",
+             1024, 16, 32, 128, 128, 3, 2, 1),
+    "det5": ("detector conv5 128->256 3x3 s2 p1, 16x16, batch 1024 per GPU (BASELINE configs[4] layer), fwd+bwd",
+             1024, 128, 256, 16, 16, 3, 2, 1),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", default="torch", choices=["torch", "jittor"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--offset-sigma", type=float, default=2.0,
+                    help="std (pixels) of the synthetic live offsets (SURVEY 8d)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--force-simt", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], bf16_burst=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def layer_bytes_flops(B, C, O, H, W, Ho, Wo, N):
+    """Algorithmic work, per launch of each role, float32."""
+    K = C * N
+    x, off, out, wgt = 4 * B * C * H * W, 4 * B * 2 * N * Ho * Wo, 4 * B * O * Ho * Wo, 4 * O * K
+    flops = 2.0 * B * Ho * Wo * K * O
+    return {
+        "fwd": dict(bytes=x + off + out + wgt, flops=flops),
+        "bwd_data": dict(bytes=out + x + off + wgt + x + off, flops=flops),   # read gout,x,off,W; write gx,goff
+        "bwd_weight": dict(bytes=out + x + off + wgt, flops=flops),           # read gout,x,off; write gW
+        "bwd": dict(bytes=out + 2 * x + 2 * off + 2 * wgt, flops=2 * flops),  # SURVEY 8d backward total
+    }
+
+
+KERNEL_ROLE = {"fwd_kernel": "fwd", "bwd_data_kernel": "bwd_data", "bwd_weight_kernel": "bwd_weight",
+               "umma_fwd_kernel": "fwd", "umma_bwd_data_kernel": "bwd_data",
+               "umma_bwd_weight_kernel": "bwd_weight"}
+
+
+def cpu_reference_step(wl, variant, micro_b, with_offset_conv, seed=0):
+    """One fwd+bwd of the reference's op chain on `micro_b` samples; returns a callable."""
+    import torch
+    from oracle import torch_chain
+    _, B, C, O, H, W, k, s, p = wl
+    torch.manual_seed(seed)
+    layer = torch_chain.ChainLayer(C, O, k, s, p, True, variant)
+    with torch.no_grad():
+        layer.weight.normal_(0, (2.0 / (C * k * k)) ** 0.5)
+        layer.offset_conv.weight.normal_(0, 0.01)
+        layer.offset_conv.bias.normal_(0, 1.0)
+    x = torch.randn(micro_b, C, H, W)
+    Ho, Wo = torch_chain.out_hw(H, W, k, s, p)
+    gout = torch.randn(micro_b, O, Ho, Wo)
+    off = torch.randn(micro_b, 2 * k * k, Ho, Wo) * 2.0
+
+    def step_layer():
+        xi = x.clone().requires_grad_(True)
+        out = layer(xi)
+        out.backward(gout)
+        layer.zero_grad(set_to_none=True)
+
+    def step_span():
+        torch_chain.chain_forward_backward(x, off, layer.weight, layer.bias, gout, variant=variant,
+                                           kernel_size=k, stride=s, padding=p)
+
+    return step_layer if with_offset_conv else step_span
+
+
+def time_cpu(fn, budget_s, min_runs=2, max_runs=7):
+    fn()  # warm-up
+    times, t_all = [], time.perf_counter()
+    while len(times) < min_runs or (len(times) < max_runs and time.perf_counter() - t_all < budget_s):
+        t0 = time.perf_counter()
+        fn()
+        times.append(time.perf_counter() - t0)
+    return statistics.median(times), len(times)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on this box's host
+    cores.  /root/reference cannot travel, so this is its op chain restated with the same
+    torch CPU kernels (oracle/torch_chain.py; pinned bit-for-bit to the unmodified reference
+    in tests/test_oracle_golden.py): kind = "port"."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    wl = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    micro_b = 8 if args.workload in ("cfg2",) else 16
+    step = cpu_reference_step(wl, args.variant, micro_b, with_offset_conv=True)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    n = 0
+    # bounded: K steps, but never more than ~150 s in total
+    while n < args.steps and (n < 2 or time.perf_counter() - t0 < 150):
+        step()
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    value = micro_b / dt
+    sample = f"{n} steps of {micro_b} samples (micro-batch of the {wl[1]}-sample workload; samples are independent)"
+    line = {
+        "impl": "reference", "metric": "DeformConv2d fwd+bwd images/sec", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": args.workload + ": " + wl[0], "variant": args.variant,
+                                        "cpu_micro_batch": micro_b, "includes_offset_conv": True},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import jittor_dcn_b200 as dcn
+    from jittor_dcn_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = dcn.load()
+
+    desc, B, C, O, H, W, k, s, p = WORKLOADS[args.workload]
+    variant = dcn.VARIANT_TORCH if args.variant == "torch" else dcn.VARIANT_JITTOR
+    flags = dcn.FLAG_FORCE_SIMT if args.force_simt else 0
+    N = k * k
+    shp = dcn.make_shape(B, C, O, H, W, k, s, p, variant, flags=flags)
+    Ho, Wo = _lib.output_hw(shp)
+
+    # ---- synthetic data, resident in HBM (seeded per rank) ---------------------------
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randn(B, C, H, W, device=dev, generator=gen)
+    off = torch.randn(B, 2 * N, Ho, Wo, device=dev, generator=gen) * args.offset_sigma
+    wt = torch.randn(O, C, k, k, device=dev, generator=gen) * (2.0 / (C * N)) ** 0.5
+    bias = torch.randn(O, device=dev, generator=gen) * 0.1
+    gout = torch.randn(B, O, Ho, Wo, device=dev, generator=gen)
+    # flat gradient bucket: [grad_weight | grad_bias | offset_conv.weight.grad | offset_conv.bias.grad]
+    n_w, n_b, n_ow, n_ob = O * C * N, O, 2 * N * C * N, 2 * N
+    bucket = torch.zeros(n_w + n_b + n_ow + n_ob, device=dev)
+
+    comm = None
+    allreduce_kind = "none"
+    if world > 1:
+        import ctypes
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            _lib.check(lib.dcn_comm_unique_id(buf), "dcn_comm_unique_id")
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid = uid.to(dev)
+        dist.broadcast(uid, 0)
+        handle = ctypes.c_void_p()
+        raw = bytes(uid.cpu().numpy().tobytes())
+        _lib.check(lib.dcn_comm_init(rank, world, raw, ctypes.byref(handle)), "dcn_comm_init")
+        comm = handle
+        allreduce_kind = "dcn_allreduce_sum_f32 (NCCL, one flat bucket)"
+
+    import ctypes
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        out = dcn.dcn_forward(x, off, wt, bias, k, s, p, variant, flags=flags)
+        gx, goff, gw, gb = dcn.dcn_backward(x, off, wt, gout, True, k, s, p, variant, flags=flags)
+        if comm is not None:
+            bucket[:n_w].copy_(gw.view(-1))
+            bucket[n_w:n_w + n_b].copy_(gb)
+            _lib.check(lib.dcn_allreduce_sum_f32(comm, ctypes.c_void_p(bucket.data_ptr()), bucket.numel(),
+                                                 1.0 / world, ctypes.c_void_p(stream.cuda_stream)),
+                       "dcn_allreduce_sum_f32")
+        return out, gx, goff
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    lib.dcn_launch_count_reset()
+    _lib.profile_begin()
+    # L2 hygiene: workloads whose inputs fit in the 126 MB L2 get it flushed (a 512 MB write)
+    # between timed iterations; the flush is outside the per-step event pairs.
+    needs_flush = (x.numel() + gout.numel()) * 4 < 400e6
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if needs_flush else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps if needs_flush else 1)]
+    barrier()
+    if needs_flush:
+        for a, b in ev:
+            flush_buf.fill_(1)
+            a.record(stream)
+            step()
+            b.record(stream)
+    else:
+        ev[0][0].record(stream)
+        for _ in range(args.steps):
+            step()
+        ev[0][1].record(stream)
+    barrier()
+    elapsed_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = int(lib.dcn_launch_count())
+    prof = _lib.profile_end()
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel ------------------------------------------------
+    pk = peaks()
+    work = layer_bytes_flops(B, C, O, H, W, Ho, Wo, N)
+    roofline, kernels = None, {}
+    for name, (cnt, tot_ms) in prof.items():
+        kernels[name] = {"launches": cnt, "avg_ms": tot_ms / max(cnt, 1), "share": tot_ms / max(elapsed_ms, 1e-9)}
+    ranked = sorted((n for n in prof if n in KERNEL_ROLE), key=lambda n: -prof[n][1])
+    if ranked:
+        top = ranked[0]
+        role = KERNEL_ROLE[top]
+        avg_s = prof[top][1] / prof[top][0] * 1e-3
+        hbm_floor = work[role]["bytes"] / (pk["hbm"] * 1e9)
+        tc_floor = work[role]["flops"] / (pk["bf16_sustained"] * 1e12)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(f"{args.workload}:{args.variant}:{top}")
+        if hbm_floor >= tc_floor:
+            ach = work[role]["bytes"] / avg_s / 1e9
+            roofline = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": ach / pk["hbm"], "traffic": traffic}
+        else:
+            ach = work[role]["flops"] / avg_s / 1e12
+            roofline = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                        "frac": ach / pk["bf16_sustained"], "traffic": traffic}
+        roofline.update({"kernel": top, "avg_ms": avg_s * 1e3, "peak_source": pk["source"],
+                         "algorithmic_bytes": work[role]["bytes"], "algorithmic_flops": work[role]["flops"]})
+
+    # ---- e2e: module API, host input buffers ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        torch.manual_seed(99 + rank)
+        cls = dcn.TorchDeformConv2d if args.variant == "torch" else dcn.TorchDeformConv2dJittorSemantics
+        layer = cls(C, O, k, s, p).to(dev)
+        layer.engine_flags = flags
+        with torch.no_grad():
+            layer.offset_conv.weight.normal_(0, 0.01)
+            layer.offset_conv.bias.normal_(0, 1.0)
+        x_host = torch.randn(B, C, H, W).pin_memory()
+        x_dev = torch.empty(B, C, H, W, device=dev)
+        params = [q for q in layer.parameters()]
+        n_par = sum(q.numel() for q in params)
+        g_host = torch.empty(n_par, dtype=torch.float32).pin_memory()
+        e_steps = max(3, min(args.steps, 10))
+
+        def e2e_step():
+            x_dev.copy_(x_host, non_blocking=True)                 # H2D of the step's input
+            xi = x_dev.detach().requires_grad_(True)
+            out = layer(xi)
+            torch.autograd.backward(out, gout)
+            flat = torch.cat([q.grad.reshape(-1) for q in params])
+            if world > 1:
+                dist.all_reduce(flat)
+            g_host.copy_(flat, non_blocking=True)                   # D2H of the step's result
+            for q in params:
+                q.grad = None
+            stream.synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / e_steps
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * B / dt, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
+               "d2h_bytes_per_step": n_par * 4, "ms_per_step": dt * 1e3, "steps": e_steps,
+               "api": f"jittor_dcn_b200.{cls.__name__}.forward + autograd backward (offset conv included)"}
+        del layer, x_host, x_dev
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        micro_b = 8 if args.workload == "cfg2" else 16
+        fn = cpu_reference_step(WORKLOADS[args.workload], args.variant, micro_b, with_offset_conv=False)
+        med, runs = time_cpu(fn, budget_s=20.0)
+        cpu = {"value": micro_b / med, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"median of {runs} fwd+bwd passes over a {micro_b}-sample micro-batch of the same layer "
+                         f"(reference op chain restated with torch CPU ops, offsets supplied)"}
+
+    if rank == 0:
+        line = {
+            "metric": "DeformConv2d fwd+bwd images/sec", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload + ": " + desc, "variant": args.variant,
+                       "batch_per_gpu": B, "global_batch": world * B, "offset_sigma_px": args.offset_sigma,
+                       "path_fwd": lib.dcn_path_name(ctypes.byref(shp), 0).decode(),
+                       "path_bwd": lib.dcn_path_name(ctypes.byref(shp), 1).decode(),
+                       "l2": ("L2 flushed (512 MB write) between timed iterations" if needs_flush else
+                              "inputs (x %.0f MB + gout %.0f MB) exceed the 126 MB L2; no flush needed"
+                              % (x.numel() * 4 / 1e6, gout.numel() * 4 / 1e6)),
+                       "allreduce": allreduce_kind, "parallelism": f"dp{world}"},
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if comm is not None:
+        lib.dcn_comm_destroy(comm)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -36,6 +36,13 @@
 extern "C" {
 #endif
 
+/* every entry point below is exported; everything else in the library is hidden */
+#if defined(__GNUC__)
+#define DCN_API __attribute__((visibility("default")))
+#else
+#define DCN_API
+#endif
+
 #define DCN_B200_VERSION 100 /* major*10000 + minor*100 + patch */
 
 typedef enum DcnStatus {
@@ -94,20 +101,26 @@ typedef struct DcnShape {
 enum { DCN_PHASE_FORWARD = 0, DCN_PHASE_BACKWARD = 1, DCN_PHASE_CORNERS = 2 };
 
 /* ---- introspection ---------------------------------------------------------------- */
-int dcn_version(void);
-const char* dcn_last_error(void);
-const char* dcn_status_string(int status);
+DCN_API int dcn_version(void);
+DCN_API const char* dcn_last_error(void);
+DCN_API const char* dcn_status_string(int status);
 /* H_out / W_out exactly as the offset conv produces them (deform_conv.py:34-35). */
-int dcn_output_hw(const DcnShape* s, int32_t* h_out, int32_t* w_out);
+DCN_API int dcn_output_hw(const DcnShape* s, int32_t* h_out, int32_t* w_out);
 /* Bytes of caller-owned scratch the given phase needs (16-byte aligned). */
-size_t dcn_workspace_bytes(const DcnShape* s, int phase);
+DCN_API size_t dcn_workspace_bytes(const DcnShape* s, int phase);
 /* Name of the kernel family dcn_forward/dcn_backward will pick for this shape
  * ("umma" = tcgen05 implicit GEMM, "simt" = generic CUDA-core kernels). */
-const char* dcn_path_name(const DcnShape* s, int phase);
+DCN_API const char* dcn_path_name(const DcnShape* s, int phase);
 /* Number of kernel launches issued by this library on the calling thread since the
  * last reset (bench.py's gpu_launches). */
-uint64_t dcn_launch_count(void);
-void dcn_launch_count_reset(void);
+DCN_API uint64_t dcn_launch_count(void);
+DCN_API void dcn_launch_count_reset(void);
+/* Per-kernel timing for bench.py's roofline: between begin and end every kernel this
+ * library launches on the calling thread is bracketed by CUDA events on its own stream.
+ * dcn_profile_end synchronises those events and writes one line per kernel name:
+ * "<name> <launches> <total_ms>\n" (NUL terminated, truncated to cap). */
+DCN_API int dcn_profile_begin(void);
+DCN_API int dcn_profile_end(char* out, size_t cap);
 
 /* ---- the hot path ------------------------------------------------------------------ */
 
@@ -115,7 +128,7 @@ void dcn_launch_count_reset(void);
  *   x       [B,C,H,W]            offset [B,2N,Ho,Wo]  (planar: channels 0..N-1 "x", N..2N-1 "y")
  *   weight  [O,C,kh,kw]          bias   [O] or NULL
  *   out     [B,O,Ho,Wo]                                                                   */
-int dcn_forward(const DcnShape* s, const void* x, const void* offset, const void* weight,
+DCN_API int dcn_forward(const DcnShape* s, const void* x, const void* offset, const void* weight,
                 const void* bias, void* out, void* workspace, size_t workspace_bytes,
                 void* stream);
 
@@ -124,23 +137,23 @@ int dcn_forward(const DcnShape* s, const void* x, const void* offset, const void
  *   grad_x      [B,C,H,W]      (overwritten, or accumulated with DCN_FLAG_ACCUM_GRAD_X;
  *                               may be NULL with DCN_FLAG_NO_GRAD_X)
  *   grad_offset [B,2N,Ho,Wo]   grad_weight [O,C,kh,kw]   grad_bias [O] or NULL            */
-int dcn_backward(const DcnShape* s, const void* x, const void* offset, const void* weight,
+DCN_API int dcn_backward(const DcnShape* s, const void* x, const void* offset, const void* weight,
                  const void* grad_out, void* grad_x, void* grad_offset, void* grad_weight,
                  void* grad_bias, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Sampling geometry only (bit-exactness probe): for every (b, n, h, w)
  *   y0,x0 [B,N,Ho,Wo] int32   floor'ed row / column of the north-west corner
  *   w4    [B,N,Ho,Wo,4] f32   corner weights nw, ne, sw, se (unmasked)                     */
-int dcn_debug_corners(const DcnShape* s, const void* offset, int32_t* y0, int32_t* x0,
+DCN_API int dcn_debug_corners(const DcnShape* s, const void* offset, int32_t* y0, int32_t* x0,
                       float* w4, void* stream);
 
 /* ---- data-parallel helpers (one process per GPU; NCCL over NVLink) --------------------
  * NCCL is dlopen'ed on first use; the core library has no link-time dependency on it.   */
-int dcn_comm_unique_id(void* out128_host);                     /* 128-byte ncclUniqueId  */
-int dcn_comm_init(int rank, int world, const void* unique_id128_host, void** comm);
+DCN_API int dcn_comm_unique_id(void* out128_host);                     /* 128-byte ncclUniqueId  */
+DCN_API int dcn_comm_init(int rank, int world, const void* unique_id128_host, void** comm);
 /* buf[i] = scale * sum_over_ranks(buf[i]), in place, float32 */
-int dcn_allreduce_sum_f32(void* comm, void* buf, size_t count, float scale, void* stream);
-int dcn_comm_destroy(void* comm);
+DCN_API int dcn_allreduce_sum_f32(void* comm, void* buf, size_t count, float scale, void* stream);
+DCN_API int dcn_comm_destroy(void* comm);
 
 #ifdef __cplusplus
 }

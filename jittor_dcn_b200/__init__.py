@@ -1,0 +1,17 @@
+"""jittor_dcn_b200 — B200-native engine behind the reference's DeformConv2d / TorchDeformConv2d.
+
+Only what the hot path needs: the C-ABI library (csrc/ -> libdcn_b200.so), its ctypes
+binding and the two module classes that mirror the reference's operator interface.
+"""
+from ._lib import (DcnError, DcnShape, FLAG_ACCUM_GRAD_X, FLAG_FORCE_SIMT, FLAG_NO_GRAD_X,
+                   OPERAND_BF16, OPERAND_FP32, VARIANT_JITTOR, VARIANT_TORCH, load, make_shape)
+from .deform_conv import DeformConv2d
+from .functional import dcn_backward, dcn_corners, dcn_forward, deform_conv2d
+from .torch_module import TorchDeformConv2d, TorchDeformConv2dJittorSemantics
+
+__all__ = [
+    "DeformConv2d", "TorchDeformConv2d", "TorchDeformConv2dJittorSemantics", "deform_conv2d",
+    "dcn_forward", "dcn_backward", "dcn_corners", "load", "make_shape", "DcnShape", "DcnError",
+    "VARIANT_JITTOR", "VARIANT_TORCH", "OPERAND_FP32", "OPERAND_BF16", "FLAG_ACCUM_GRAD_X",
+    "FLAG_FORCE_SIMT", "FLAG_NO_GRAD_X",
+]

@@ -1,0 +1,256 @@
+// dcn_api.cu — the C ABI declared in include/dcn_b200.h: validation, workspace carving and
+// dispatch to a kernel family.  No torch types, no allocation, no device synchronisation.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "dcn_common.cuh"
+#include "dcn_umma.h"
+
+namespace dcn {
+
+static thread_local char g_err[512] = "";
+static thread_local uint64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return DCN_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches += (uint64_t)n; }
+
+// ---- per-kernel event profiler ------------------------------------------------------
+struct ProfRec {
+  const char* name;
+  cudaEvent_t a, b;
+};
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec>* g_prof = nullptr;
+
+void profile_mark(const char* name, cudaStream_t st, bool begin) {
+  if (!g_prof_on) return;
+  if (begin) {
+    ProfRec r{name, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    g_prof->push_back(r);
+  } else if (!g_prof->empty()) {
+    cudaEventRecord(g_prof->back().b, st);
+  }
+}
+
+static int check_ptr(const void* p, const char* name, bool required = true) {
+  if (!p) {
+    if (!required) return DCN_OK;
+    set_error("%s is NULL", name);
+    return DCN_ERR_NULL_POINTER;
+  }
+  if ((uintptr_t)p & 15u) {
+    set_error("%s (%p) is not 16-byte aligned", name, p);
+    return DCN_ERR_MISALIGNED;
+  }
+  return DCN_OK;
+}
+
+static int geo_or_error(const DcnShape* s, Geo* g) {
+  int rc = make_geo(s, g);
+  if (rc == DCN_ERR_NULL_POINTER) set_error("DcnShape is NULL");
+  if (rc == DCN_ERR_BAD_SHAPE)
+    set_error("bad shape B=%d C=%d O=%d H=%d W=%d k=(%d,%d) s=(%d,%d) p=(%d,%d) variant=%d", s->B,
+              s->C, s->O, s->H, s->W, s->kh, s->kw, s->sh, s->sw, s->ph, s->pw, s->variant);
+  if (rc == DCN_OK && s->operand != DCN_OPERAND_FP32 && s->operand != DCN_OPERAND_BF16) {
+    set_error("unknown operand mode %d", s->operand);
+    rc = DCN_ERR_UNSUPPORTED;
+  }
+  return rc;
+}
+
+static size_t plan_bytes(const Geo& g) { return align_up(sizeof(Tap) * (size_t)g.B * g.P, 256); }
+
+static bool use_umma(const DcnShape* s, const Geo& g, int phase) {
+  if (s->flags & DCN_FLAG_FORCE_SIMT) return false;
+  return umma_supported(g, s->operand, phase);
+}
+
+}  // namespace dcn
+
+using namespace dcn;
+
+extern "C" {
+
+int dcn_version(void) { return DCN_B200_VERSION; }
+
+const char* dcn_last_error(void) { return g_err; }
+
+const char* dcn_status_string(int status) {
+  switch (status) {
+    case DCN_OK: return "ok";
+    case DCN_ERR_BAD_SHAPE: return "bad shape";
+    case DCN_ERR_NULL_POINTER: return "null pointer";
+    case DCN_ERR_MISALIGNED: return "misaligned pointer";
+    case DCN_ERR_WORKSPACE: return "workspace too small";
+    case DCN_ERR_CUDA: return "CUDA error";
+    case DCN_ERR_UNSUPPORTED: return "unsupported configuration";
+    case DCN_ERR_NCCL: return "NCCL error";
+    default: return "unknown status";
+  }
+}
+
+int dcn_output_hw(const DcnShape* s, int32_t* h_out, int32_t* w_out) {
+  Geo g;
+  int rc = geo_or_error(s, &g);
+  if (rc) return rc;
+  if (h_out) *h_out = g.Ho;
+  if (w_out) *w_out = g.Wo;
+  return DCN_OK;
+}
+
+size_t dcn_workspace_bytes(const DcnShape* s, int phase) {
+  Geo g;
+  if (geo_or_error(s, &g)) return 0;
+  if (phase == DCN_PHASE_CORNERS) return 0;
+  if (use_umma(s, g, phase)) return umma_workspace_bytes(g, s->operand, phase);
+  if (s->operand != DCN_OPERAND_FP32) return 0;
+  return plan_bytes(g);
+}
+
+const char* dcn_path_name(const DcnShape* s, int phase) {
+  Geo g;
+  if (geo_or_error(s, &g)) return "invalid";
+  return use_umma(s, g, phase) ? "umma" : "simt";
+}
+
+int dcn_profile_begin(void) {
+  if (!g_prof) g_prof = new std::vector<ProfRec>();
+  for (auto& r : *g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof->clear();
+  g_prof_on = true;
+  return DCN_OK;
+}
+
+int dcn_profile_end(char* out, size_t cap) {
+  g_prof_on = false;
+  if (!g_prof) return DCN_OK;
+  std::map<std::string, std::pair<int, double>> agg;
+  std::vector<std::string> order;
+  for (auto& r : *g_prof) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto it = agg.find(r.name);
+      if (it == agg.end()) {
+        order.push_back(r.name);
+        agg[r.name] = {1, (double)ms};
+      } else {
+        it->second.first += 1;
+        it->second.second += ms;
+      }
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof->clear();
+  size_t used = 0;
+  if (out && cap) out[0] = 0;
+  for (auto& n : order) {
+    char line[256];
+    int len = snprintf(line, sizeof line, "%s %d %.6f\n", n.c_str(), agg[n].first, agg[n].second);
+    if (out && used + (size_t)len + 1 < cap) {
+      memcpy(out + used, line, (size_t)len + 1);
+      used += (size_t)len;
+    }
+  }
+  return DCN_OK;
+}
+
+uint64_t dcn_launch_count(void) { return g_launches; }
+void dcn_launch_count_reset(void) { g_launches = 0; }
+
+int dcn_forward(const DcnShape* s, const void* x, const void* offset, const void* weight,
+                const void* bias, void* out, void* workspace, size_t workspace_bytes,
+                void* stream) {
+  Geo g;
+  int rc = geo_or_error(s, &g);
+  if (rc) return rc;
+  if ((rc = check_ptr(x, "x")) || (rc = check_ptr(offset, "offset")) ||
+      (rc = check_ptr(weight, "weight")) || (rc = check_ptr(bias, "bias", false)) ||
+      (rc = check_ptr(out, "out")))
+    return rc;
+  const size_t need = dcn_workspace_bytes(s, DCN_PHASE_FORWARD);
+  if (need && (rc = check_ptr(workspace, "workspace"))) return rc;
+  if (workspace_bytes < need) {
+    set_error("forward workspace: have %zu bytes, need %zu", workspace_bytes, need);
+    return DCN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_umma(s, g, DCN_PHASE_FORWARD))
+    return umma_forward(g, s->operand, s->flags, x, (const float*)offset, weight, (const float*)bias,
+                        out, workspace, st);
+  if (s->operand != DCN_OPERAND_FP32) {
+    set_error("operand mode %d needs the tcgen05 path, which does not cover this shape", s->operand);
+    return DCN_ERR_UNSUPPORTED;
+  }
+  Tap* plan = (Tap*)workspace;
+  if ((rc = launch_plan(g, (const float*)offset, plan, st))) return rc;
+  return simt_forward(g, (const float*)x, plan, (const float*)weight, (const float*)bias, (float*)out,
+                      st);
+}
+
+int dcn_backward(const DcnShape* s, const void* x, const void* offset, const void* weight,
+                 const void* grad_out, void* grad_x, void* grad_offset, void* grad_weight,
+                 void* grad_bias, void* workspace, size_t workspace_bytes, void* stream) {
+  Geo g;
+  int rc = geo_or_error(s, &g);
+  if (rc) return rc;
+  const bool want_gx = !(s->flags & DCN_FLAG_NO_GRAD_X);
+  if ((rc = check_ptr(x, "x")) || (rc = check_ptr(offset, "offset")) ||
+      (rc = check_ptr(weight, "weight")) || (rc = check_ptr(grad_out, "grad_out")) ||
+      (rc = check_ptr(grad_x, "grad_x", want_gx)) || (rc = check_ptr(grad_offset, "grad_offset")) ||
+      (rc = check_ptr(grad_weight, "grad_weight")) || (rc = check_ptr(grad_bias, "grad_bias", false)))
+    return rc;
+  const size_t need = dcn_workspace_bytes(s, DCN_PHASE_BACKWARD);
+  if (need && (rc = check_ptr(workspace, "workspace"))) return rc;
+  if (workspace_bytes < need) {
+    set_error("backward workspace: have %zu bytes, need %zu", workspace_bytes, need);
+    return DCN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_umma(s, g, DCN_PHASE_BACKWARD))
+    return umma_backward(g, s->operand, s->flags, x, (const float*)offset, weight, grad_out,
+                         (float*)grad_x, (float*)grad_offset, (float*)grad_weight,
+                         (float*)grad_bias, workspace, st);
+  if (s->operand != DCN_OPERAND_FP32) {
+    set_error("operand mode %d needs the tcgen05 path, which does not cover this shape", s->operand);
+    return DCN_ERR_UNSUPPORTED;
+  }
+  Tap* plan = (Tap*)workspace;
+  if ((rc = launch_plan(g, (const float*)offset, plan, st))) return rc;
+  return simt_backward(g, s->flags, (const float*)x, plan, (const float*)weight,
+                       (const float*)grad_out, (float*)grad_x, (float*)grad_offset,
+                       (float*)grad_weight, (float*)grad_bias, st);
+}
+
+int dcn_debug_corners(const DcnShape* s, const void* offset, int32_t* y0, int32_t* x0, float* w4,
+                      void* stream) {
+  Geo g;
+  int rc = geo_or_error(s, &g);
+  if (rc) return rc;
+  if ((rc = check_ptr(offset, "offset")) || (rc = check_ptr(y0, "y0")) ||
+      (rc = check_ptr(x0, "x0")) || (rc = check_ptr(w4, "w4")))
+    return rc;
+  return launch_corners(g, (const float*)offset, y0, x0, w4, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+"""Tensor-level entry points: torch tensors in, raw device pointers across the C ABI.
+
+PyTorch is used for device memory, streams and autograd plumbing only; all arithmetic of
+the operator happens in libdcn_b200.so.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (FLAG_ACCUM_GRAD_X, FLAG_FORCE_SIMT, FLAG_NO_GRAD_X, OPERAND_BF16, OPERAND_FP32,
+                   PHASE_BACKWARD, PHASE_FORWARD, VARIANT_JITTOR, VARIANT_TORCH)
+
+_workspaces = {}
+
+
+def _workspace(device, stream_id, nbytes):
+    """Caller-owned scratch, one growing buffer per (device, stream)."""
+    key = (device.index, stream_id)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _dev_ready(t, dtype=torch.float32):
+    """Dense, 16-byte aligned tensor of the wanted dtype on its current CUDA device."""
+    if t is None:
+        return None
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _compute_device(x):
+    if x.is_cuda:
+        return x.device
+    if not torch.cuda.is_available():
+        raise _lib.DcnError("jittor_dcn_b200 needs a CUDA device (B200, sm_100a): there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_device(t, dev):
+    """Host tensors are staged through pinned memory (the reference feeds CPU tensors,
+    train.py:239); CUDA tensors are used in place."""
+    if t is None or t.device == dev:
+        return t
+    if t.device.type == "cpu":
+        t = t.detach().contiguous()
+        try:
+            t = t.pin_memory()
+        except RuntimeError:
+            pass
+        return t.to(dev, non_blocking=True)
+    return t.to(dev)
+
+
+def _shape_of(x, weight, kernel_size, stride, padding, variant, operand, flags):
+    B, C, H, W = x.shape
+    O = weight.shape[0]
+    return _lib.make_shape(B, C, O, H, W, kernel_size, stride, padding, variant, operand, flags)
+
+
+def dcn_forward(x, offset, weight, bias, kernel_size=3, stride=1, padding=1, variant=VARIANT_TORCH,
+                operand=OPERAND_FP32, flags=0):
+    """out[B,O,Ho,Wo] = engine forward on CUDA tensors (no autograd)."""
+    lib = _lib.load()
+    shp = _shape_of(x, weight, kernel_size, stride, padding, variant, operand, flags)
+    Ho, Wo = _lib.output_hw(shp)
+    N = shp.kh * shp.kw
+    if tuple(offset.shape) != (shp.B, 2 * N, Ho, Wo):
+        raise ValueError(f"offset shape {tuple(offset.shape)} != {(shp.B, 2 * N, Ho, Wo)}")
+    if tuple(weight.shape) != (shp.O, shp.C, shp.kh, shp.kw):
+        raise ValueError(f"weight shape {tuple(weight.shape)} != {(shp.O, shp.C, shp.kh, shp.kw)}")
+    act = torch.bfloat16 if operand == OPERAND_BF16 else torch.float32
+    x, weight = _dev_ready(x, act), _dev_ready(weight, act)
+    offset, bias = _dev_ready(offset), _dev_ready(bias)
+    out = torch.empty((shp.B, shp.O, Ho, Wo), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream(x.device)
+        need = lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_FORWARD)
+        ws = _workspace(x.device, stream.cuda_stream, need)
+        rc = lib.dcn_forward(ctypes.byref(shp), _ptr(x), _ptr(offset), _ptr(weight), _ptr(bias),
+                             _ptr(out), _ptr(ws), ws.numel(), ctypes.c_void_p(stream.cuda_stream))
+    _lib.check(rc, "dcn_forward")
+    return out
+
+
+def dcn_backward(x, offset, weight, grad_out, has_bias, kernel_size=3, stride=1, padding=1,
+                 variant=VARIANT_TORCH, operand=OPERAND_FP32, flags=0, need_grad_x=True):
+    """-> grad_x (or None), grad_offset, grad_weight, grad_bias (or None); all float32."""
+    lib = _lib.load()
+    if not need_grad_x:
+        flags |= FLAG_NO_GRAD_X
+    shp = _shape_of(x, weight, kernel_size, stride, padding, variant, operand, flags)
+    Ho, Wo = _lib.output_hw(shp)
+    N = shp.kh * shp.kw
+    act = torch.bfloat16 if operand == OPERAND_BF16 else torch.float32
+    x, weight, grad_out = _dev_ready(x, act), _dev_ready(weight, act), _dev_ready(grad_out, act)
+    offset = _dev_ready(offset)
+    dev = x.device
+    gx = torch.empty(x.shape, dtype=torch.float32, device=dev) if need_grad_x else None
+    goff = torch.empty((shp.B, 2 * N, Ho, Wo), dtype=torch.float32, device=dev)
+    gw = torch.empty(weight.shape, dtype=torch.float32, device=dev)
+    gb = torch.empty((shp.O,), dtype=torch.float32, device=dev) if has_bias else None
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        need = lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_BACKWARD)
+        ws = _workspace(dev, stream.cuda_stream, need)
+        rc = lib.dcn_backward(ctypes.byref(shp), _ptr(x), _ptr(offset), _ptr(weight), _ptr(grad_out),
+                              _ptr(gx), _ptr(goff), _ptr(gw), _ptr(gb), _ptr(ws), ws.numel(),
+                              ctypes.c_void_p(stream.cuda_stream))
+    _lib.check(rc, "dcn_backward")
+    return gx, goff, gw, gb
+
+
+def dcn_corners(offset, in_hw, kernel_size=3, stride=1, padding=1, variant=VARIANT_TORCH):
+    """Sampling geometry only: y0, x0 [B,N,Ho,Wo] int32 and w4 [B,N,Ho,Wo,4] float32."""
+    lib = _lib.load()
+    B = offset.shape[0]
+    shp = _lib.make_shape(B, 1, 1, in_hw[0], in_hw[1], kernel_size, stride, padding, variant)
+    Ho, Wo = _lib.output_hw(shp)
+    N = shp.kh * shp.kw
+    offset = _dev_ready(offset)
+    dev = offset.device
+    y0 = torch.empty((B, N, Ho, Wo), dtype=torch.int32, device=dev)
+    x0 = torch.empty_like(y0)
+    w4 = torch.empty((B, N, Ho, Wo, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        rc = lib.dcn_debug_corners(ctypes.byref(shp), _ptr(offset), _ptr(y0), _ptr(x0), _ptr(w4),
+                                   ctypes.c_void_p(stream.cuda_stream))
+    _lib.check(rc, "dcn_debug_corners")
+    return y0, x0, w4
+
+
+class DeformConvFunction(torch.autograd.Function):
+    """autograd node standing where the reference has grid_sample + matmul + their autograd
+    (train.py:102-140 forward, train.py:249 backward)."""
+
+    @staticmethod
+    def forward(ctx, x, offset, weight, bias, cfg):
+        kernel_size, stride, padding, variant, operand, flags = cfg
+        home = x.device
+        dev = _compute_device(x)
+        xd, od, wd = _to_device(x, dev), _to_device(offset, dev), _to_device(weight, dev)
+        bd = _to_device(bias, dev)
+        out = dcn_forward(xd, od, wd, bd, kernel_size, stride, padding, variant, operand, flags)
+        ctx.save_for_backward(xd, od, wd)
+        ctx.cfg, ctx.home, ctx.has_bias = cfg, home, bias is not None
+        ctx.dtypes = (x.dtype, offset.dtype, weight.dtype)
+        return out if home == dev else out.to(home)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xd, od, wd = ctx.saved_tensors
+        kernel_size, stride, padding, variant, operand, flags = ctx.cfg
+        dev = xd.device
+        gx, goff, gw, gb = dcn_backward(xd, od, wd, _to_device(grad_out, dev), ctx.has_bias,
+                                        kernel_size, stride, padding, variant, operand, flags,
+                                        need_grad_x=ctx.needs_input_grad[0])
+        home = ctx.home
+
+        def back(t, dtype):
+            if t is None:
+                return None
+            t = t.to(dtype) if t.dtype != dtype else t
+            return t if home == dev else t.to(home)
+
+        return (back(gx, ctx.dtypes[0]), back(goff, ctx.dtypes[1]), back(gw, ctx.dtypes[2]),
+                back(gb, torch.float32), None)
+
+
+def deform_conv2d(x, offset, weight, bias=None, kernel_size=3, stride=1, padding=1,
+                  variant=VARIANT_TORCH, operand=OPERAND_FP32, flags=0):
+    """Differentiable DeformConv2d core: everything after the offset conv."""
+    cfg = (_lib._pair(kernel_size), _lib._pair(stride), _lib._pair(padding), variant, operand, flags)
+    return DeformConvFunction.apply(x, offset, weight, bias, cfg)

@@ -1,0 +1,57 @@
+"""`TorchDeformConv2d` — drop-in for the class of the same name in the reference's train.py:70-140.
+
+Same constructor, attributes, parameter names/shapes (state_dict compatible:
+``weight``, ``bias``, ``offset_conv.weight``, ``offset_conv.bias``) and initialisation
+(train.py:87-93).  ``forward`` keeps the companion offset convolution as a framework conv
+(train.py:98) and hands everything after it (train.py:102-140 and its autograd) to the
+B200 engine.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .functional import deform_conv2d
+
+
+class TorchDeformConv2d(nn.Module):
+    variant = _lib.VARIANT_TORCH
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, bias=True):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size if isinstance(kernel_size, tuple) else (kernel_size, kernel_size)
+        self.stride = stride if isinstance(stride, tuple) else (stride, stride)
+        self.padding = padding if isinstance(padding, tuple) else (padding, padding)
+        self.N = self.kernel_size[0] * self.kernel_size[1]
+        self.operand = _lib.OPERAND_FP32
+        self.engine_flags = 0
+
+        # companion offset conv: C -> 2N, same k/s/p (train.py:80-85)
+        self.offset_conv = nn.Conv2d(in_channels, 2 * self.N, kernel_size=self.kernel_size,
+                                     stride=self.stride, padding=self.padding)
+        # He-style normal init of the main weight, zero bias (train.py:87-90)
+        std = math.sqrt(2.0 / (in_channels * self.kernel_size[0] * self.kernel_size[1]))
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels, *self.kernel_size))
+        nn.init.normal_(self.weight, mean=0.0, std=std)
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+        # offsets start at zero (train.py:92-93)
+        nn.init.zeros_(self.offset_conv.weight)
+        nn.init.zeros_(self.offset_conv.bias)
+
+    def forward(self, x):
+        offset = self.offset_conv(x)
+        return deform_conv2d(x, offset, self.weight, self.bias, self.kernel_size, self.stride,
+                             self.padding, self.variant, self.operand, self.engine_flags)
+
+    def extra_repr(self):
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, "
+                f"stride={self.stride}, padding={self.padding}, bias={self.bias is not None}")
+
+
+class TorchDeformConv2dJittorSemantics(TorchDeformConv2d):
+    """PyTorch-hosted module with the Jittor operator's semantics (deform_conv.py:56-81):
+    normalisation by the OUTPUT extent and (n, c)-ordered columns."""
+    variant = _lib.VARIANT_JITTOR

@@ -1,0 +1,107 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports exactly the
+symbols include/dcn_b200.h declares, and rejects bad arguments before touching a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import jittor_dcn_b200 as dcn
+from jittor_dcn_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "dcn_b200.h")).read()
+    return sorted(set(re.findall(r"DCN_API[^;(]*?\b(dcn_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_list_the_same_symbols():
+    assert _declared() == sorted(_lib.EXPORTS)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = dcn.load()
+    for name in _declared():
+        assert hasattr(lib, name), name
+    assert lib.dcn_version() == 100
+
+
+def test_shape_struct_matches_header():
+    text = open(os.path.join(ROOT, "include", "dcn_b200.h")).read()
+    body = re.search(r"typedef struct DcnShape \{(.*?)\} DcnShape;", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n.strip() for decl in re.findall(r"int32_t ([^;]+);", body) for n in decl.split(",")]
+    assert names == [f[0] for f in _lib.DcnShape._fields_]
+    assert ctypes.sizeof(_lib.DcnShape) == 4 * len(names)
+
+
+def test_output_extent_follows_the_offset_conv():
+    # deform_conv.py:34-35
+    for (H, W, k, s, p), exp in [((128, 128, 3, 2, 1), (64, 64)), ((17, 23, 3, 1, 1), (17, 23)),
+                                 ((20, 28, 3, 2, 1), (10, 14)), ((9, 11, (1, 3), 1, (0, 1)), (9, 11)),
+                                 ((6, 6, 1, 1, 0), (6, 6))]:
+        assert _lib.output_hw(dcn.make_shape(1, 2, 3, H, W, k, s, p)) == exp
+
+
+def test_bad_shapes_are_rejected_without_a_gpu():
+    lib = dcn.load()
+    bad = [dcn.make_shape(0, 4, 8, 10, 10), dcn.make_shape(1, 4, 8, 1, 10, 3, 1, 0),
+           dcn.make_shape(1, 4, 8, 10, 10, 3, 0, 1), dcn.make_shape(1, 4, 8, 10, 10, variant=7),
+           dcn.make_shape(4, 4096, 8, 1024, 1024)]
+    for s in bad:
+        assert lib.dcn_workspace_bytes(ctypes.byref(s), 0) == 0
+        assert lib.dcn_output_hw(ctypes.byref(s), None, None) == -1
+        assert b"bad shape" in lib.dcn_last_error()
+
+
+def test_null_and_misaligned_pointers_are_rejected_without_a_gpu():
+    lib = dcn.load()
+    s = dcn.make_shape(1, 4, 8, 10, 10)
+    buf = ctypes.create_string_buffer(1 << 16)
+    base = (ctypes.addressof(buf) + 255) // 256 * 256
+    ok = ctypes.c_void_p(base)
+    rc = lib.dcn_forward(ctypes.byref(s), None, ok, ok, None, ok, ok, 1 << 15, None)
+    assert rc == -2 and b"x is NULL" in lib.dcn_last_error()
+    rc = lib.dcn_forward(ctypes.byref(s), ok, ctypes.c_void_p(base + 4), ok, None, ok, ok, 1 << 15, None)
+    assert rc == -3 and b"offset" in lib.dcn_last_error()
+    rc = lib.dcn_forward(ctypes.byref(s), ok, ok, ok, None, ok, ok, 16, None)
+    assert rc == -4 and b"workspace" in lib.dcn_last_error()
+    rc = lib.dcn_backward(ctypes.byref(s), ok, ok, ok, ok, None, ok, ok, None, ok, 1 << 15, None)
+    assert rc == -2 and b"grad_x" in lib.dcn_last_error()
+    assert lib.dcn_status_string(-4) == b"workspace too small"
+
+
+def test_module_keeps_the_reference_interface():
+    """ctor signature, attributes, parameter names/shapes and init of train.py:70-93."""
+    m = dcn.TorchDeformConv2d(16, 32, 3, 2, 1)
+    assert (m.in_channels, m.out_channels, m.kernel_size, m.stride, m.padding, m.N) == \
+        (16, 32, (3, 3), (2, 2), (1, 1), 9)
+    sd = m.state_dict()
+    assert list(sd) == ["weight", "bias", "offset_conv.weight", "offset_conv.bias"]
+    assert tuple(sd["weight"].shape) == (32, 16, 3, 3) and tuple(sd["bias"].shape) == (32,)
+    assert tuple(sd["offset_conv.weight"].shape) == (18, 16, 3, 3)
+    assert float(sd["offset_conv.weight"].abs().max()) == 0.0 and float(sd["bias"].abs().max()) == 0.0
+    std = float(sd["weight"].std())
+    assert abs(std - (2.0 / (16 * 9)) ** 0.5) < 0.02
+    m2 = dcn.TorchDeformConv2d(4, 8, (1, 3), (1, 1), (0, 1), bias=False)
+    assert m2.bias is None and m2.N == 3 and list(m2.state_dict()) == ["weight", "offset_conv.weight", "offset_conv.bias"]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = dcn.TorchDeformConv2d(2, 2)
+    with pytest.raises(dcn.DcnError):
+        m(torch.zeros(1, 2, 4, 4))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "jittor_dcn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no CPU fallback", ""), os.path.join(dirpath, f)

@@ -1,0 +1,200 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI (ctypes), against
+  (1) the committed golden vectors made by the UNMODIFIED reference (tests/golden/), and
+  (2) the CPU oracle (oracle/dcn_oracle.c) on seeded inputs.
+Tolerances are north_star's: sampling indices / corner weights bit-exact; forward 1e-4
+relative; input / offset / weight gradients 1e-3 relative (max-abs error over max-abs value).
+"""
+import numpy as np
+import pytest
+import torch
+
+import jittor_dcn_b200 as dcn
+from oracle import dcn_oracle as orc
+from tests.util import golden, golden_names, rel_err, shape_from_cfg
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-4
+GRAD_TOL = 1e-3
+FLAG_SETS = [0, dcn.FLAG_FORCE_SIMT]
+
+
+def _cuda(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def _ksp(cfg):
+    B, C, O, H, W, kh, kw, sh, sw, ph, pw = (int(v) for v in cfg)
+    return (kh, kw), (sh, sw), (ph, pw)
+
+
+def _engine(g, variant, flags):
+    k, s, p = _ksp(g["cfg"])
+    x, off, w, gout = (_cuda(g[n]) for n in ("x", "off", "weight", "gout"))
+    b = _cuda(g["bias"]) if "bias" in g else None
+    out = dcn.dcn_forward(x, off, w, b, k, s, p, variant, flags=flags)
+    gx, goff, gw, gb = dcn.dcn_backward(x, off, w, gout, b is not None, k, s, p, variant, flags=flags)
+    torch.cuda.synchronize()
+    return out, gx, goff, gw, gb
+
+
+@pytest.mark.parametrize("name", golden_names("stencil_"))
+@pytest.mark.parametrize("variant", [dcn.VARIANT_TORCH, dcn.VARIANT_JITTOR])
+def test_corners_bit_exact(name, variant):
+    g = golden(name)
+    s = shape_from_cfg(g["cfg"], variant)
+    k, st, p = _ksp(g["cfg"])
+    y0, x0, w4, _ = orc.corners(s, g["off"])
+    gy0, gx0, gw4 = dcn.dcn_corners(_cuda(g["off"]), (s.H, s.W), k, st, p, variant)
+    assert np.array_equal(gy0.cpu().numpy(), y0)
+    assert np.array_equal(gx0.cpu().numpy(), x0)
+    assert np.array_equal(gw4.cpu().numpy().view(np.uint32), w4.view(np.uint32))
+
+
+@pytest.mark.parametrize("S", [128, 64, 56, 32, 28, 14])
+def test_zero_offset_wobble_bit_exact(S):
+    """The float32 normalise/un-normalise round trip against the reference run."""
+    g = golden(f"wobble_{S}")
+    off = torch.zeros(1, 18, S, S, device="cuda")
+    y0, x0, w4 = (t.cpu().numpy() for t in dcn.dcn_corners(off, (S, S), 3, 1, 1, dcn.VARIANT_TORCH))
+    for probe, idx, ww, hi_k in (("rows", y0[0, 0, 0, :], w4[0, 0, 0, :, :], 2),
+                                 ("cols", x0[0, 0, :, 0], w4[0, 0, :, 0, :], 1)):
+        exp = np.zeros((S, S), np.float32)
+        for t in range(S):
+            if 0 <= idx[t] < S:
+                exp[t, idx[t]] = ww[t, 0]
+            if 0 <= idx[t] + 1 < S:
+                exp[t, idx[t] + 1] = ww[t, hi_k]
+        assert np.array_equal(exp, g[probe]), probe
+
+
+@pytest.mark.parametrize("shape", [(3, 128, 128, 3, 2, 1), (2, 28, 28, 3, 1, 1), (2, 56, 40, 3, 1, 1),
+                                   (1, 16, 16, (5, 3), 2, (2, 1))])
+@pytest.mark.parametrize("variant", [dcn.VARIANT_TORCH, dcn.VARIANT_JITTOR])
+def test_corners_bit_exact_random_offsets(shape, variant):
+    B, H, W, k, s, p = shape
+    rng = np.random.default_rng(7)
+    sh = orc.make_shape(B, 1, 1, H, W, k, s, p, variant)
+    Ho, Wo = orc.out_hw(sh)
+    off = (rng.standard_normal((B, 2 * sh.kh * sh.kw, Ho, Wo)) * 3).astype(np.float32)
+    off[0, :, :, 0] = 0
+    off.reshape(-1)[::97] *= 1e3     # far out of range
+    off.reshape(-1)[5::1013] = np.inf
+    y0, x0, w4, _ = orc.corners(sh, off)
+    gy0, gx0, gw4 = dcn.dcn_corners(_cuda(off), (H, W), k, s, p, variant)
+    assert np.array_equal(gy0.cpu().numpy(), y0)
+    assert np.array_equal(gx0.cpu().numpy(), x0)
+    a, b = gw4.cpu().numpy(), w4
+    both_nan = np.isnan(a) & np.isnan(b)
+    assert np.array_equal(a.view(np.uint32)[~both_nan], b.view(np.uint32)[~both_nan])
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS)
+@pytest.mark.parametrize("name", golden_names("layer_"))
+def test_layer_against_reference_golden(name, flags):
+    """Forward and all four gradients against the unmodified reference's own outputs."""
+    g = golden(name)
+    out, gx, goff, gw, gb = _engine(g, dcn.VARIANT_TORCH, flags)
+    assert rel_err(out.cpu().numpy(), g["out"]) < FWD_TOL
+    assert rel_err(gx.cpu().numpy(), g["gx"]) < GRAD_TOL
+    assert rel_err(goff.cpu().numpy(), g["goff"]) < GRAD_TOL
+    assert rel_err(gw.cpu().numpy(), g["gw"]) < GRAD_TOL
+    if "gb" in g:
+        assert rel_err(gb.cpu().numpy(), g["gb"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS)
+@pytest.mark.parametrize("name", golden_names("jittor_"))
+def test_layer_jittor_variant_against_transliteration(name, flags):
+    g = golden(name)
+    s = shape_from_cfg(g["cfg"], orc.VARIANT_JITTOR)
+    if min(orc.out_hw(s)) == 1:
+        pytest.skip("H_out or W_out == 1: the reference divides by zero (deform_conv.py:37-38)")
+    out, gx, goff, gw, gb = _engine(g, dcn.VARIANT_JITTOR, flags)
+    assert rel_err(out.cpu().numpy(), g["out"]) < FWD_TOL
+    assert rel_err(gx.cpu().numpy(), g["gx"]) < GRAD_TOL
+    assert rel_err(goff.cpu().numpy(), g["goff"]) < GRAD_TOL
+    assert rel_err(gw.cpu().numpy(), g["gw"]) < GRAD_TOL
+
+
+ORACLE_CASES = [
+    # B  C    O    H   W   k  s  p  sigma
+    (2, 16,  32,  32, 32, 3, 2, 1, 1.0),     # detector conv2-like (small)
+    (2, 64,  64,  16, 16, 3, 1, 1, 2.0),     # cfg2 channel counts
+    (1, 128, 128, 14, 14, 3, 1, 1, 1.0),     # C > Ho*Wo: GEMM rows straddle channels
+    (2, 32,  64,  16, 16, 3, 2, 1, 0.0),     # zero offsets
+    (1, 256, 256, 7,  7,  3, 1, 1, 1.5),     # cfg3 channel counts
+    (3, 5,   7,   9,  13, 3, 1, 1, 1.0),     # nothing aligned
+    (2, 64,  128, 12, 20, 3, 1, 1, 4.0),     # non-square, many out-of-bounds taps
+]
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS)
+@pytest.mark.parametrize("variant", [dcn.VARIANT_TORCH, dcn.VARIANT_JITTOR])
+@pytest.mark.parametrize("case", ORACLE_CASES)
+def test_forward_backward_against_oracle(case, variant, flags):
+    B, C, O, H, W, k, s, p, sigma = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    sh = orc.make_shape(B, C, O, H, W, k, s, p, variant)
+    Ho, Wo = orc.out_hw(sh)
+    N = sh.kh * sh.kw
+    g = dict(cfg=np.array([B, C, O, H, W, sh.kh, sh.kw, sh.sh, sh.sw, sh.ph, sh.pw]),
+             x=rng.standard_normal((B, C, H, W)).astype(np.float32),
+             off=(rng.standard_normal((B, 2 * N, Ho, Wo)) * sigma).astype(np.float32),
+             weight=(rng.standard_normal((O, C, sh.kh, sh.kw)) * (2.0 / (C * N)) ** 0.5).astype(np.float32),
+             bias=rng.standard_normal(O).astype(np.float32),
+             gout=rng.standard_normal((B, O, Ho, Wo)).astype(np.float32))
+    ref_out = orc.forward(sh, g["x"], g["off"], g["weight"], g["bias"])
+    ref = orc.backward(sh, g["x"], g["off"], g["weight"], g["gout"])
+    out, gx, goff, gw, gb = _engine(g, variant, flags)
+    assert rel_err(out.cpu().numpy(), ref_out) < FWD_TOL
+    for got, exp, nm in zip((gx, goff, gw, gb), ref, ("gx", "goff", "gw", "gb")):
+        assert rel_err(got.cpu().numpy(), exp) < GRAD_TOL, nm
+
+
+def test_module_with_live_offset_conv_matches_reference():
+    """state_dict of the reference module in, same output and parameter gradients out."""
+    g = golden("module_live_offsets")
+    m = dcn.TorchDeformConv2d(8, 16, 3, 2, 1).cuda()
+    m.load_state_dict({k[3:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("sd.")})
+    x = _cuda(g["x"]).requires_grad_(True)
+    out = m(x)
+    out.backward(_cuda(g["gout"]))
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < FWD_TOL
+    assert rel_err(x.grad.cpu().numpy(), g["gx"]) < GRAD_TOL
+    for name, prm in m.named_parameters():
+        assert rel_err(prm.grad.cpu().numpy(), g["grad." + name]) < GRAD_TOL, name
+
+
+def test_host_tensors_drop_in():
+    """The reference feeds CPU tensors (train.py:239): the module must accept them."""
+    g = golden("module_live_offsets")
+    m = dcn.TorchDeformConv2d(8, 16, 3, 2, 1)
+    m.load_state_dict({k[3:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("sd.")})
+    x = torch.as_tensor(g["x"]).requires_grad_(True)
+    out = m(x)
+    assert out.device.type == "cpu"
+    out.backward(torch.as_tensor(g["gout"]))
+    assert rel_err(out.detach().numpy(), g["out"]) < FWD_TOL
+    assert rel_err(x.grad.numpy(), g["gx"]) < GRAD_TOL
+    assert rel_err(m.weight.grad.numpy(), g["grad.weight"]) < GRAD_TOL
+
+
+def test_flags_accumulate_and_skip_grad_x():
+    g = golden("layer_a_s1")
+    k, s, p = _ksp(g["cfg"])
+    x, off, w, gout = (_cuda(g[n]) for n in ("x", "off", "weight", "gout"))
+    gx, goff, gw, gb = dcn.dcn_backward(x, off, w, gout, True, k, s, p)
+    gx2, goff2, gw2, _ = dcn.dcn_backward(x, off, w, gout, False, k, s, p, need_grad_x=False)
+    assert gx2 is None
+    assert rel_err(goff2.cpu().numpy(), goff.cpu().numpy()) < 1e-5
+    assert rel_err(gw2.cpu().numpy(), gw.cpu().numpy()) < 1e-5
+
+
+def test_error_path_reports_small_workspace():
+    import ctypes
+    lib = dcn.load()
+    s = dcn.make_shape(1, 4, 8, 10, 10)
+    t = torch.zeros(4096, device="cuda")
+    p = ctypes.c_void_p(t.data_ptr())
+    assert lib.dcn_forward(ctypes.byref(s), p, p, p, None, p, p, 16, None) == -4
