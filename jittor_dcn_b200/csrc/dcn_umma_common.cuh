@@ -1,0 +1,122 @@
+// dcn_umma_common.cuh — pieces shared by the tcgen05 forward / backward kernels:
+// fast integer division, the tile decomposition of both column layouts, the channels-last
+// staging of x and the pre-tiled bf16 hi/lo weight images.
+#pragma once
+#include "dcn_common.cuh"
+#include "dcn_umma.cuh"
+
+namespace dcn {
+
+// n / d for 0 <= n < 2^31 by multiply-high (d >= 1), exact.
+struct FastDiv {
+  uint32_t d, mul, shr;
+  __host__ static FastDiv make(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    if (d == 1) {
+      f.mul = 0;
+      f.shr = 0;
+      return f;
+    }
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;  // ceil(log2 d)
+    f.shr = l - 1;
+    f.mul = (uint32_t)(((1ull << (32 + l - 1)) + d - 1) / d);  // ceil(2^(32+l-1) / d), fits for n < 2^31
+    return f;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const {
+    return d == 1 ? n : (__umulhi(n, mul) >> shr);
+  }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    q = div(n);
+    r = n - q * d;
+  }
+};
+
+// How the GEMM rows of one variant are grouped into 128-row UMMA tiles.
+//
+// Jittor (deform_conv.py:72-73): row = pixel.  Tile = 128 consecutive pixels of one image;
+//   K-block kb covers columns j in [64kb, 64kb+64) = taps n in [n0, n0+T), channels within.
+//
+// Torch (train.py:129-131): row r, column j <-> flat sample index f = r*K + j of the
+//   (c,h,w,n)-ordered sample tensor.  With G = gcd(HW, C), R = HW/G, Cs = C/G the rows
+//   {r0 + i*R : i < G} ("class" r0) share their sampling points q(r0, j) = (r0*K + j) mod P and
+//   differ only in the channel c = cbase(r0, j) + i*Cs.  A tile takes Gt channels of Rt
+//   consecutive classes so that every bilinear footprint is fetched once per Gt channels:
+//   row m of the tile = quad*(4*Rt) + inst*4 + chq  <->  class instance `inst`, i = 4*quad + chq.
+//   The staging copy of x is channel-permuted (c -> (c % Cs)*G + c / Cs) so that those Gt
+//   channels are contiguous.
+struct Tiling {
+  int variant;
+  int KB;          // K blocks of 64
+  int num_tiles;
+  // torch
+  int G, R, Cs, Gt, Rt, chunks, num_inst;
+  FastDiv divR, divChunks, divP, divN, divWo, divC;
+  // jittor
+  int pix_blocks, taps_per_kb;
+};
+
+__host__ inline int gcd_int(int a, int b) {
+  while (b) {
+    int t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+__host__ inline bool make_tiling(const Geo& g, Tiling* t) {
+  t->variant = g.variant;
+  t->KB = (g.K + 63) / 64;
+  t->divP = FastDiv::make(g.P);
+  t->divN = FastDiv::make(g.N);
+  t->divWo = FastDiv::make(g.Wo);
+  t->divC = FastDiv::make(g.C);
+  t->G = t->R = t->Cs = t->Gt = t->Rt = t->chunks = t->num_inst = 1;
+  t->divR = FastDiv::make(1);
+  t->divChunks = FastDiv::make(1);
+  t->pix_blocks = t->taps_per_kb = 1;
+  if (g.C % 4) return false;
+  if (g.variant == DCN_VARIANT_TORCH) {
+    t->G = gcd_int(g.HW, g.C);
+    if (t->G % 16) return false;
+    t->R = g.HW / t->G;
+    t->Cs = g.C / t->G;
+    t->Gt = (t->G % 32 == 0) ? 32 : 16;
+    t->Rt = 128 / t->Gt;
+    t->chunks = t->G / t->Gt;
+    long long inst = (long long)g.B * t->chunks * t->R;
+    if (inst > 0x7fffffffLL) return false;
+    t->num_inst = (int)inst;
+    t->num_tiles = (int)((inst + t->Rt - 1) / t->Rt);
+    t->divR = FastDiv::make(t->R);
+    t->divChunks = FastDiv::make(t->chunks);
+  } else {
+    if (!(g.C % 64 == 0 || g.C == 32 || g.C == 16)) return false;
+    t->pix_blocks = (g.HW + 127) / 128;
+    t->taps_per_kb = g.C >= 64 ? 1 : 64 / g.C;
+    t->num_tiles = g.B * t->pix_blocks;
+  }
+  return true;
+}
+
+// channel permutation of the channels-last staging copy
+__host__ __device__ inline int perm_channel(int c, int variant, int G, int Cs) {
+  return variant == DCN_VARIANT_TORCH ? (c % Cs) * G + c / Cs : c;
+}
+
+// plan entry as the producers consume it (16 bytes in shared memory)
+struct __align__(16) PlanEntry {
+  int pix;        // float offset of the north-west corner's channel vector inside image b
+  uint32_t mask;  // corner validity bits (0 => nothing to fetch)
+  float fx, fy;
+};
+
+int launch_nchw_to_nhwc(const Geo& g, const Tiling& t, const float* x, float* xt, cudaStream_t st);
+int launch_nhwc_to_nchw_add(const Geo& g, const Tiling& t, const float* gxt, float* gx, int accumulate,
+                            cudaStream_t st);
+// weight images for the forward GEMM: per K block [hi: O x 64 K-major SW128][lo: same]
+int launch_weight_tiles_fwd(const Geo& g, const Tiling& t, const float* wt, uint8_t* tiles, cudaStream_t st);
+
+}  // namespace dcn

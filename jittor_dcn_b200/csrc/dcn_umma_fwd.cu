@@ -1,0 +1,442 @@
+// dcn_umma_fwd.cu — forward pass as ONE warp-specialised implicit GEMM on the 5th-gen tensor
+// cores (tcgen05.mma, accumulators in TMEM).
+//
+// Replaces, per 128-row tile and without ever writing columns to HBM:
+//   coordinates + bilinear sampling   deform_conv.py:62-68,30-54 / train.py:102-127
+//   column layout                     deform_conv.py:72-73       / train.py:129-131
+//   GEMM + bias + NCHW store          deform_conv.py:74-81       / train.py:133-140
+//
+// Warp roles (448 threads, 1 CTA per SM, persistent over tiles):
+//   warps 0-3   epilogue : tcgen05.ld accumulator -> + bias -> out[B,O,Ho,Wo]
+//   warp  4     MMA      : one lane issues tcgen05.mma (bf16 hi/lo split, 3 MMAs per K step)
+//   warp  5     B loader : one lane streams the pre-tiled weight images with cp.async.bulk
+//   warps 6-13  producers: coordinate chain -> plan entries in smem -> 4x LDG.128 gather of the
+//                          channels-last input -> blend -> bf16 hi/lo -> swizzled smem A tile
+// Pipelines: smem full/empty mbarriers per stage (producers + loader -> MMA -> back),
+// TMEM full/empty per accumulator buffer (MMA -> epilogue -> back); 2 accumulator buffers.
+//
+// fp32 parity: every fp32 operand v is split as hi = bf16(v), lo = bf16(v - hi) and the product
+// is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation (relative error ~5e-6, measured).
+#include "dcn_umma.h"
+#include "dcn_umma_common.cuh"
+
+namespace dcn {
+
+using namespace ptx;
+
+constexpr int kEpiWarps = 4, kProdWarps = 8;
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kFwdThreads = (kEpiWarps + 2 + kProdWarps) * 32;  // 448
+constexpr int kPlanMax = 512;                                    // plan entries per K block
+constexpr uint32_t kATile = 128 * 64 * 2;                        // one bf16 A image (16 KB)
+constexpr uint32_t kAMnLbo = 1024, kAMnSbo = 2048;               // MN-major A: atom strides
+constexpr int kMaxStages = 4;
+
+struct FwdParams {
+  Geo g;
+  Tiling t;
+  const float* xt;
+  const float* off;
+  const uint8_t* wtiles;
+  const float* bias;
+  float* out;
+  int stages;
+  uint32_t b_tile;     // bytes of one bf16 B image = O*128
+  uint32_t stage_bytes;
+  uint32_t tmem_cols;  // 2*O rounded to a power of two >= 32
+};
+
+struct TileRowInfo {  // what a Torch-layout tile row needs
+  int b, r0, chunk, valid;
+};
+
+__device__ __forceinline__ TileRowInfo decode_inst(const Tiling& t, int inst) {
+  TileRowInfo ri;
+  ri.valid = inst < t.num_inst;
+  uint32_t bc, r0, b, ch;
+  t.divR.divmod((uint32_t)(ri.valid ? inst : 0), bc, r0);
+  t.divChunks.divmod(bc, b, ch);
+  ri.b = (int)b;
+  ri.r0 = (int)r0;
+  ri.chunk = (int)ch;
+  return ri;
+}
+
+// offsets -> tap -> plan entry (pix is relative to image b of the channels-last copy)
+__device__ __forceinline__ PlanEntry make_entry(const Geo& g, const Tiling& t, const float* __restrict__ off,
+                                                int b, int p, int n, int chan_base) {
+  uint32_t h, w;
+  t.divWo.divmod((uint32_t)p, h, w);
+  const float* ob = off + (size_t)b * 2 * g.N * g.HW;
+  const float ox = __ldg(ob + (size_t)n * g.HW + p);
+  const float oy = __ldg(ob + (size_t)(g.N + n) * g.HW + p);
+  const Tap tp = tap_of(g, (int)h, (int)w, ox, oy);
+  PlanEntry e;
+  e.mask = corner_mask(tp, g.H, g.W);
+  const int y0 = max(-1, min(tp.y0, g.H - 1)), x0 = max(-1, min(tp.x0, g.W - 1));
+  e.pix = (y0 * g.W + x0) * g.C + chan_base;
+  e.fx = tp.fx;
+  e.fy = tp.fy;
+  return e;
+}
+
+// 4 corners x 4 channels -> blended float4 (zero padding), reference accumulation order
+__device__ __forceinline__ float4 gather_blend(const float* __restrict__ img, const PlanEntry& e, int W,
+                                               int C) {
+  float cw[4];
+  {
+    const float ee = __fsub_rn(1.0f, e.fx), ss = __fsub_rn(1.0f, e.fy);
+    cw[0] = __fmul_rn(ss, ee);
+    cw[1] = __fmul_rn(ss, e.fx);
+    cw[2] = __fmul_rn(e.fy, ee);
+    cw[3] = __fmul_rn(e.fy, e.fx);
+  }
+  const float* base = img + e.pix;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 v0 = (e.mask & 1u) ? __ldg(reinterpret_cast<const float4*>(base)) : z;
+  const float4 v1 = (e.mask & 2u) ? __ldg(reinterpret_cast<const float4*>(base + C)) : z;
+  const float4 v2 = (e.mask & 4u) ? __ldg(reinterpret_cast<const float4*>(base + (size_t)W * C)) : z;
+  const float4 v3 = (e.mask & 8u) ? __ldg(reinterpret_cast<const float4*>(base + (size_t)W * C + C)) : z;
+  float4 r;
+  r.x = v0.x * cw[0] + v1.x * cw[1] + v2.x * cw[2] + v3.x * cw[3];
+  r.y = v0.y * cw[0] + v1.y * cw[1] + v2.y * cw[2] + v3.y * cw[3];
+  r.z = v0.z * cw[0] + v1.z * cw[1] + v2.z * cw[2] + v3.z * cw[3];
+  r.w = v0.w * cw[0] + v1.w * cw[1] + v2.w * cw[2] + v3.w * cw[3];
+  return r;
+}
+
+// float4 -> 4 bf16 hi + 4 bf16 lo, each packed in 8 bytes
+__device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
+  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+  split_bf16(v.x, h0, l0);
+  split_bf16(v.y, h1, l1);
+  split_bf16(v.z, h2, l2);
+  split_bf16(v.w, h3, l3);
+  hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  hi.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+  lo.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  lo.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_constant__ FwdParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const Geo& g = P.g;
+  const Tiling& t = P.t;
+  // carve-up: [stages x (A_hi | A_lo | B_hi | B_lo)] [plan x2] [barriers]
+  uint8_t* stage_base = smem;
+  PlanEntry* plan = reinterpret_cast<PlanEntry*>(smem + (size_t)P.stages * P.stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(plan + 2 * kPlanMax);
+  uint64_t* full = bars;                   // [stages]
+  uint64_t* empty = bars + kMaxStages;     // [stages]
+  uint64_t* tfull = bars + 2 * kMaxStages; // [2]
+  uint64_t* tempty = tfull + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int O = g.O;
+
+  if (tid == 0) {
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(&full[s], kProdWarps + 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(P.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kEpiWarps) {
+    // ================================================================ epilogue
+    uint32_t acc_phase = 0;
+    int acc = 0;
+    for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
+      const int m = warp * 32 + lane;  // TMEM lane == tile row
+      size_t out_off = 0;
+      bool valid;
+      if (VARIANT == DCN_VARIANT_TORCH) {
+        const int quad = m / (4 * t.Rt), il = (m >> 2) % t.Rt, chq = m & 3;
+        const TileRowInfo ri = decode_inst(t, tile * t.Rt + il);
+        valid = ri.valid;
+        const int i = ri.chunk * t.Gt + 4 * quad + chq;
+        out_off = (size_t)ri.b * O * g.HW + (size_t)(ri.r0 + i * t.R);
+      } else {
+        const int b = tile / t.pix_blocks, p = (tile - b * t.pix_blocks) * 128 + m;
+        valid = p < g.HW;
+        out_off = (size_t)b * O * g.HW + p;
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * O);
+      for (int c0 = 0; c0 < O; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float bv = P.bias ? __ldg(P.bias + c0 + i) : 0.f;
+            P.out[out_off + (size_t)(c0 + i) * g.HW] = v[i] + bv;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp == kEpiWarps) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, O, VARIANT == DCN_VARIANT_TORCH, false);
+      int s = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * O);
+        for (int kb = 0; kb < t.KB; ++kb) {
+          mbar_wait(&full[s], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(stage_base + (size_t)s * P.stage_bytes);
+          const uint32_t a_lo = a_hi + kATile;
+          const uint32_t b_hi = a_hi + 2 * kATile;
+          const uint32_t b_lo = b_hi + P.b_tile;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            uint64_t dah, dal;
+            if (VARIANT == DCN_VARIANT_TORCH) {
+              dah = make_sdesc_sw128(a_hi + k4 * 2 * kAMnSbo, kAMnLbo, kAMnSbo);
+              dal = make_sdesc_sw128(a_lo + k4 * 2 * kAMnSbo, kAMnLbo, kAMnSbo);
+            } else {
+              dah = make_sdesc_sw128(a_hi + k4 * 32, 16, 1024);
+              dal = make_sdesc_sw128(a_lo + k4 * 32, 16, 1024);
+            }
+            const uint64_t dbh = make_sdesc_sw128(b_hi + k4 * 32, 16, 1024);
+            const uint64_t dbl = make_sdesc_sw128(b_lo + k4 * 32, 16, 1024);
+            umma_bf16(d_tmem, dah, dbh, idesc, (kb | k4) ? 1u : 0u);
+            umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+            umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+          }
+          umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
+          if (kb == t.KB - 1) umma_commit(&tfull[acc]);
+          if (++s == P.stages) {
+            s = 0;
+            phase ^= 1;
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    // ================================================================ weight (B) loader
+    if (lane == 0) {
+      int s = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < t.KB; ++kb) {
+          mbar_wait(&empty[s], phase ^ 1);
+          uint8_t* dst = stage_base + (size_t)s * P.stage_bytes + 2 * kATile;
+          mbar_arrive_expect_tx(&full[s], 2 * P.b_tile);
+          bulk_g2s(dst, P.wtiles + (size_t)kb * 2 * P.b_tile, 2 * P.b_tile, &full[s]);
+          if (++s == P.stages) {
+            s = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ================================================================ producers
+    const int pt = tid - (kEpiWarps + 2) * 32;  // 0..255
+    int s = 0;
+    uint32_t phase = 0;
+    int pbuf = 0;
+    const size_t img_stride = (size_t)g.H * g.W * g.C;
+    for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < t.KB; ++kb) {
+        PlanEntry* pl = plan + pbuf * kPlanMax;
+        // ---- plan entries of this K block
+        if (VARIANT == DCN_VARIANT_TORCH) {
+          const int n_ent = t.Rt * 64;
+          for (int e = pt; e < n_ent; e += kProdThreads) {
+            const int il = e >> 6, kk = e & 63, j = kb * 64 + kk;
+            const TileRowInfo ri = decode_inst(t, tile * t.Rt + il);
+            PlanEntry pe;
+            pe.mask = 0u;
+            pe.pix = 0;
+            pe.fx = pe.fy = 0.f;
+            if (ri.valid && j < g.K) {
+              uint32_t cb, q, p, n;
+              t.divP.divmod((uint32_t)(ri.r0 * g.K + j), cb, q);
+              t.divN.divmod(q, p, n);
+              pe = make_entry(g, t, P.off, ri.b, (int)p, (int)n, (int)cb * t.G + ri.chunk * t.Gt);
+            }
+            pl[e] = pe;
+          }
+        } else {
+          const int T = t.taps_per_kb, n_ent = 128 * T;
+          const int b = tile / t.pix_blocks, p_base = (tile - b * t.pix_blocks) * 128;
+          const int n_first = (kb * 64) / g.C;
+          for (int e = pt; e < n_ent; e += kProdThreads) {
+            const int tl = e >> 7, m = e & 127, p = p_base + m, n = n_first + tl;
+            PlanEntry pe;
+            pe.mask = 0u;
+            pe.pix = 0;
+            pe.fx = pe.fy = 0.f;
+            if (p < g.HW && n < g.N) pe = make_entry(g, t, P.off, b, p, n, 0);
+            pl[e] = pe;
+          }
+        }
+        bar_sync(1, kProdThreads);
+        // ---- wait for the stage, then fill the A images
+        mbar_wait(&empty[s], phase ^ 1);
+        uint8_t* a_hi = stage_base + (size_t)s * P.stage_bytes;
+        uint8_t* a_lo = a_hi + kATile;
+        if (VARIANT == DCN_VARIANT_TORCH) {
+          const int quads = t.Gt >> 2;                 // 8 or 4 lanes share one sampling point
+          const int quad = pt % quads, jl = pt / quads; // jl in [0, 256/quads)
+          const int j_per_pass = kProdThreads / quads;  // 32 or 64
+          for (int il = 0; il < t.Rt; ++il) {
+            const TileRowInfo ri = decode_inst(t, tile * t.Rt + il);
+            const float* img = P.xt + (size_t)ri.b * img_stride + quad * 4;
+            const int m = quad * (4 * t.Rt) + il * 4;
+#pragma unroll 2
+            for (int kk = jl; kk < 64; kk += j_per_pass) {
+              const PlanEntry pe = pl[il * 64 + kk];
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (pe.mask) v = gather_blend(img, pe, g.W, g.C);
+              uint2 hi, lo;
+              split4(v, hi, lo);
+              const uint32_t o = mnmajor_sw128_off(m, kk, kAMnLbo, kAMnSbo);
+              *reinterpret_cast<uint2*>(a_hi + o) = hi;
+              *reinterpret_cast<uint2*>(a_lo + o) = lo;
+            }
+          }
+        } else {
+          const int b = tile / t.pix_blocks;
+          const int quad = pt & 15, m0 = pt >> 4;  // 16 quads = 64 columns of the K block
+          const int j = kb * 64 + quad * 4;
+          const int n = j / g.C, c = j - n * g.C, tl = n - (kb * 64) / g.C;
+          const float* img = P.xt + (size_t)b * img_stride + c;
+          const bool col_ok = j < g.K;
+#pragma unroll 2
+          for (int m = m0; m < 128; m += 16) {
+            const PlanEntry pe = pl[tl * 128 + m];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_ok && pe.mask) v = gather_blend(img, pe, g.W, g.C);
+            uint2 hi, lo;
+            split4(v, hi, lo);
+            const uint32_t o = kmajor_sw128_off(m, quad * 4);
+            *reinterpret_cast<uint2*>(a_hi + o) = hi;
+            *reinterpret_cast<uint2*>(a_lo + o) = lo;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+        if (++s == P.stages) {
+          s = 0;
+          phase ^= 1;
+        }
+        pbuf ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+static uint32_t pow2_cols(int cols) {
+  uint32_t c = 32;
+  while ((int)c < cols) c <<= 1;
+  return c;
+}
+
+bool umma_fwd_supported(const Geo& g, int operand) {
+  if (operand != DCN_OPERAND_FP32) return false;
+  if (g.O % 16 || g.O < 16 || g.O > 256) return false;
+  Tiling t;
+  if (!make_tiling(g, &t)) return false;
+  if (g.variant == DCN_VARIANT_TORCH && t.Rt * 64 > kPlanMax) return false;
+  if (g.variant == DCN_VARIANT_JITTOR && 128 * t.taps_per_kb > kPlanMax) return false;
+  return true;
+}
+
+size_t umma_fwd_workspace(const Geo& g) {
+  Tiling t;
+  make_tiling(g, &t);
+  const size_t xt = align_up(sizeof(float) * (size_t)g.B * g.C * g.H * g.W, 1024);
+  const size_t wt = align_up((size_t)t.KB * 2 * g.O * 128, 1024);
+  return xt + wt;
+}
+
+int umma_forward_fp32(const Geo& g, const float* x, const float* off, const float* wt, const float* bias,
+                      float* out, void* workspace, cudaStream_t st) {
+  FwdParams P;
+  P.g = g;
+  if (!make_tiling(g, &P.t)) {
+    set_error("umma forward: shape not tileable");
+    return DCN_ERR_UNSUPPORTED;
+  }
+  float* xt = (float*)workspace;
+  uint8_t* wtiles = (uint8_t*)workspace + align_up(sizeof(float) * (size_t)g.B * g.C * g.H * g.W, 1024);
+  int rc;
+  if ((rc = launch_nchw_to_nhwc(g, P.t, x, xt, st))) return rc;
+  if ((rc = launch_weight_tiles_fwd(g, P.t, wt, wtiles, st))) return rc;
+  P.xt = xt;
+  P.off = off;
+  P.wtiles = wtiles;
+  P.bias = bias;
+  P.out = out;
+  P.b_tile = (uint32_t)g.O * 128;
+  P.stage_bytes = 2 * kATile + 2 * P.b_tile;
+  const size_t fixed = 2 * kPlanMax * sizeof(PlanEntry) + 256 + 1024;
+  int stages = (int)((227 * 1024 - fixed) / P.stage_bytes);
+  P.stages = stages > kMaxStages ? kMaxStages : stages;
+  if (P.stages < 2) {
+    set_error("umma forward: not enough shared memory for 2 stages");
+    return DCN_ERR_UNSUPPORTED;
+  }
+  P.tmem_cols = pow2_cols(2 * g.O);
+  const size_t smem = (size_t)P.stages * P.stage_bytes + fixed;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = P.t.num_tiles < sms ? P.t.num_tiles : sms;
+  KernelScope scope("umma_fwd_kernel", st);
+  if (g.variant == DCN_VARIANT_TORCH) {
+    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel<DCN_VARIANT_TORCH>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_fwd_kernel<DCN_VARIANT_TORCH><<<grid, kFwdThreads, smem, st>>>(P);
+  } else {
+    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel<DCN_VARIANT_JITTOR>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_fwd_kernel<DCN_VARIANT_JITTOR><<<grid, kFwdThreads, smem, st>>>(P);
+  }
+  DCN_KERNEL_CHECK("umma_fwd_kernel");
+  return DCN_OK;
+}
+
+}  // namespace dcn
