@@ -106,12 +106,18 @@ __host__ __device__ inline int perm_channel(int c, int variant, int G, int Cs) {
   return variant == DCN_VARIANT_TORCH ? (c % Cs) * G + c / Cs : c;
 }
 
-// plan entry as the producers consume it (16 bytes in shared memory)
+// Plan entry as the gather warps consume it (32 bytes in shared memory): the four corners'
+// float offsets inside image b of the channels-last copy and their weights.  An out-of-image
+// corner (zero padding) points at the all-zero pad pixel that closes every image and carries
+// weight 0, so the gather needs no branches and never multiplies a foreign (possibly
+// non-finite) value.
 struct __align__(16) PlanEntry {
-  int pix;        // float offset of the north-west corner's channel vector inside image b
-  uint32_t mask;  // corner validity bits (0 => nothing to fetch)
-  float fx, fy;
+  int off[4];   // nw, ne, sw, se
+  float w[4];
 };
+
+// channels-last staging copy: [B][H*W + 1][C]; pixel H*W of every image is zero
+__host__ __device__ inline size_t xt_image_stride(const Geo& g) { return (size_t)(g.H * g.W + 1) * g.C; }
 
 int launch_nchw_to_nhwc(const Geo& g, const Tiling& t, const float* x, float* xt, cudaStream_t st);
 int launch_nhwc_to_nchw_add(const Geo& g, const Tiling& t, const float* gxt, float* gx, int accumulate,

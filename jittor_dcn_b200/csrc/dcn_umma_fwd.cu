@@ -27,7 +27,7 @@ using namespace ptx;
 constexpr int kEpiWarps = 4, kProdWarps = 8;
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kFwdThreads = (kEpiWarps + 2 + kProdWarps) * 32;  // 448
-constexpr int kPlanMax = 512;                                    // plan entries per K block
+constexpr int kPlanMax = 512;                                    // plan entries per K block (32 B each)
 constexpr uint32_t kATile = 128 * 64 * 2;                        // one bf16 A image (16 KB)
 constexpr uint32_t kAMnLbo = 1024, kAMnSbo = 2048;               // MN-major A: atom strides
 constexpr int kMaxStages = 4;
@@ -62,46 +62,79 @@ __device__ __forceinline__ TileRowInfo decode_inst(const Tiling& t, int inst) {
   return ri;
 }
 
-// offsets -> tap -> plan entry (pix is relative to image b of the channels-last copy)
-__device__ __forceinline__ PlanEntry make_entry(const Geo& g, const Tiling& t, const float* __restrict__ off,
-                                                int b, int p, int n, int chan_base) {
+// One plan entry in the making: the index math is done and the two offset loads are in
+// flight (issued one K block ahead so that their latency hides behind the gather phase).
+struct PlanWork {
+  float ox, oy;
+  int h, w, chan_base, valid;
+};
+
+template <int VARIANT>
+__device__ __forceinline__ void plan_prepare(const Geo& g, const Tiling& t, const float* __restrict__ off,
+                                             int tile, int kb, int e, PlanWork& pw) {
+  pw.valid = 0;
+  pw.ox = pw.oy = 0.f;
+  pw.h = pw.w = pw.chan_base = 0;
+  int b, p, n;
+  if (VARIANT == DCN_VARIANT_TORCH) {
+    const int il = e >> 6, kk = e & 63, j = kb * 64 + kk;
+    const TileRowInfo ri = decode_inst(t, tile * t.Rt + il);
+    if (!ri.valid || j >= g.K) return;
+    uint32_t cb, q, pp, nn;
+    t.divP.divmod((uint32_t)(ri.r0 * g.K + j), cb, q);
+    t.divN.divmod(q, pp, nn);
+    b = ri.b;
+    p = (int)pp;
+    n = (int)nn;
+    pw.chan_base = (int)cb * t.G + ri.chunk * t.Gt;
+  } else {
+    const int tl = e >> 7, m = e & 127;
+    b = tile / t.pix_blocks;
+    p = (tile - b * t.pix_blocks) * 128 + m;
+    n = (kb * 64) / g.C + tl;
+    if (p >= g.HW || n >= g.N) return;
+  }
   uint32_t h, w;
   t.divWo.divmod((uint32_t)p, h, w);
+  pw.h = (int)h;
+  pw.w = (int)w;
   const float* ob = off + (size_t)b * 2 * g.N * g.HW;
-  const float ox = __ldg(ob + (size_t)n * g.HW + p);
-  const float oy = __ldg(ob + (size_t)(g.N + n) * g.HW + p);
-  const Tap tp = tap_of(g, (int)h, (int)w, ox, oy);
+  pw.ox = __ldg(ob + (size_t)n * g.HW + p);
+  pw.oy = __ldg(ob + (size_t)(g.N + n) * g.HW + p);
+  pw.valid = 1;
+}
+
+// coordinate chain (bit-exact, dcn_common.cuh:tap_of) -> branch-free gather entry
+__device__ __forceinline__ PlanEntry plan_finish(const Geo& g, const PlanWork& pw) {
   PlanEntry e;
-  e.mask = corner_mask(tp, g.H, g.W);
-  const int y0 = max(-1, min(tp.y0, g.H - 1)), x0 = max(-1, min(tp.x0, g.W - 1));
-  e.pix = (y0 * g.W + x0) * g.C + chan_base;
-  e.fx = tp.fx;
-  e.fy = tp.fy;
+  const int pad = g.H * g.W * g.C + pw.chan_base;  // the zero pixel
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    e.off[k] = pad;
+    e.w[k] = 0.f;
+  }
+  if (pw.valid) {
+    const Tap tp = tap_of(g, pw.h, pw.w, pw.ox, pw.oy);
+    const unsigned m = corner_mask(tp, g.H, g.W);
+    if (m) {
+      float cw[4];
+      corner_weights(tp, cw);
+      const int base = (tp.y0 * g.W + tp.x0) * g.C + pw.chan_base;  // only used for valid corners
+      if (m & 1u) { e.off[0] = base;                     e.w[0] = cw[0]; }
+      if (m & 2u) { e.off[1] = base + g.C;               e.w[1] = cw[1]; }
+      if (m & 4u) { e.off[2] = base + g.W * g.C;         e.w[2] = cw[2]; }
+      if (m & 8u) { e.off[3] = base + g.W * g.C + g.C;   e.w[3] = cw[3]; }
+    }
+  }
   return e;
 }
 
-// 4 corners x 4 channels -> blended float4 (zero padding), reference accumulation order
-__device__ __forceinline__ float4 gather_blend(const float* __restrict__ img, const PlanEntry& e, int W,
-                                               int C) {
-  float cw[4];
-  {
-    const float ee = __fsub_rn(1.0f, e.fx), ss = __fsub_rn(1.0f, e.fy);
-    cw[0] = __fmul_rn(ss, ee);
-    cw[1] = __fmul_rn(ss, e.fx);
-    cw[2] = __fmul_rn(e.fy, ee);
-    cw[3] = __fmul_rn(e.fy, e.fx);
-  }
-  const float* base = img + e.pix;
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 v0 = (e.mask & 1u) ? __ldg(reinterpret_cast<const float4*>(base)) : z;
-  const float4 v1 = (e.mask & 2u) ? __ldg(reinterpret_cast<const float4*>(base + C)) : z;
-  const float4 v2 = (e.mask & 4u) ? __ldg(reinterpret_cast<const float4*>(base + (size_t)W * C)) : z;
-  const float4 v3 = (e.mask & 8u) ? __ldg(reinterpret_cast<const float4*>(base + (size_t)W * C + C)) : z;
+__device__ __forceinline__ float4 blend4(const float4 v[4], const PlanEntry& e) {
   float4 r;
-  r.x = v0.x * cw[0] + v1.x * cw[1] + v2.x * cw[2] + v3.x * cw[3];
-  r.y = v0.y * cw[0] + v1.y * cw[1] + v2.y * cw[2] + v3.y * cw[3];
-  r.z = v0.z * cw[0] + v1.z * cw[1] + v2.z * cw[2] + v3.z * cw[3];
-  r.w = v0.w * cw[0] + v1.w * cw[1] + v2.w * cw[2] + v3.w * cw[3];
+  r.x = fmaf(v[3].x, e.w[3], fmaf(v[2].x, e.w[2], fmaf(v[1].x, e.w[1], v[0].x * e.w[0])));
+  r.y = fmaf(v[3].y, e.w[3], fmaf(v[2].y, e.w[2], fmaf(v[1].y, e.w[1], v[0].y * e.w[0])));
+  r.z = fmaf(v[3].z, e.w[3], fmaf(v[2].z, e.w[2], fmaf(v[1].z, e.w[1], v[0].z * e.w[0])));
+  r.w = fmaf(v[3].w, e.w[3], fmaf(v[2].w, e.w[2], fmaf(v[1].w, e.w[1], v[0].w * e.w[0])));
   return r;
 }
 
@@ -267,84 +300,102 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
     int s = 0;
     uint32_t phase = 0;
     int pbuf = 0;
-    const size_t img_stride = (size_t)g.H * g.W * g.C;
+    const size_t img_stride = xt_image_stride(g);
+    const int n_ent = VARIANT == DCN_VARIANT_TORCH ? t.Rt * 64 : 128 * t.taps_per_kb;
+    // static per-thread item geometry
+    const int quads = VARIANT == DCN_VARIANT_TORCH ? (t.Gt >> 2) : 16;
+    const int quad = pt % quads, lane_hi = pt / quads;   // torch: lane_hi = column slot jl; jittor: row slot m0
+    const int pass_shift = (VARIANT == DCN_VARIANT_TORCH && t.Gt == 32) ? 1 : 0;  // 2 column passes per class
+    PlanWork pw[2];
+    {
+      const int tile0 = blockIdx.x;
+      if (tile0 < t.num_tiles) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (pt + u * kProdThreads < n_ent) plan_prepare<VARIANT>(g, t, P.off, tile0, 0, pt + u * kProdThreads, pw[u]);
+      }
+    }
     for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
+      // image index of the rows this thread fills (Torch: one per class instance of the tile)
+      int img_b[8];
+      if (VARIANT == DCN_VARIANT_TORCH) {
+#pragma unroll
+        for (int il = 0; il < 8; ++il) img_b[il] = il < t.Rt ? decode_inst(t, tile * t.Rt + il).b : 0;
+      } else {
+        img_b[0] = tile / t.pix_blocks;
+      }
       for (int kb = 0; kb < t.KB; ++kb) {
         PlanEntry* pl = plan + pbuf * kPlanMax;
-        // ---- plan entries of this K block
-        if (VARIANT == DCN_VARIANT_TORCH) {
-          const int n_ent = t.Rt * 64;
-          for (int e = pt; e < n_ent; e += kProdThreads) {
-            const int il = e >> 6, kk = e & 63, j = kb * 64 + kk;
-            const TileRowInfo ri = decode_inst(t, tile * t.Rt + il);
-            PlanEntry pe;
-            pe.mask = 0u;
-            pe.pix = 0;
-            pe.fx = pe.fy = 0.f;
-            if (ri.valid && j < g.K) {
-              uint32_t cb, q, p, n;
-              t.divP.divmod((uint32_t)(ri.r0 * g.K + j), cb, q);
-              t.divN.divmod(q, p, n);
-              pe = make_entry(g, t, P.off, ri.b, (int)p, (int)n, (int)cb * t.G + ri.chunk * t.Gt);
-            }
-            pl[e] = pe;
+        // ---- finish this K block's plan entries (their offset loads were issued a block ago)
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (pt + u * kProdThreads < n_ent) pl[pt + u * kProdThreads] = plan_finish(g, pw[u]);
+        // ---- and start the next block's
+        {
+          int ntile = tile, nkb = kb + 1;
+          if (nkb == t.KB) {
+            nkb = 0;
+            ntile = tile + gridDim.x;
           }
-        } else {
-          const int T = t.taps_per_kb, n_ent = 128 * T;
-          const int b = tile / t.pix_blocks, p_base = (tile - b * t.pix_blocks) * 128;
-          const int n_first = (kb * 64) / g.C;
-          for (int e = pt; e < n_ent; e += kProdThreads) {
-            const int tl = e >> 7, m = e & 127, p = p_base + m, n = n_first + tl;
-            PlanEntry pe;
-            pe.mask = 0u;
-            pe.pix = 0;
-            pe.fx = pe.fy = 0.f;
-            if (p < g.HW && n < g.N) pe = make_entry(g, t, P.off, b, p, n, 0);
-            pl[e] = pe;
+          if (ntile < t.num_tiles) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+              if (pt + u * kProdThreads < n_ent)
+                plan_prepare<VARIANT>(g, t, P.off, ntile, nkb, pt + u * kProdThreads, pw[u]);
           }
         }
         bar_sync(1, kProdThreads);
-        // ---- wait for the stage, then fill the A images
+        // ---- wait for the stage, then fill the A images: 2 batches of 4 items, 16 LDG.128 in flight
         mbar_wait(&empty[s], phase ^ 1);
         uint8_t* a_hi = stage_base + (size_t)s * P.stage_bytes;
         uint8_t* a_lo = a_hi + kATile;
-        if (VARIANT == DCN_VARIANT_TORCH) {
-          const int quads = t.Gt >> 2;                 // 8 or 4 lanes share one sampling point
-          const int quad = pt % quads, jl = pt / quads; // jl in [0, 256/quads)
-          const int j_per_pass = kProdThreads / quads;  // 32 or 64
-          for (int il = 0; il < t.Rt; ++il) {
-            const TileRowInfo ri = decode_inst(t, tile * t.Rt + il);
-            const float* img = P.xt + (size_t)ri.b * img_stride + quad * 4;
-            const int m = quad * (4 * t.Rt) + il * 4;
-#pragma unroll 2
-            for (int kk = jl; kk < 64; kk += j_per_pass) {
-              const PlanEntry pe = pl[il * 64 + kk];
-              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (pe.mask) v = gather_blend(img, pe, g.W, g.C);
-              uint2 hi, lo;
-              split4(v, hi, lo);
-              const uint32_t o = mnmajor_sw128_off(m, kk, kAMnLbo, kAMnSbo);
-              *reinterpret_cast<uint2*>(a_hi + o) = hi;
-              *reinterpret_cast<uint2*>(a_lo + o) = lo;
+        int jit_c = 0, jit_tl = 0;
+        bool col_ok = true;
+        if (VARIANT != DCN_VARIANT_TORCH) {
+          const int j = kb * 64 + quad * 4;
+          const int n = j / g.C;
+          jit_c = j - n * g.C;
+          jit_tl = n - (kb * 64) / g.C;
+          col_ok = j < g.K;
+        }
+#pragma unroll
+        for (int batch = 0; batch < 2; ++batch) {
+          PlanEntry e[4];
+          const float* ip[4];
+          uint32_t so[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int it = batch * 4 + u;
+            if (VARIANT == DCN_VARIANT_TORCH) {
+              const int il = it >> pass_shift;
+              const int kk = lane_hi + ((it & pass_shift) ? 32 : 0);
+              e[u] = pl[il * 64 + kk];
+              const int bimg = pass_shift ? img_b[it >> 1] : img_b[it];  // static register indices
+              ip[u] = P.xt + (size_t)bimg * img_stride + quad * 4;
+              so[u] = mnmajor_sw128_off(quad * (4 * t.Rt) + il * 4, kk, kAMnLbo, kAMnSbo);
+            } else {
+              const int m = lane_hi + 16 * it;
+              e[u] = pl[jit_tl * 128 + m];
+              ip[u] = P.xt + (size_t)img_b[0] * img_stride + jit_c;
+              so[u] = kmajor_sw128_off(m, quad * 4);
+              if (!col_ok) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) e[u].w[k] = 0.f;
+              }
             }
           }
-        } else {
-          const int b = tile / t.pix_blocks;
-          const int quad = pt & 15, m0 = pt >> 4;  // 16 quads = 64 columns of the K block
-          const int j = kb * 64 + quad * 4;
-          const int n = j / g.C, c = j - n * g.C, tl = n - (kb * 64) / g.C;
-          const float* img = P.xt + (size_t)b * img_stride + c;
-          const bool col_ok = j < g.K;
-#pragma unroll 2
-          for (int m = m0; m < 128; m += 16) {
-            const PlanEntry pe = pl[tl * 128 + m];
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col_ok && pe.mask) v = gather_blend(img, pe, g.W, g.C);
+          float4 v[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[u][k] = __ldg(reinterpret_cast<const float4*>(ip[u] + e[u].off[k]));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 r = blend4(v[u], e[u]);
             uint2 hi, lo;
-            split4(v, hi, lo);
-            const uint32_t o = kmajor_sw128_off(m, quad * 4);
-            *reinterpret_cast<uint2*>(a_hi + o) = hi;
-            *reinterpret_cast<uint2*>(a_lo + o) = lo;
+            split4(r, hi, lo);
+            *reinterpret_cast<uint2*>(a_hi + so[u]) = hi;
+            *reinterpret_cast<uint2*>(a_lo + so[u]) = lo;
           }
         }
         fence_proxy_async_smem();
@@ -387,7 +438,7 @@ bool umma_fwd_supported(const Geo& g, int operand) {
 size_t umma_fwd_workspace(const Geo& g) {
   Tiling t;
   make_tiling(g, &t);
-  const size_t xt = align_up(sizeof(float) * (size_t)g.B * g.C * g.H * g.W, 1024);
+  const size_t xt = align_up(sizeof(float) * (size_t)g.B * xt_image_stride(g), 1024);
   const size_t wt = align_up((size_t)t.KB * 2 * g.O * 128, 1024);
   return xt + wt;
 }
@@ -401,7 +452,7 @@ int umma_forward_fp32(const Geo& g, const float* x, const float* off, const floa
     return DCN_ERR_UNSUPPORTED;
   }
   float* xt = (float*)workspace;
-  uint8_t* wtiles = (uint8_t*)workspace + align_up(sizeof(float) * (size_t)g.B * g.C * g.H * g.W, 1024);
+  uint8_t* wtiles = (uint8_t*)workspace + align_up(sizeof(float) * (size_t)g.B * xt_image_stride(g), 1024);
   int rc;
   if ((rc = launch_nchw_to_nhwc(g, P.t, x, xt, st))) return rc;
   if ((rc = launch_weight_tiles_fwd(g, P.t, wt, wtiles, st))) return rc;

@@ -30,8 +30,11 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(Geo g, int variant, i
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int p = p0 + ty + 8 * i, d = d0 + tx;
-    if (d < g.C && p < HWi) xt[((size_t)b * HWi + p) * g.C + d] = tile[tx][ty + 8 * i];
+    if (d < g.C && p < HWi) xt[((size_t)b * (HWi + 1) + p) * g.C + d] = tile[tx][ty + 8 * i];
   }
+  // the zero pad pixel that closes the image (target of out-of-image corners)
+  if (blockIdx.x == 0 && threadIdx.x < 32 && d0 + tx < g.C)
+    xt[((size_t)b * (HWi + 1) + HWi) * g.C + d0 + tx] = 0.f;
 }
 
 int launch_nchw_to_nhwc(const Geo& g, const Tiling& t, const float* x, float* xt, cudaStream_t st) {
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(Geo g, int variant, i
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int p = p0 + ty + 8 * i, d = d0 + tx;
-    if (d < g.C && p < HWi) tile[ty + 8 * i][tx] = __ldg(gxt + ((size_t)b * HWi + p) * g.C + d);
+    if (d < g.C && p < HWi) tile[ty + 8 * i][tx] = __ldg(gxt + ((size_t)b * (HWi + 1) + p) * g.C + d);
   }
   __syncthreads();
 #pragma unroll
