@@ -83,7 +83,7 @@ __host__ inline bool make_tiling(const Geo& g, Tiling* t) {
     if (t->G % 16) return false;
     t->R = g.HW / t->G;
     t->Cs = g.C / t->G;
-    t->Gt = (t->G % 32 == 0) ? 32 : 16;
+    t->Gt = (t->G % 64 == 0) ? 64 : ((t->G % 32 == 0) ? 32 : 16);
     t->Rt = 128 / t->Gt;
     t->chunks = t->G / t->Gt;
     long long inst = (long long)g.B * t->chunks * t->R;

@@ -6,17 +6,22 @@
 //   column layout                     deform_conv.py:72-73       / train.py:129-131
 //   GEMM + bias + NCHW store          deform_conv.py:74-81       / train.py:133-140
 //
-// Warp roles (448 threads, 1 CTA per SM, persistent over tiles):
+// Warp roles (512 threads, 1 CTA per SM, persistent over tiles):
 //   warps 0-3   epilogue : tcgen05.ld accumulator -> + bias -> out[B,O,Ho,Wo]
 //   warp  4     MMA      : one lane issues tcgen05.mma (bf16 hi/lo split, 3 MMAs per K step)
 //   warp  5     B loader : one lane streams the pre-tiled weight images with cp.async.bulk
-//   warps 6-13  producers: coordinate chain -> plan entries in smem -> 4x LDG.128 gather of the
-//                          channels-last input -> blend -> bf16 hi/lo -> swizzled smem A tile
-// Pipelines: smem full/empty mbarriers per stage (producers + loader -> MMA -> back),
-// TMEM full/empty per accumulator buffer (MMA -> epilogue -> back); 2 accumulator buffers.
+//   warps 6-7   plan     : offsets -> bit-exact coordinate chain -> branch-free gather entries
+//                          (corner offsets + masked weights) in a 2-deep smem ring, one K block
+//                          ahead of the gather warps
+//   warps 8-15  gather   : 4x LDG.128 per entry from the channels-last input -> blend ->
+//                          bf16 hi/lo -> swizzled smem A images
+// Pipelines (all mbarrier based): plan ring (plan -> gather -> back), smem stages
+// (gather + loader -> MMA -> back), TMEM accumulators (MMA -> epilogue -> back; 2 buffers).
 //
 // fp32 parity: every fp32 operand v is split as hi = bf16(v), lo = bf16(v - hi) and the product
 // is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation (relative error ~5e-6, measured).
+#include <cstdlib>
+
 #include "dcn_umma.h"
 #include "dcn_umma_common.cuh"
 
@@ -24,9 +29,12 @@ namespace dcn {
 
 using namespace ptx;
 
-constexpr int kEpiWarps = 4, kProdWarps = 8;
+constexpr int kEpiWarps = 4, kPlanWarps = 2, kProdWarps = 8;
+constexpr int kPlanThreads = kPlanWarps * 32;
 constexpr int kProdThreads = kProdWarps * 32;
-constexpr int kFwdThreads = (kEpiWarps + 2 + kProdWarps) * 32;  // 448
+constexpr int kFirstPlanWarp = kEpiWarps + 2, kFirstProdWarp = kFirstPlanWarp + kPlanWarps;
+constexpr int kFwdThreads = (kFirstProdWarp + kProdWarps) * 32;  // 512
+constexpr int kPlanPerThread = 8;                                // kPlanMax / kPlanThreads
 constexpr int kPlanMax = 512;                                    // plan entries per K block (32 B each)
 constexpr uint32_t kATile = 128 * 64 * 2;                        // one bf16 A image (16 KB)
 constexpr uint32_t kAMnLbo = 1024, kAMnSbo = 2048;               // MN-major A: atom strides
@@ -41,6 +49,7 @@ struct FwdParams {
   const float* bias;
   float* out;
   int stages;
+  int plan_cap;        // plan entries per buffer (n_ent rounded up to 256)
   uint32_t b_tile;     // bytes of one bf16 B image = O*128
   uint32_t stage_bytes;
   uint32_t tmem_cols;  // 2*O rounded to a power of two >= 32
@@ -160,12 +169,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
   // carve-up: [stages x (A_hi | A_lo | B_hi | B_lo)] [plan x2] [barriers]
   uint8_t* stage_base = smem;
   PlanEntry* plan = reinterpret_cast<PlanEntry*>(smem + (size_t)P.stages * P.stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(plan + 2 * kPlanMax);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(plan + 2 * P.plan_cap);
   uint64_t* full = bars;                   // [stages]
   uint64_t* empty = bars + kMaxStages;     // [stages]
   uint64_t* tfull = bars + 2 * kMaxStages; // [2]
   uint64_t* tempty = tfull + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* pfull = tempty + 2;            // [2] plan ring
+  uint64_t* pempty = pfull + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int O = g.O;
@@ -178,6 +189,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], kEpiWarps);
+      mbar_init(&pfull[a], kPlanWarps);
+      mbar_init(&pempty[a], kProdWarps);
     }
     fence_barrier_init();
   }
@@ -294,27 +307,58 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
         }
       }
     }
+  } else if (warp < kFirstProdWarp) {
+    // ================================================================ plan warps
+    const int pt = tid - kFirstPlanWarp * 32;  // 0..63
+    const int n_ent = VARIANT == DCN_VARIANT_TORCH ? t.Rt * 64 : 128 * t.taps_per_kb;
+    int pbuf = 0;
+    uint32_t pphase = 0;
+    PlanWork pw[kPlanPerThread];
+    if ((int)blockIdx.x < t.num_tiles) {
+#pragma unroll
+      for (int u = 0; u < kPlanPerThread; ++u)
+        if (pt + u * kPlanThreads < n_ent)
+          plan_prepare<VARIANT>(g, t, P.off, blockIdx.x, 0, pt + u * kPlanThreads, pw[u]);
+    }
+    for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < t.KB; ++kb) {
+        PlanEntry* pl = plan + pbuf * P.plan_cap;
+        mbar_wait(&pempty[pbuf], pphase ^ 1);
+        // finish this K block's entries (their offset loads were issued one block ago) ...
+#pragma unroll
+        for (int u = 0; u < kPlanPerThread; ++u)
+          if (pt + u * kPlanThreads < n_ent) pl[pt + u * kPlanThreads] = plan_finish(g, pw[u]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pfull[pbuf]);
+        // ... and start the next block's
+        int ntile = tile, nkb = kb + 1;
+        if (nkb == t.KB) {
+          nkb = 0;
+          ntile = tile + gridDim.x;
+        }
+        if (ntile < t.num_tiles) {
+#pragma unroll
+          for (int u = 0; u < kPlanPerThread; ++u)
+            if (pt + u * kPlanThreads < n_ent)
+              plan_prepare<VARIANT>(g, t, P.off, ntile, nkb, pt + u * kPlanThreads, pw[u]);
+        }
+        pbuf ^= 1;
+        if (pbuf == 0) pphase ^= 1;
+      }
+    }
   } else {
-    // ================================================================ producers
-    const int pt = tid - (kEpiWarps + 2) * 32;  // 0..255
+    // ================================================================ gather warps
+    const int pt = tid - kFirstProdWarp * 32;  // 0..255
     int s = 0;
     uint32_t phase = 0;
     int pbuf = 0;
+    uint32_t pphase = 0;
     const size_t img_stride = xt_image_stride(g);
-    const int n_ent = VARIANT == DCN_VARIANT_TORCH ? t.Rt * 64 : 128 * t.taps_per_kb;
-    // static per-thread item geometry
+    // static per-thread item geometry: `quads` lanes share one sampling point
     const int quads = VARIANT == DCN_VARIANT_TORCH ? (t.Gt >> 2) : 16;
-    const int quad = pt % quads, lane_hi = pt / quads;   // torch: lane_hi = column slot jl; jittor: row slot m0
-    const int pass_shift = (VARIANT == DCN_VARIANT_TORCH && t.Gt == 32) ? 1 : 0;  // 2 column passes per class
-    PlanWork pw[2];
-    {
-      const int tile0 = blockIdx.x;
-      if (tile0 < t.num_tiles) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-          if (pt + u * kProdThreads < n_ent) plan_prepare<VARIANT>(g, t, P.off, tile0, 0, pt + u * kProdThreads, pw[u]);
-      }
-    }
+    const int quad = pt % quads, lane_hi = pt / quads;  // torch: column slot; jittor: row slot
+    const int col_step = kProdThreads / quads;           // torch: columns covered per pass
+    const int pass_shift = VARIANT != DCN_VARIANT_TORCH ? 0 : (t.Gt == 64 ? 2 : (t.Gt == 32 ? 1 : 0));
     for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
       // image index of the rows this thread fills (Torch: one per class instance of the tile)
       int img_b[8];
@@ -325,30 +369,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
         img_b[0] = tile / t.pix_blocks;
       }
       for (int kb = 0; kb < t.KB; ++kb) {
-        PlanEntry* pl = plan + pbuf * kPlanMax;
-        // ---- finish this K block's plan entries (their offset loads were issued a block ago)
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-          if (pt + u * kProdThreads < n_ent) pl[pt + u * kProdThreads] = plan_finish(g, pw[u]);
-        // ---- and start the next block's
-        {
-          int ntile = tile, nkb = kb + 1;
-          if (nkb == t.KB) {
-            nkb = 0;
-            ntile = tile + gridDim.x;
-          }
-          if (ntile < t.num_tiles) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-              if (pt + u * kProdThreads < n_ent)
-                plan_prepare<VARIANT>(g, t, P.off, ntile, nkb, pt + u * kProdThreads, pw[u]);
-          }
-        }
-        bar_sync(1, kProdThreads);
-        // ---- wait for the stage, then fill the A images: 2 batches of 4 items, 16 LDG.128 in flight
-        mbar_wait(&empty[s], phase ^ 1);
-        uint8_t* a_hi = stage_base + (size_t)s * P.stage_bytes;
-        uint8_t* a_lo = a_hi + kATile;
+        const PlanEntry* pl = plan + pbuf * P.plan_cap;
         int jit_c = 0, jit_tl = 0;
         bool col_ok = true;
         if (VARIANT != DCN_VARIANT_TORCH) {
@@ -358,6 +379,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
           jit_tl = n - (kb * 64) / g.C;
           col_ok = j < g.K;
         }
+        mbar_wait(&pfull[pbuf], pphase);
+        mbar_wait(&empty[s], phase ^ 1);
+        uint8_t* a_hi = stage_base + (size_t)s * P.stage_bytes;
+        uint8_t* a_lo = a_hi + kATile;
+        // 2 batches of 4 items, 16 LDG.128 in flight per thread
 #pragma unroll
         for (int batch = 0; batch < 2; ++batch) {
           PlanEntry e[4];
@@ -368,9 +394,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
             const int it = batch * 4 + u;
             if (VARIANT == DCN_VARIANT_TORCH) {
               const int il = it >> pass_shift;
-              const int kk = lane_hi + ((it & pass_shift) ? 32 : 0);
+              const int kk = lane_hi + (it & ((1 << pass_shift) - 1)) * col_step;
               e[u] = pl[il * 64 + kk];
-              const int bimg = pass_shift ? img_b[it >> 1] : img_b[it];  // static register indices
+              const int bimg = pass_shift == 2 ? img_b[it >> 2] : (pass_shift == 1 ? img_b[it >> 1] : img_b[it]);
               ip[u] = P.xt + (size_t)bimg * img_stride + quad * 4;
               so[u] = mnmajor_sw128_off(quad * (4 * t.Rt) + il * 4, kk, kAMnLbo, kAMnSbo);
             } else {
@@ -400,12 +426,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
+        if (lane == 0) {
+          mbar_arrive(&full[s]);
+          mbar_arrive(&pempty[pbuf]);
+        }
         if (++s == P.stages) {
           s = 0;
           phase ^= 1;
         }
         pbuf ^= 1;
+        if (pbuf == 0) pphase ^= 1;
       }
     }
   }
@@ -431,6 +461,7 @@ bool umma_fwd_supported(const Geo& g, int operand) {
   Tiling t;
   if (!make_tiling(g, &t)) return false;
   if (g.variant == DCN_VARIANT_TORCH && t.Rt * 64 > kPlanMax) return false;
+  static_assert(kPlanMax == kPlanPerThread * kPlanThreads, "plan slots");
   if (g.variant == DCN_VARIANT_JITTOR && 128 * t.taps_per_kb > kPlanMax) return false;
   return true;
 }
@@ -463,9 +494,17 @@ int umma_forward_fp32(const Geo& g, const float* x, const float* off, const floa
   P.out = out;
   P.b_tile = (uint32_t)g.O * 128;
   P.stage_bytes = 2 * kATile + 2 * P.b_tile;
-  const size_t fixed = 2 * kPlanMax * sizeof(PlanEntry) + 256 + 1024;
+  const int n_ent = g.variant == DCN_VARIANT_TORCH ? P.t.Rt * 64 : 128 * P.t.taps_per_kb;
+  P.plan_cap = (n_ent + 255) / 256 * 256;
+  const size_t fixed = 2 * (size_t)P.plan_cap * sizeof(PlanEntry) + 256 + 1024;  // plan ring, barriers, align slack
   int stages = (int)((227 * 1024 - fixed) / P.stage_bytes);
-  P.stages = stages > kMaxStages ? kMaxStages : stages;
+  // Two stages are enough to overlap the (fast) MMAs with the (slow) gather, and every KB of
+  // shared memory not taken is L1 for the gather's footprint (L1 + smem share 256 KB).
+  int want = 2;
+  if (const char* e = getenv("DCN_FWD_STAGES")) want = atoi(e);
+  if (want < 2) want = 2;
+  if (want > kMaxStages) want = kMaxStages;
+  P.stages = stages > want ? want : stages;
   if (P.stages < 2) {
     set_error("umma forward: not enough shared memory for 2 stages");
     return DCN_ERR_UNSUPPORTED;
