@@ -49,6 +49,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, for roles that wait long (epilogue, MMA issuer, bulk loader): back off with
+// nanosleep so that the polling does not steal issue slots from the gather warps.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns = 128) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (tcgen05.mma, bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -179,6 +189,19 @@ __device__ __forceinline__ uint32_t kmajor_sw128_off(int row, int k) {
 __device__ __forceinline__ uint32_t mnmajor_sw128_off(int m, int k, uint32_t lbo, uint32_t sbo) {
   return (uint32_t)((m >> 6) * lbo + (k >> 3) * sbo + (k & 7) * 128 + (((((m & 63) >> 3) ^ k) & 7) << 4) +
                     (m & 7) * 2);
+}
+
+// two floats -> packed bf16x2 (a in the low half = lower address), one cvt instruction
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+// (a, b) -> packed hi and packed lo with hi + lo ~= v to 16 mantissa bits (6 instructions)
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(a, b);
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+  lo = pack_bf16x2(a - ha, b - hb);
 }
 
 // fp32 -> (hi, lo) bf16 pair with hi + lo ~= v to 16 mantissa bits

@@ -6,14 +6,15 @@
 //   column layout                     deform_conv.py:72-73       / train.py:129-131
 //   GEMM + bias + NCHW store          deform_conv.py:74-81       / train.py:133-140
 //
-// Warp roles (512 threads, 1 CTA per SM, persistent over tiles):
+// Warp roles (832 threads, 1 CTA per SM, persistent over tiles; the gather is issue/latency
+// bound, so it gets most of the warps):
 //   warps 0-3   epilogue : tcgen05.ld accumulator -> + bias -> out[B,O,Ho,Wo]
 //   warp  4     MMA      : one lane issues tcgen05.mma (bf16 hi/lo split, 3 MMAs per K step)
 //   warp  5     B loader : one lane streams the pre-tiled weight images with cp.async.bulk
-//   warps 6-7   plan     : offsets -> bit-exact coordinate chain -> branch-free gather entries
+//   warps 6-9   plan     : offsets -> bit-exact coordinate chain -> branch-free gather entries
 //                          (corner offsets + masked weights) in a 2-deep smem ring, one K block
 //                          ahead of the gather warps
-//   warps 8-15  gather   : 4x LDG.128 per entry from the channels-last input -> blend ->
+//   warps 10-25 gather   : 4x LDG.128 per entry from the channels-last input -> blend ->
 //                          bf16 hi/lo -> swizzled smem A images
 // Pipelines (all mbarrier based): plan ring (plan -> gather -> back), smem stages
 // (gather + loader -> MMA -> back), TMEM accumulators (MMA -> epilogue -> back; 2 buffers).
@@ -29,12 +30,13 @@ namespace dcn {
 
 using namespace ptx;
 
-constexpr int kEpiWarps = 4, kPlanWarps = 2, kProdWarps = 8;
+constexpr int kEpiWarps = 4, kPlanWarps = 4, kProdWarps = 16;
 constexpr int kPlanThreads = kPlanWarps * 32;
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kFirstPlanWarp = kEpiWarps + 2, kFirstProdWarp = kFirstPlanWarp + kPlanWarps;
-constexpr int kFwdThreads = (kFirstProdWarp + kProdWarps) * 32;  // 512
-constexpr int kPlanPerThread = 8;                                // kPlanMax / kPlanThreads
+constexpr int kFwdThreads = (kFirstProdWarp + kProdWarps) * 32;  // 832
+constexpr int kPlanPerThread = 4;                                // kPlanMax / kPlanThreads
+constexpr int kItems = 128 * 16 / kProdThreads;                  // float4 items per thread and K block (4)
 constexpr int kPlanMax = 512;                                    // plan entries per K block (32 B each)
 constexpr uint32_t kATile = 128 * 64 * 2;                        // one bf16 A image (16 KB)
 constexpr uint32_t kAMnLbo = 1024, kAMnSbo = 2048;               // MN-major A: atom strides
@@ -49,6 +51,7 @@ struct FwdParams {
   const float* bias;
   float* out;
   int stages;
+  int dbg;             // DCN_FWD_DBG timing experiments (results invalid when non-zero)
   int plan_cap;        // plan entries per buffer (n_ent rounded up to 256)
   uint32_t b_tile;     // bytes of one bf16 B image = O*128
   uint32_t stage_bytes;
@@ -149,21 +152,16 @@ __device__ __forceinline__ float4 blend4(const float4 v[4], const PlanEntry& e) 
 
 // float4 -> 4 bf16 hi + 4 bf16 lo, each packed in 8 bytes
 __device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
-  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-  split_bf16(v.x, h0, l0);
-  split_bf16(v.y, h1, l1);
-  split_bf16(v.z, h2, l2);
-  split_bf16(v.w, h3, l3);
-  hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-  hi.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-  lo.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  lo.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+  split_pair(v.x, v.y, hi.x, lo.x);
+  split_pair(v.z, v.w, hi.y, lo.y);
 }
 
 template <int VARIANT>
 __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic (a uintptr_t round trip would lose the shared
+  // address space and turn every LDS/STS below into a slow generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const Geo& g = P.g;
   const Tiling& t = P.t;
   // carve-up: [stages x (A_hi | A_lo | B_hi | B_lo)] [plan x2] [barriers]
@@ -225,13 +223,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
         valid = p < g.HW;
         out_off = (size_t)b * O * g.HW + p;
       }
-      mbar_wait(&tfull[acc], acc_phase);
+      mbar_wait_relaxed(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * O);
       for (int c0 = 0; c0 < O; c0 += 16) {
         float v[16];
         tmem_ld16(taddr + c0, v);
-        if (valid) {
+        if (valid && !(P.dbg & 16)) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float bv = P.bias ? __ldg(P.bias + c0 + i) : 0.f;
@@ -252,11 +250,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
       int s = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        mbar_wait_relaxed(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * O);
         for (int kb = 0; kb < t.KB; ++kb) {
-          mbar_wait(&full[s], phase);
+          mbar_wait_relaxed(&full[s], phase, 64);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(stage_base + (size_t)s * P.stage_bytes);
           const uint32_t a_lo = a_hi + kATile;
@@ -264,6 +262,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
           const uint32_t b_lo = b_hi + P.b_tile;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
+            if (P.dbg & 8) break;
             uint64_t dah, dal;
             if (VARIANT == DCN_VARIANT_TORCH) {
               dah = make_sdesc_sw128(a_hi + k4 * 2 * kAMnSbo, kAMnLbo, kAMnSbo);
@@ -296,7 +295,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < t.KB; ++kb) {
-          mbar_wait(&empty[s], phase ^ 1);
+          mbar_wait_relaxed(&empty[s], phase ^ 1);
           uint8_t* dst = stage_base + (size_t)s * P.stage_bytes + 2 * kATile;
           mbar_arrive_expect_tx(&full[s], 2 * P.b_tile);
           bulk_g2s(dst, P.wtiles + (size_t)kb * 2 * P.b_tile, 2 * P.b_tile, &full[s]);
@@ -323,11 +322,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
     for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < t.KB; ++kb) {
         PlanEntry* pl = plan + pbuf * P.plan_cap;
-        mbar_wait(&pempty[pbuf], pphase ^ 1);
+        mbar_wait_relaxed(&pempty[pbuf], pphase ^ 1, 64);
         // finish this K block's entries (their offset loads were issued one block ago) ...
 #pragma unroll
         for (int u = 0; u < kPlanPerThread; ++u)
-          if (pt + u * kPlanThreads < n_ent) pl[pt + u * kPlanThreads] = plan_finish(g, pw[u]);
+          if (pt + u * kPlanThreads < n_ent) {
+            if (P.dbg & 2) {
+              PlanEntry pe;
+              pe.off[0] = pe.off[1] = pe.off[2] = pe.off[3] = (pt & 63) * g.C;
+              pe.w[0] = pe.w[1] = pe.w[2] = pe.w[3] = 0.25f;
+              pl[pt + u * kPlanThreads] = pe;
+            } else {
+              pl[pt + u * kPlanThreads] = plan_finish(g, pw[u]);
+            }
+          }
         __syncwarp();
         if (lane == 0) mbar_arrive(&pfull[pbuf]);
         // ... and start the next block's
@@ -336,7 +344,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
           nkb = 0;
           ntile = tile + gridDim.x;
         }
-        if (ntile < t.num_tiles) {
+        if (ntile < t.num_tiles && !(P.dbg & 2)) {
 #pragma unroll
           for (int u = 0; u < kPlanPerThread; ++u)
             if (pt + u * kPlanThreads < n_ent)
@@ -348,95 +356,140 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
     }
   } else {
     // ================================================================ gather warps
-    const int pt = tid - kFirstProdWarp * 32;  // 0..255
-    int s = 0;
-    uint32_t phase = 0;
-    int pbuf = 0;
-    uint32_t pphase = 0;
+    // kItems (4) float4 items per thread and K block, software pipelined one item deep: the 4
+    // LDG.128 of item i+1 (possibly the first item of the NEXT K block) are issued before item
+    // i is blended, so every warp always has gathers in flight.
+    const int pt = tid - kFirstProdWarp * 32;  // 0..511
     const size_t img_stride = xt_image_stride(g);
-    // static per-thread item geometry: `quads` lanes share one sampling point
+    // `quads` lanes share one sampling point; a "pair" is one (class instance, column) of the
+    // Torch tile or one row of the Jittor tile
     const int quads = VARIANT == DCN_VARIANT_TORCH ? (t.Gt >> 2) : 16;
-    const int quad = pt % quads, lane_hi = pt / quads;  // torch: column slot; jittor: row slot
-    const int col_step = kProdThreads / quads;           // torch: columns covered per pass
-    const int pass_shift = VARIANT != DCN_VARIANT_TORCH ? 0 : (t.Gt == 64 ? 2 : (t.Gt == 32 ? 1 : 0));
-    for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
-      // image index of the rows this thread fills (Torch: one per class instance of the tile)
-      int img_b[8];
+    const int quad = pt % quads, slot = pt / quads;
+    const int pairs_per_pass = kProdThreads / quads;
+    int ent_idx[kItems], item_il[kItems];
+    uint32_t st_off[kItems];
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
+      const int pair = slot + it * pairs_per_pass;
       if (VARIANT == DCN_VARIANT_TORCH) {
-#pragma unroll
-        for (int il = 0; il < 8; ++il) img_b[il] = il < t.Rt ? decode_inst(t, tile * t.Rt + il).b : 0;
+        const int il = pair >> 6, kk = pair & 63;
+        item_il[it] = il;
+        ent_idx[it] = pair;  // = il * 64 + kk
+        st_off[it] = mnmajor_sw128_off(quad * (4 * t.Rt) + il * 4, kk, kAMnLbo, kAMnSbo);
       } else {
-        img_b[0] = tile / t.pix_blocks;
+        item_il[it] = 0;
+        ent_idx[it] = pair;  // row m
+        st_off[it] = kmajor_sw128_off(pair, quad * 4);
       }
-      for (int kb = 0; kb < t.KB; ++kb) {
-        const PlanEntry* pl = plan + pbuf * P.plan_cap;
-        int jit_c = 0, jit_tl = 0;
-        bool col_ok = true;
-        if (VARIANT != DCN_VARIANT_TORCH) {
-          const int j = kb * 64 + quad * 4;
-          const int n = j / g.C;
-          jit_c = j - n * g.C;
-          jit_tl = n - (kb * 64) / g.C;
-          col_ok = j < g.K;
-        }
-        mbar_wait(&pfull[pbuf], pphase);
-        mbar_wait(&empty[s], phase ^ 1);
-        uint8_t* a_hi = stage_base + (size_t)s * P.stage_bytes;
-        uint8_t* a_lo = a_hi + kATile;
-        // 2 batches of 4 items, 16 LDG.128 in flight per thread
-#pragma unroll
-        for (int batch = 0; batch < 2; ++batch) {
-          PlanEntry e[4];
-          const float* ip[4];
-          uint32_t so[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int it = batch * 4 + u;
-            if (VARIANT == DCN_VARIANT_TORCH) {
-              const int il = it >> pass_shift;
-              const int kk = lane_hi + (it & ((1 << pass_shift) - 1)) * col_step;
-              e[u] = pl[il * 64 + kk];
-              const int bimg = pass_shift == 2 ? img_b[it >> 2] : (pass_shift == 1 ? img_b[it >> 1] : img_b[it]);
-              ip[u] = P.xt + (size_t)bimg * img_stride + quad * 4;
-              so[u] = mnmajor_sw128_off(quad * (4 * t.Rt) + il * 4, kk, kAMnLbo, kAMnSbo);
-            } else {
-              const int m = lane_hi + 16 * it;
-              e[u] = pl[jit_tl * 128 + m];
-              ip[u] = P.xt + (size_t)img_b[0] * img_stride + jit_c;
-              so[u] = kmajor_sw128_off(m, quad * 4);
-              if (!col_ok) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) e[u].w[k] = 0.f;
-              }
-            }
-          }
-          float4 v[4][4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[u][k] = __ldg(reinterpret_cast<const float4*>(ip[u] + e[u].off[k]));
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float4 r = blend4(v[u], e[u]);
-            uint2 hi, lo;
-            split4(r, hi, lo);
-            *reinterpret_cast<uint2*>(a_hi + so[u]) = hi;
-            *reinterpret_cast<uint2*>(a_lo + so[u]) = lo;
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&full[s]);
-          mbar_arrive(&pempty[pbuf]);
-        }
-        if (++s == P.stages) {
-          s = 0;
-          phase ^= 1;
-        }
-        pbuf ^= 1;
-        if (pbuf == 0) pphase ^= 1;
+    }
+    // position of one K block in the three rings it touches
+    struct Pos {
+      int tile, kb, s, pbuf;
+      uint32_t phase, pphase;
+    };
+    auto advance = [&](Pos& q) {
+      if (++q.kb == t.KB) {
+        q.kb = 0;
+        q.tile += gridDim.x;
       }
+      if (++q.s == P.stages) {
+        q.s = 0;
+        q.phase ^= 1;
+      }
+      q.pbuf ^= 1;
+      if (q.pbuf == 0) q.pphase ^= 1;
+    };
+    const float* img[kItems];  // load side: image base (+ channel quad) of each item's rows
+    auto set_images = [&](int tile) {
+#pragma unroll
+      for (int it = 0; it < kItems; ++it) {
+        if (VARIANT == DCN_VARIANT_TORCH)
+          img[it] = P.xt + (size_t)decode_inst(t, tile * t.Rt + item_il[it]).b * img_stride + quad * 4;
+        else
+          img[it] = P.xt + (size_t)(tile / t.pix_blocks) * img_stride;
+      }
+    };
+    // Jittor layout: channel offset / tap slot of this thread's 4 columns inside K block kb
+    auto jit_cols = [&](int kb, int& c, int& tl, bool& ok) {
+      const int j = kb * 64 + quad * 4;
+      const int n = j / g.C;
+      c = j - n * g.C;
+      tl = n - (kb * 64) / g.C;
+      ok = j < g.K;
+    };
+    float4 v[2][4];  // [buffer][corner]
+    auto issue = [&](const Pos& q, int it, int buf) {
+      const PlanEntry* pl = plan + q.pbuf * P.plan_cap;
+      int jc = 0, tl = 0;
+      bool ok = true;
+      if (VARIANT != DCN_VARIANT_TORCH) {
+        jit_cols(q.kb, jc, tl, ok);
+        pl += tl * 128;
+      }
+      const int4 off = *reinterpret_cast<const int4*>(pl[ent_idx[it]].off);
+      const float* base = img[it] + jc;
+      if (P.dbg & 1) {
+        v[buf][0] = v[buf][1] = v[buf][2] = v[buf][3] =
+            make_float4((float)off.x, (float)off.y, (float)off.z, (float)off.w);
+      } else {
+        v[buf][0] = __ldg(reinterpret_cast<const float4*>(base + off.x));
+        v[buf][1] = __ldg(reinterpret_cast<const float4*>(base + off.y));
+        v[buf][2] = __ldg(reinterpret_cast<const float4*>(base + off.z));
+        v[buf][3] = __ldg(reinterpret_cast<const float4*>(base + off.w));
+      }
+    };
+    Pos cur{(int)blockIdx.x, 0, 0, 0, 0u, 0u};
+    if (cur.tile < t.num_tiles) {
+      set_images(cur.tile);
+      mbar_wait(&pfull[cur.pbuf], cur.pphase);
+      mbar_wait(&empty[cur.s], cur.phase ^ 1);
+      issue(cur, 0, 0);
+    }
+    while (cur.tile < t.num_tiles) {
+      Pos nxt = cur;
+      advance(nxt);
+      const PlanEntry* pl = plan + cur.pbuf * P.plan_cap;
+      bool col_ok = true;
+      if (VARIANT != DCN_VARIANT_TORCH) {
+        int jc, tl;
+        jit_cols(cur.kb, jc, tl, col_ok);
+        pl += tl * 128;
+      }
+      uint8_t* a_hi = stage_base + (size_t)cur.s * P.stage_bytes;
+      uint8_t* a_lo = a_hi + kATile;
+#pragma unroll
+      for (int it = 0; it < kItems; ++it) {
+        // keep the L1 fed: next item first
+        if (it < kItems - 1) {
+          issue(cur, it + 1, (it + 1) & 1);
+        } else if (nxt.tile < t.num_tiles) {
+          if (nxt.tile != cur.tile) set_images(nxt.tile);
+          mbar_wait(&pfull[nxt.pbuf], nxt.pphase);
+          mbar_wait(&empty[nxt.s], nxt.phase ^ 1);
+          issue(nxt, 0, 0);
+        }
+        float4 w = *reinterpret_cast<const float4*>(pl[ent_idx[it]].w);
+        if (VARIANT != DCN_VARIANT_TORCH && !col_ok) w = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* c4 = v[it & 1];
+        float4 r;
+        r.x = fmaf(c4[3].x, w.w, fmaf(c4[2].x, w.z, fmaf(c4[1].x, w.y, c4[0].x * w.x)));
+        r.y = fmaf(c4[3].y, w.w, fmaf(c4[2].y, w.z, fmaf(c4[1].y, w.y, c4[0].y * w.x)));
+        r.z = fmaf(c4[3].z, w.w, fmaf(c4[2].z, w.z, fmaf(c4[1].z, w.y, c4[0].z * w.x)));
+        r.w = fmaf(c4[3].w, w.w, fmaf(c4[2].w, w.z, fmaf(c4[1].w, w.y, c4[0].w * w.x)));
+        uint2 hi, lo;
+        split4(r, hi, lo);
+        if (!(P.dbg & 4) || hi.x == 0x12345678u) {
+          *reinterpret_cast<uint2*>(a_hi + st_off[it]) = hi;
+          *reinterpret_cast<uint2*>(a_lo + st_off[it]) = lo;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&full[cur.s]);
+        mbar_arrive(&pempty[cur.pbuf]);
+      }
+      cur = nxt;
     }
   }
 
@@ -501,6 +554,8 @@ int umma_forward_fp32(const Geo& g, const float* x, const float* off, const floa
   // Two stages are enough to overlap the (fast) MMAs with the (slow) gather, and every KB of
   // shared memory not taken is L1 for the gather's footprint (L1 + smem share 256 KB).
   int want = 2;
+  P.dbg = 0;
+  if (const char* e = getenv("DCN_FWD_DBG")) P.dbg = atoi(e);
   if (const char* e = getenv("DCN_FWD_STAGES")) want = atoi(e);
   if (want < 2) want = 2;
   if (want > kMaxStages) want = kMaxStages;

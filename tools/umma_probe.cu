@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128) umma_test_kernel(const float* __restrict_
                                                         const float* __restrict__ Bm,
                                                         float* __restrict__ D) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int KT = 64 * KB;
   constexpr int A_TILE = 128 * 64 * 2, B_TILE = N * 64 * 2;
   uint8_t* sA = smem;
