@@ -417,13 +417,15 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(Geo g, const float* __re
 
 int simt_backward(const Geo& g, int flags, const float* x, const Tap* plan, const float* wt,
                   const float* gout, float* gx, float* goff, float* gw, float* gb,
-                  cudaStream_t st) {
+                  cudaStream_t st, int parts) {
   const bool want_gx = !(flags & DCN_FLAG_NO_GRAD_X) && gx != nullptr;
-  if (want_gx && !(flags & DCN_FLAG_ACCUM_GRAD_X))
-    DCN_CUDA_TRY(cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)g.B * g.C * g.H * g.W, st));
-  DCN_CUDA_TRY(cudaMemsetAsync(goff, 0, sizeof(float) * (size_t)g.B * 2 * g.N * g.HW, st));
-  DCN_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.O * g.K, st));
-  {
+  if (parts & SIMT_BWD_DATA) {
+    if (want_gx && !(flags & DCN_FLAG_ACCUM_GRAD_X))
+      DCN_CUDA_TRY(cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)g.B * g.C * g.H * g.W, st));
+    DCN_CUDA_TRY(cudaMemsetAsync(goff, 0, sizeof(float) * (size_t)g.B * 2 * g.N * g.HW, st));
+  }
+  if (parts & SIMT_BWD_WEIGHT) DCN_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.O * g.K, st));
+  if (parts & SIMT_BWD_DATA) {
     dim3 grid((g.HW + TM - 1) / TM, (g.K + TN - 1) / TN, g.B);
     {
       KernelScope scope("bwd_data_kernel", st);
@@ -437,7 +439,7 @@ int simt_backward(const Geo& g, int flags, const float* x, const Tap* plan, cons
     offset_scale_kernel<<<(unsigned)min((total + 255) / 256, (size_t)8192), 256, 0, st>>>(g, goff);
     DCN_KERNEL_CHECK("offset_scale_kernel");
   }
-  {
+  if (parts & SIMT_BWD_WEIGHT) {
     const int tiles = ((g.O + TM - 1) / TM) * ((g.K + TN - 1) / TN);
     const int chunks = ((g.HW + TK - 1) / TK) * g.B;
     int splits = max(1, min(chunks, (148 * 8 + tiles - 1) / tiles));
@@ -451,7 +453,7 @@ int simt_backward(const Geo& g, int flags, const float* x, const Tap* plan, cons
       bwd_weight_kernel<DCN_VARIANT_JITTOR><<<grid, 256, 0, st>>>(g, cps, x, plan, gout, gw);
     DCN_KERNEL_CHECK("bwd_weight_kernel");
   }
-  if (gb) {
+  if (gb && (parts & SIMT_BWD_BIAS)) {
     bias_grad_kernel<<<g.O, 256, 0, st>>>(g, gout, gb);
     DCN_KERNEL_CHECK("bias_grad_kernel");
   }

@@ -42,6 +42,8 @@ constexpr uint32_t kATile = 128 * 64 * 2;                        // one bf16 A i
 constexpr uint32_t kAMnLbo = 1024, kAMnSbo = 2048;               // MN-major A: atom strides
 constexpr int kMaxStages = 4;
 
+enum { MODE_FWD = 0, MODE_WGRAD = 1 };
+
 struct FwdParams {
   Geo g;
   Tiling t;
@@ -50,6 +52,13 @@ struct FwdParams {
   const uint8_t* wtiles;
   const float* bias;
   float* out;
+  // weight-gradient mode (MODE_WGRAD): gW[o, j] += sum_rows gout[row, o] * S[row, j]
+  const float* gout;
+  float* gw;
+  int nslices, nchunks, kb_per_slice;  // CTA = (K slice, chunk of row tiles)
+  int o_blocks;                        // ceil(O / 128) accumulators
+  int n_gbuf;                          // 1 or 2 buffers for the converted grad_out tile
+  uint32_t g_img;                      // bytes of one bf16 image of the grad_out tile: o_blocks*128 rows x 128 B
   int stages;
   int dbg;             // DCN_FWD_DBG timing experiments (results invalid when non-zero)
   int plan_cap;        // plan entries per buffer (n_ent rounded up to 256)
@@ -156,17 +165,19 @@ __device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
   split_pair(v.z, v.w, hi.y, lo.y);
 }
 
-template <int VARIANT>
-__global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_constant__ FwdParams P) {
+template <int VARIANT, int MODE>
+__global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic (a uintptr_t round trip would lose the shared
   // address space and turn every LDS/STS below into a slow generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const Geo& g = P.g;
   const Tiling& t = P.t;
-  // carve-up: [stages x (A_hi | A_lo | B_hi | B_lo)] [plan x2] [barriers]
+  // carve-up: [stages x (A_hi | A_lo | B_hi | B_lo)] [grad_out tile buffers (WGRAD)] [plan x2] [barriers]
   uint8_t* stage_base = smem;
-  PlanEntry* plan = reinterpret_cast<PlanEntry*>(smem + (size_t)P.stages * P.stage_bytes);
+  uint8_t* gbuf_base = smem + (size_t)P.stages * P.stage_bytes;
+  const uint32_t gbuf_bytes = MODE == MODE_WGRAD ? 4u * P.g_img : 0u;  // 2 row halves x (hi | lo)
+  PlanEntry* plan = reinterpret_cast<PlanEntry*>(gbuf_base + (size_t)(MODE == MODE_WGRAD ? P.n_gbuf : 0) * gbuf_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(plan + 2 * P.plan_cap);
   uint64_t* full = bars;                   // [stages]
   uint64_t* empty = bars + kMaxStages;     // [stages]
@@ -174,14 +185,31 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
   uint64_t* tempty = tfull + 2;            // [2]
   uint64_t* pfull = tempty + 2;            // [2] plan ring
   uint64_t* pempty = pfull + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + 2);
+  uint64_t* afull = pempty + 2;            // [2] converted grad_out tile (WGRAD)
+  uint64_t* aempty = afull + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int O = g.O;
+  // which (tile, K block) pairs this CTA walks: forward = all K blocks of every gridDim-th tile;
+  // weight gradient = one slice of K blocks for one chunk of the row tiles
+  int tile0, tile_step, kb0, kb1;
+  if (MODE == MODE_FWD) {
+    tile0 = blockIdx.x;
+    tile_step = gridDim.x;
+    kb0 = 0;
+    kb1 = t.KB;
+  } else {
+    const int slice = blockIdx.x % P.nslices;
+    tile0 = blockIdx.x / P.nslices;
+    tile_step = P.nchunks;
+    kb0 = slice * P.kb_per_slice;
+    kb1 = min(t.KB, kb0 + P.kb_per_slice);
+  }
 
   if (tid == 0) {
     for (int s = 0; s < P.stages; ++s) {
-      mbar_init(&full[s], kProdWarps + 1);
+      mbar_init(&full[s], MODE == MODE_FWD ? kProdWarps + 1 : kProdWarps);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -189,6 +217,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
       mbar_init(&tempty[a], kEpiWarps);
       mbar_init(&pfull[a], kPlanWarps);
       mbar_init(&pempty[a], kProdWarps);
+      mbar_init(&afull[a], kEpiWarps);
+      mbar_init(&aempty[a], 1);
     }
     fence_barrier_init();
   }
@@ -205,10 +235,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < kEpiWarps) {
-    // ================================================================ epilogue
+    if constexpr (MODE == MODE_FWD) {
+    // ================================================================ epilogue (forward)
     uint32_t acc_phase = 0;
     int acc = 0;
-    for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < t.num_tiles; tile += tile_step) {
       const int m = warp * 32 + lane;  // TMEM lane == tile row
       size_t out_off = 0;
       bool valid;
@@ -243,13 +274,95 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    } else {
+    // ================================================================ grad_out converter, then the
+    // one-shot epilogue (weight gradient).  Per row tile: g[row m, o] = gout[b(m), o, r(m)] is
+    // split into bf16 hi/lo and stored K-major ([o][64 rows] per row half) as the A operand.
+    const int ct = tid;  // 0..127
+    const int O_pad = P.o_blocks * 128;
+    int ab = 0;
+    uint32_t aphase = 0;
+    for (int tile = tile0; tile < t.num_tiles; tile += tile_step) {
+      mbar_wait_relaxed(&aempty[ab], aphase ^ 1);
+      uint8_t* gb = gbuf_base + (size_t)ab * gbuf_bytes;
+      // items: (o, group of 4 consecutive tile rows); lanes run along the row groups
+      for (int item = ct; item < O_pad * 32; item += kEpiWarps * 32) {
+        const int o = item >> 5, mq = item & 31, m = mq * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o < O) {
+          if (VARIANT == DCN_VARIANT_TORCH) {
+            // rows m..m+3 = channels 4*quad..+3 of class instance il (dcn_umma_common.cuh:Tiling)
+            const int quad = m / (4 * t.Rt), il = (m >> 2) % t.Rt;
+            const TileRowInfo ri = decode_inst(t, tile * t.Rt + il);
+            if (ri.valid) {
+              const float* src = P.gout + ((size_t)ri.b * O + o) * g.HW + ri.r0 +
+                                 (size_t)(ri.chunk * t.Gt + 4 * quad) * t.R;
+              v.x = __ldg(src);
+              v.y = __ldg(src + t.R);
+              v.z = __ldg(src + 2 * (size_t)t.R);
+              v.w = __ldg(src + 3 * (size_t)t.R);
+            }
+          } else {
+            const int b = tile / t.pix_blocks, p = (tile - b * t.pix_blocks) * 128 + m;
+            const float* src = P.gout + ((size_t)b * O + o) * g.HW + p;
+            if (p + 3 < g.HW && (g.HW & 3) == 0) {
+              v = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+              if (p < g.HW) v.x = __ldg(src);
+              if (p + 1 < g.HW) v.y = __ldg(src + 1);
+              if (p + 2 < g.HW) v.z = __ldg(src + 2);
+              if (p + 3 < g.HW) v.w = __ldg(src + 3);
+            }
+          }
+        }
+        uint2 hi, lo;
+        split4(v, hi, lo);
+        // image of row half h: [hi: O_pad x 64][lo: O_pad x 64]
+        uint8_t* img_h = gb + (size_t)(m >> 6) * 2 * P.g_img;
+        const uint32_t so = kmajor_sw128_off(o, m & 63);
+        *reinterpret_cast<uint2*>(img_h + so) = hi;
+        *reinterpret_cast<uint2*>(img_h + P.g_img + so) = lo;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&afull[ab]);
+      if (P.n_gbuf == 2) {
+        ab ^= 1;
+        if (ab == 0) aphase ^= 1;
+      } else {
+        aphase ^= 1;
+      }
+    }
+    // ---- epilogue: accumulators -> gW (one red.global.add per element; each CTA owns a K slice
+    // for a chunk of the rows, so O*K*nchunks adds in total)
+    mbar_wait_relaxed(&tfull[0], 0);
+    tc_fence_after();
+    const int ncols = (kb1 - kb0) * 64;
+    for (int ob = 0; ob < P.o_blocks; ++ob) {
+      const int o = ob * 128 + warp * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ob * ncols);
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        if (o < O) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int j = kb0 * 64 + c0 + i;
+            if (j < g.K) atomicAdd(P.gw + (size_t)o * g.K + j, v[i]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    }
   } else if (warp == kEpiWarps) {
-    // ================================================================ MMA issuer
+    if constexpr (MODE == MODE_FWD) {
+    // ================================================================ MMA issuer (forward)
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, O, VARIANT == DCN_VARIANT_TORCH, false);
       int s = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < t.num_tiles; tile += tile_step) {
         mbar_wait_relaxed(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * O);
@@ -288,13 +401,74 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp == kEpiWarps + 1) {
-    // ================================================================ weight (B) loader
+    } else {
+    // ================================================================ MMA issuer (weight gradient)
+    // D[o, j] += g^T[o, rows] * S[rows, j]: A = converted grad_out tile (K-major, K = tile rows),
+    // B = the sample image the gather warps wrote — the forward's A image read as a B operand:
+    //   Torch  image (rows contiguous per column) = K-major B, 8-column groups 2048 B apart,
+    //          row half h at +1024;
+    //   Jittor image (columns contiguous per row) = MN-major B, 8-row groups 1024 B apart.
     if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 64, false, VARIANT != DCN_VARIANT_TORCH);
+      const int ncols = (kb1 - kb0) * 64;
+      int s = 0, ab = 0;
+      uint32_t phase = 0, aphase = 0;
+      bool first_tile = true;
+      for (int tile = tile0; tile < t.num_tiles; tile += tile_step) {
+        mbar_wait_relaxed(&afull[ab], aphase, 64);
+        const uint32_t gb = smem_u32(gbuf_base + (size_t)ab * gbuf_bytes);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait_relaxed(&full[s], phase, 64);
+          tc_fence_after();
+          const uint32_t s_hi = smem_u32(stage_base + (size_t)s * P.stage_bytes);
+          const uint32_t s_lo = s_hi + kATile;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {  // 8 steps of 16 tile rows
+            const int h = ks >> 2, k4 = ks & 3;
+            uint64_t dsh, dsl;
+            if (VARIANT == DCN_VARIANT_TORCH) {
+              dsh = make_sdesc_sw128(s_hi + h * 1024 + k4 * 32, 16, 2048);
+              dsl = make_sdesc_sw128(s_lo + h * 1024 + k4 * 32, 16, 2048);
+            } else {
+              dsh = make_sdesc_sw128(s_hi + ks * 2048, 1024, 1024);
+              dsl = make_sdesc_sw128(s_lo + ks * 2048, 1024, 1024);
+            }
+            for (int ob = 0; ob < P.o_blocks; ++ob) {
+              const uint32_t g_hi = gb + h * 2 * P.g_img + ob * (128 * 128) + k4 * 32;
+              const uint32_t g_lo = g_hi + P.g_img;
+              const uint64_t dgh = make_sdesc_sw128(g_hi, 16, 1024);
+              const uint64_t dgl = make_sdesc_sw128(g_lo, 16, 1024);
+              const uint32_t d_tmem = tmem_base + (uint32_t)(ob * ncols + (kb - kb0) * 64);
+              umma_bf16(d_tmem, dgh, dsh, idesc, (first_tile && ks == 0) ? 0u : 1u);
+              umma_bf16(d_tmem, dgh, dsl, idesc, 1u);
+              umma_bf16(d_tmem, dgl, dsh, idesc, 1u);
+            }
+          }
+          umma_commit(&empty[s]);
+          if (++s == P.stages) {
+            s = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&aempty[ab]);  // grad_out tile buffer reusable
+        first_tile = false;
+        if (P.n_gbuf == 2) {
+          ab ^= 1;
+          if (ab == 0) aphase ^= 1;
+        } else {
+          aphase ^= 1;
+        }
+      }
+      umma_commit(&tfull[0]);
+    }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    // ================================================================ weight (B) loader (forward only)
+    if (MODE == MODE_FWD && lane == 0) {
       int s = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < t.KB; ++kb) {
+      for (int tile = tile0; tile < t.num_tiles; tile += tile_step) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_relaxed(&empty[s], phase ^ 1);
           uint8_t* dst = stage_base + (size_t)s * P.stage_bytes + 2 * kATile;
           mbar_arrive_expect_tx(&full[s], 2 * P.b_tile);
@@ -313,14 +487,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
     int pbuf = 0;
     uint32_t pphase = 0;
     PlanWork pw[kPlanPerThread];
-    if ((int)blockIdx.x < t.num_tiles) {
+    if (tile0 < t.num_tiles) {
 #pragma unroll
       for (int u = 0; u < kPlanPerThread; ++u)
         if (pt + u * kPlanThreads < n_ent)
-          plan_prepare<VARIANT>(g, t, P.off, blockIdx.x, 0, pt + u * kPlanThreads, pw[u]);
+          plan_prepare<VARIANT>(g, t, P.off, tile0, kb0, pt + u * kPlanThreads, pw[u]);
     }
-    for (int tile = blockIdx.x; tile < t.num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < t.KB; ++kb) {
+    for (int tile = tile0; tile < t.num_tiles; tile += tile_step) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         PlanEntry* pl = plan + pbuf * P.plan_cap;
         mbar_wait_relaxed(&pempty[pbuf], pphase ^ 1, 64);
         // finish this K block's entries (their offset loads were issued one block ago) ...
@@ -340,9 +514,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
         if (lane == 0) mbar_arrive(&pfull[pbuf]);
         // ... and start the next block's
         int ntile = tile, nkb = kb + 1;
-        if (nkb == t.KB) {
-          nkb = 0;
-          ntile = tile + gridDim.x;
+        if (nkb == kb1) {
+          nkb = kb0;
+          ntile = tile + tile_step;
         }
         if (ntile < t.num_tiles && !(P.dbg & 2)) {
 #pragma unroll
@@ -388,9 +562,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
       uint32_t phase, pphase;
     };
     auto advance = [&](Pos& q) {
-      if (++q.kb == t.KB) {
-        q.kb = 0;
-        q.tile += gridDim.x;
+      if (++q.kb == kb1) {
+        q.kb = kb0;
+        q.tile += tile_step;
       }
       if (++q.s == P.stages) {
         q.s = 0;
@@ -438,7 +612,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_fwd_kernel(const __grid_c
         v[buf][3] = __ldg(reinterpret_cast<const float4*>(base + off.w));
       }
     };
-    Pos cur{(int)blockIdx.x, 0, 0, 0, 0u, 0u};
+    Pos cur{tile0, kb0, 0, 0, 0u, 0u};
     if (cur.tile < t.num_tiles) {
       set_images(cur.tile);
       mbar_wait(&pfull[cur.pbuf], cur.pphase);
@@ -508,23 +682,54 @@ static uint32_t pow2_cols(int cols) {
   return c;
 }
 
+static int num_sms() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+static bool tiling_ok(const Geo& g, Tiling* t) {
+  if (!make_tiling(g, t)) return false;
+  if (g.variant == DCN_VARIANT_TORCH && t->Rt * 64 > kPlanMax) return false;
+  if (g.variant == DCN_VARIANT_JITTOR && 128 * t->taps_per_kb > kPlanMax) return false;
+  static_assert(kPlanMax == kPlanPerThread * kPlanThreads, "plan slots");
+  return true;
+}
+
 bool umma_fwd_supported(const Geo& g, int operand) {
   if (operand != DCN_OPERAND_FP32) return false;
   if (g.O % 16 || g.O < 16 || g.O > 256) return false;
   Tiling t;
-  if (!make_tiling(g, &t)) return false;
-  if (g.variant == DCN_VARIANT_TORCH && t.Rt * 64 > kPlanMax) return false;
-  static_assert(kPlanMax == kPlanPerThread * kPlanThreads, "plan slots");
-  if (g.variant == DCN_VARIANT_JITTOR && 128 * t.taps_per_kb > kPlanMax) return false;
-  return true;
+  return tiling_ok(g, &t);
 }
+
+bool umma_wgrad_supported(const Geo& g, int operand) {
+  if (operand != DCN_OPERAND_FP32) return false;
+  if (g.O > 256) return false;
+  Tiling t;
+  return tiling_ok(g, &t);
+}
+
+size_t umma_xt_bytes(const Geo& g) { return align_up(sizeof(float) * (size_t)g.B * xt_image_stride(g), 1024); }
 
 size_t umma_fwd_workspace(const Geo& g) {
   Tiling t;
   make_tiling(g, &t);
-  const size_t xt = align_up(sizeof(float) * (size_t)g.B * xt_image_stride(g), 1024);
-  const size_t wt = align_up((size_t)t.KB * 2 * g.O * 128, 1024);
-  return xt + wt;
+  return umma_xt_bytes(g) + align_up((size_t)t.KB * 2 * g.O * 128, 1024);
+}
+
+static void common_params(const Geo& g, FwdParams& P) {
+  const int n_ent = g.variant == DCN_VARIANT_TORCH ? P.t.Rt * 64 : 128 * P.t.taps_per_kb;
+  P.plan_cap = (n_ent + 255) / 256 * 256;
+  P.dbg = 0;
+  if (const char* e = getenv("DCN_FWD_DBG")) P.dbg = atoi(e);
+  P.gout = nullptr;
+  P.gw = nullptr;
+  P.nslices = P.nchunks = P.kb_per_slice = 1;
+  P.o_blocks = 1;
+  P.n_gbuf = 0;
+  P.g_img = 0;
 }
 
 int umma_forward_fp32(const Geo& g, const float* x, const float* off, const float* wt, const float* bias,
@@ -535,8 +740,9 @@ int umma_forward_fp32(const Geo& g, const float* x, const float* off, const floa
     set_error("umma forward: shape not tileable");
     return DCN_ERR_UNSUPPORTED;
   }
+  common_params(g, P);
   float* xt = (float*)workspace;
-  uint8_t* wtiles = (uint8_t*)workspace + align_up(sizeof(float) * (size_t)g.B * xt_image_stride(g), 1024);
+  uint8_t* wtiles = (uint8_t*)workspace + umma_xt_bytes(g);
   int rc;
   if ((rc = launch_nchw_to_nhwc(g, P.t, x, xt, st))) return rc;
   if ((rc = launch_weight_tiles_fwd(g, P.t, wt, wtiles, st))) return rc;
@@ -547,15 +753,11 @@ int umma_forward_fp32(const Geo& g, const float* x, const float* off, const floa
   P.out = out;
   P.b_tile = (uint32_t)g.O * 128;
   P.stage_bytes = 2 * kATile + 2 * P.b_tile;
-  const int n_ent = g.variant == DCN_VARIANT_TORCH ? P.t.Rt * 64 : 128 * P.t.taps_per_kb;
-  P.plan_cap = (n_ent + 255) / 256 * 256;
   const size_t fixed = 2 * (size_t)P.plan_cap * sizeof(PlanEntry) + 256 + 1024;  // plan ring, barriers, align slack
   int stages = (int)((227 * 1024 - fixed) / P.stage_bytes);
-  // Two stages are enough to overlap the (fast) MMAs with the (slow) gather, and every KB of
-  // shared memory not taken is L1 for the gather's footprint (L1 + smem share 256 KB).
-  int want = 2;
-  P.dbg = 0;
-  if (const char* e = getenv("DCN_FWD_DBG")) P.dbg = atoi(e);
+  // A few stages are enough to overlap the (fast) MMAs with the (slow) gather; every KB of
+  // shared memory not taken stays L1 for the gather's footprint (L1 + smem share 256 KB).
+  int want = 3;
   if (const char* e = getenv("DCN_FWD_STAGES")) want = atoi(e);
   if (want < 2) want = 2;
   if (want > kMaxStages) want = kMaxStages;
@@ -566,21 +768,74 @@ int umma_forward_fp32(const Geo& g, const float* x, const float* off, const floa
   }
   P.tmem_cols = pow2_cols(2 * g.O);
   const size_t smem = (size_t)P.stages * P.stage_bytes + fixed;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = num_sms();
   const int grid = P.t.num_tiles < sms ? P.t.num_tiles : sms;
   KernelScope scope("umma_fwd_kernel", st);
   if (g.variant == DCN_VARIANT_TORCH) {
-    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel<DCN_VARIANT_TORCH>,
+    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<DCN_VARIANT_TORCH, MODE_FWD>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_fwd_kernel<DCN_VARIANT_TORCH><<<grid, kFwdThreads, smem, st>>>(P);
+    umma_gemm_kernel<DCN_VARIANT_TORCH, MODE_FWD><<<grid, kFwdThreads, smem, st>>>(P);
   } else {
-    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel<DCN_VARIANT_JITTOR>,
+    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<DCN_VARIANT_JITTOR, MODE_FWD>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_fwd_kernel<DCN_VARIANT_JITTOR><<<grid, kFwdThreads, smem, st>>>(P);
+    umma_gemm_kernel<DCN_VARIANT_JITTOR, MODE_FWD><<<grid, kFwdThreads, smem, st>>>(P);
   }
   DCN_KERNEL_CHECK("umma_fwd_kernel");
+  return DCN_OK;
+}
+
+// grad_weight[O, K] (zeroed here) = sum over all rows of gout^T * S, S re-sampled by the same
+// plan / gather warps as the forward pass.  xt = channels-last staging copy (already built).
+int umma_wgrad_fp32(const Geo& g, const float* xt, const float* off, const float* gout, float* gw,
+                    cudaStream_t st) {
+  FwdParams P;
+  P.g = g;
+  if (!make_tiling(g, &P.t)) {
+    set_error("umma wgrad: shape not tileable");
+    return DCN_ERR_UNSUPPORTED;
+  }
+  common_params(g, P);
+  DCN_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.O * g.K, st));
+  P.xt = xt;
+  P.off = off;
+  P.wtiles = nullptr;
+  P.bias = nullptr;
+  P.out = nullptr;
+  P.gout = gout;
+  P.gw = gw;
+  P.o_blocks = (g.O + 127) / 128;
+  P.g_img = (uint32_t)P.o_blocks * 128 * 128;
+  P.n_gbuf = P.o_blocks == 1 ? 2 : 1;
+  const int kb_max = 8 / P.o_blocks;  // 512 TMEM columns
+  P.nslices = (P.t.KB + kb_max - 1) / kb_max;
+  P.kb_per_slice = (P.t.KB + P.nslices - 1) / P.nslices;
+  P.nslices = (P.t.KB + P.kb_per_slice - 1) / P.kb_per_slice;
+  const int sms = num_sms();
+  P.nchunks = sms / P.nslices;
+  if (P.nchunks < 1) P.nchunks = 1;
+  if (P.nchunks > P.t.num_tiles) P.nchunks = P.t.num_tiles;
+  P.b_tile = 0;
+  P.stage_bytes = 2 * kATile;
+  P.stages = 2;
+  P.tmem_cols = pow2_cols(P.o_blocks * P.kb_per_slice * 64);
+  const size_t fixed = 2 * (size_t)P.plan_cap * sizeof(PlanEntry) + 256 + 1024;
+  const size_t smem = (size_t)P.stages * P.stage_bytes + (size_t)P.n_gbuf * 4 * P.g_img + fixed;
+  if (smem > 227 * 1024) {
+    set_error("umma wgrad: %zu bytes of shared memory needed", smem);
+    return DCN_ERR_UNSUPPORTED;
+  }
+  const int grid = P.nslices * P.nchunks;
+  KernelScope scope("umma_bwd_weight_kernel", st);
+  if (g.variant == DCN_VARIANT_TORCH) {
+    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<DCN_VARIANT_TORCH, MODE_WGRAD>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_gemm_kernel<DCN_VARIANT_TORCH, MODE_WGRAD><<<grid, kFwdThreads, smem, st>>>(P);
+  } else {
+    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<DCN_VARIANT_JITTOR, MODE_WGRAD>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_gemm_kernel<DCN_VARIANT_JITTOR, MODE_WGRAD><<<grid, kFwdThreads, smem, st>>>(P);
+  }
+  DCN_KERNEL_CHECK("umma_bwd_weight_kernel");
   return DCN_OK;
 }
 
