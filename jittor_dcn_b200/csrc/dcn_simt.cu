@@ -415,6 +415,14 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(Geo g, const float* __re
   }
 }
 
+int launch_offset_scale(const Geo& g, float* goff, cudaStream_t st) {
+  const size_t total = (size_t)g.B * 2 * g.N * g.HW;
+  KernelScope scope("offset_scale_kernel", st);
+  offset_scale_kernel<<<(unsigned)min((total + 255) / 256, (size_t)8192), 256, 0, st>>>(g, goff);
+  DCN_KERNEL_CHECK("offset_scale_kernel");
+  return DCN_OK;
+}
+
 int simt_backward(const Geo& g, int flags, const float* x, const Tap* plan, const float* wt,
                   const float* gout, float* gx, float* goff, float* gw, float* gb,
                   cudaStream_t st, int parts) {

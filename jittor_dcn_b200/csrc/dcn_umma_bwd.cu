@@ -1,11 +1,15 @@
-// dcn_umma_bwd.cu — backward pass on the tensor path.
+// dcn_umma_bwd.cu — backward pass on the tensor path: orchestration.
 //
-//   grad_weight   tcgen05 GEMM gW = gout^T * S with S re-sampled by the forward's plan / gather
-//                 warps (dcn_umma_fwd.cu, MODE_WGRAD); nothing is materialised.
-//   grad_x, grad_offset   (this revision) generic CUDA-core kernel: gA = gout * Wm, bilinear
-//                 col2im scatter with red.global.add.f32 and coordinate-gradient reduction
-//                 (dcn_simt.cu:bwd_data_kernel).
+//   grad_x, grad_offset   dcn_umma_bwd_data.cu: tcgen05 GEMM gA = gout * Wm whose TMEM accumulator is
+//                 consumed in place by the bilinear col2im scatter (red.global.add.f32 into a
+//                 channels-last grad copy) and the warp-shuffle coordinate-gradient reduction
+//                 (Torch column layout).  The Jittor column layout still uses the generic
+//                 CUDA-core kernel (dcn_simt.cu:bwd_data_kernel) for this part.
+//   grad_weight   dcn_umma_fwd.cu (MODE_WGRAD): tcgen05 GEMM gW = gout^T * S, S re-sampled by the
+//                 forward's plan / gather warps; nothing is materialised.
 //   grad_bias     column sums of gout (dcn_simt.cu:bias_grad_kernel).
+#include <cstdlib>
+
 #include "dcn_umma.h"
 #include "dcn_umma_common.cuh"
 
@@ -15,28 +19,57 @@ bool umma_wgrad_supported(const Geo& g, int operand);
 size_t umma_xt_bytes(const Geo& g);
 int umma_wgrad_fp32(const Geo& g, const float* xt, const float* off, const float* gout, float* gw,
                     cudaStream_t st);
+bool umma_bwd_data_supported(const Geo& g, int operand);
+size_t umma_bwd_data_wtile_bytes(const Geo& g);
+int umma_bwd_data_fp32(const Geo& g, const float* xt, float* gxt, const float* off, const float* wt,
+                       const float* gout, float* goff, uint8_t* wtiles, cudaStream_t st);
 
 static size_t plan_bytes(const Geo& g) { return align_up(sizeof(Tap) * (size_t)g.B * g.P, 1024); }
 
+static bool use_umma_data(const Geo& g, int operand) {
+  if (const char* e = getenv("DCN_BWD_DATA_SIMT"))
+    if (atoi(e)) return false;
+  return umma_bwd_data_supported(g, operand);
+}
+
 bool umma_bwd_supported(const Geo& g, int operand) { return umma_wgrad_supported(g, operand); }
 
-size_t umma_bwd_workspace(const Geo& g) { return plan_bytes(g) + umma_xt_bytes(g); }
+size_t umma_bwd_workspace(const Geo& g) {
+  // [xt] then either [gxt | Wm^T tiles] (tensor-path data gradient) or [sampling plan] (generic)
+  const size_t a = umma_xt_bytes(g) + umma_bwd_data_wtile_bytes(g);
+  const size_t b = plan_bytes(g);
+  return umma_xt_bytes(g) + (a > b ? a : b);
+}
 
 int umma_backward_fp32(const Geo& g, int flags, const float* x, const float* off, const float* wt,
                        const float* gout, float* gx, float* goff, float* gw, float* gb, void* workspace,
                        cudaStream_t st) {
-  Tap* plan = (Tap*)workspace;
-  float* xt = (float*)((uint8_t*)workspace + plan_bytes(g));
+  float* xt = (float*)workspace;
+  uint8_t* rest = (uint8_t*)workspace + umma_xt_bytes(g);
   Tiling t;
   if (!make_tiling(g, &t)) {
     set_error("umma backward: shape not tileable");
     return DCN_ERR_UNSUPPORTED;
   }
   int rc;
-  if ((rc = launch_plan(g, off, plan, st))) return rc;
-  if ((rc = simt_backward(g, flags, x, plan, wt, gout, gx, goff, gw, gb, st, SIMT_BWD_DATA | SIMT_BWD_BIAS)))
-    return rc;
   if ((rc = launch_nchw_to_nhwc(g, t, x, xt, st))) return rc;
+  const bool want_gx = !(flags & DCN_FLAG_NO_GRAD_X) && gx != nullptr;
+  if (use_umma_data(g, DCN_OPERAND_FP32)) {
+    float* gxt = (float*)rest;
+    uint8_t* wtiles = rest + umma_xt_bytes(g);
+    if (want_gx) DCN_CUDA_TRY(cudaMemsetAsync(gxt, 0, sizeof(float) * (size_t)g.B * xt_image_stride(g), st));
+    DCN_CUDA_TRY(cudaMemsetAsync(goff, 0, sizeof(float) * (size_t)g.B * 2 * g.N * g.HW, st));
+    if ((rc = umma_bwd_data_fp32(g, xt, want_gx ? gxt : nullptr, off, wt, gout, goff, wtiles, st))) return rc;
+    if ((rc = launch_offset_scale(g, goff, st))) return rc;
+    if (want_gx && (rc = launch_nhwc_to_nchw_add(g, t, gxt, gx, (flags & DCN_FLAG_ACCUM_GRAD_X) ? 1 : 0, st)))
+      return rc;
+    if ((rc = simt_backward(g, flags, x, nullptr, wt, gout, gx, goff, gw, gb, st, SIMT_BWD_BIAS))) return rc;
+  } else {
+    Tap* plan = (Tap*)rest;
+    if ((rc = launch_plan(g, off, plan, st))) return rc;
+    if ((rc = simt_backward(g, flags, x, plan, wt, gout, gx, goff, gw, gb, st, SIMT_BWD_DATA | SIMT_BWD_BIAS)))
+      return rc;
+  }
   return umma_wgrad_fp32(g, xt, off, gout, gw, st);
 }
 

@@ -1,0 +1,525 @@
+// dcn_umma_bwd_data.cu — grad_x and grad_offset on the tensor path (Torch column layout).
+//
+// The autograd of train.py:102-134 as ONE kernel per 128-row tile:
+//   GEMM-1    gA[rows, j] = gout[rows, :] * Wm[:, j]              (tcgen05.mma, TMEM accumulator)
+//   scatter   grad_x[corner] += w_corner * gA                     (red.global.add.f32, coalesced:
+//                                                                   32 lanes = 32 contiguous channels
+//                                                                   of the channels-last grad copy)
+//   coord     g_ix, g_iy = sum_c gA * d(sample)/d(ix, iy)         (butterfly warp-shuffle
+//                                                                   reduce-scatter, then one
+//                                                                   red.global per column)
+// gA never leaves TMEM/registers.  Tile rows are ordered (class instance, channel) so that a
+// TMEM lane IS a channel: lane l of warp-quarter q holds, for every column j, the gradient of
+// the sample (channel base(j) + l, sampling point q(r0, j)) — see dcn_umma_common.cuh:Tiling.
+//
+// Warp roles (768 threads, 1 CTA / SM, persistent over row tiles):
+//   warps  0-15  scatter / coord-grad epilogue (quarter = w % 4 of the TMEM lanes, w / 4 = column part)
+//   warp   16    MMA issuer          warp 17  Wm^T tile loader (cp.async.bulk)
+//   warps 18-19  grad_out converter (fp32 -> bf16 hi/lo, K-major A operand, once per tile)
+//   warps 20-23  plan: offsets -> bit-exact coordinate chain -> scatter entries (2-deep ring)
+#include <cstdlib>
+
+#include "dcn_umma.h"
+#include "dcn_umma_common.cuh"
+
+namespace dcn {
+
+using namespace ptx;
+
+namespace bd {
+
+constexpr int kScatWarps = 16, kConvWarps = 2, kPlanWarps = 4;
+constexpr int kMmaWarp = kScatWarps, kLoadWarp = kScatWarps + 1;
+constexpr int kFirstConvWarp = kScatWarps + 2, kFirstPlanWarp = kFirstConvWarp + kConvWarps;
+constexpr int kThreads = (kFirstPlanWarp + kPlanWarps) * 32;  // 768
+constexpr int kPlanThreads = kPlanWarps * 32;
+constexpr int kPlanPerThread = 8;
+constexpr int kPlanMax = kPlanThreads * kPlanPerThread;  // 1024 entries per column block
+constexpr uint32_t kGImg = 128 * 64 * 2;                 // one bf16 image of a grad_out K block
+
+// what the scatter warps need for one (class instance, column): 48 bytes
+struct __align__(16) ScatEntry {
+  int off[4];   // corner offsets inside image b of the channels-last copies (pad pixel if invalid)
+  float w[4];   // corner weights, 0 for invalid corners
+  float fx, fy;
+  int gidx;     // index of grad_offset[b, n, p] (the "x" offset); "y" is N*HW further; -1 = none
+  int pad_;
+};
+
+struct Params {
+  Geo g;
+  Tiling t;
+  const float* xt;       // channels-last x (coordinate gradient needs the corner values)
+  float* gxt;            // channels-last grad_x accumulator (zeroed), may be null
+  const float* off;
+  const float* gout;
+  const uint8_t* wtiles; // [cblocks][OB][hi|lo][ncols x 64] K-major SW128 images of Wm^T
+  float* goff;           // raw g_iy / g_ix accumulators (zeroed); scaled afterwards
+  int Gt, Rt, chunks, num_inst, num_tiles;  // backward tiling (rows = (instance, channel))
+  FastDiv divR, divChunks;
+  int ncols;             // columns (j) per accumulator block: 128 or 64
+  int cblocks;           // ceil(K / ncols)
+  int OB;                // ceil(O / 64) K blocks of the GEMM
+  int plan_cap;          // entries per plan buffer = Rt * ncols
+  uint32_t w_stage;      // bytes of one Wm^T stage = 2 * ncols * 128
+  uint32_t tmem_cols;
+};
+
+struct RowInfo {
+  int b, r0, chunk, valid;
+};
+__device__ __forceinline__ RowInfo decode(const Params& P, int inst) {
+  RowInfo ri;
+  ri.valid = inst < P.num_inst;
+  uint32_t bc, r0, b, ch;
+  P.divR.divmod((uint32_t)(ri.valid ? inst : 0), bc, r0);
+  P.divChunks.divmod(bc, b, ch);
+  ri.b = (int)b;
+  ri.r0 = (int)r0;
+  ri.chunk = (int)ch;
+  return ri;
+}
+
+struct PlanWork {
+  float ox, oy;
+  int h, w, chan_base, gidx, valid;
+};
+
+__device__ __forceinline__ void plan_prepare(const Params& P, int tile, int cb, int e, PlanWork& pw) {
+  const Geo& g = P.g;
+  pw.valid = 0;
+  pw.ox = pw.oy = 0.f;
+  pw.h = pw.w = pw.chan_base = 0;
+  pw.gidx = -1;
+  const int il = e / P.ncols, cc = e - il * P.ncols, j = cb * P.ncols + cc;
+  const RowInfo ri = decode(P, tile * P.Rt + il);
+  if (!ri.valid || j >= g.K) return;
+  uint32_t cbase, q, p, n, h, w;
+  P.t.divP.divmod((uint32_t)(ri.r0 * g.K + j), cbase, q);
+  P.t.divN.divmod(q, p, n);
+  P.t.divWo.divmod(p, h, w);
+  pw.chan_base = (int)cbase * P.t.G + ri.chunk * P.Gt;
+  pw.h = (int)h;
+  pw.w = (int)w;
+  pw.gidx = (ri.b * 2 * g.N + (int)n) * g.HW + (int)p;
+  const float* ob = P.off + (size_t)ri.b * 2 * g.N * g.HW;
+  pw.ox = __ldg(ob + (size_t)n * g.HW + p);
+  pw.oy = __ldg(ob + (size_t)(g.N + n) * g.HW + p);
+  pw.valid = 1;
+}
+
+__device__ __forceinline__ ScatEntry plan_finish(const Geo& g, const PlanWork& pw) {
+  ScatEntry e;
+  const int pad = g.H * g.W * g.C + pw.chan_base;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    e.off[k] = pad;
+    e.w[k] = 0.f;
+  }
+  e.fx = e.fy = 0.f;
+  e.gidx = -1;
+  e.pad_ = 0;
+  if (pw.valid) {
+    const Tap tp = tap_of(g, pw.h, pw.w, pw.ox, pw.oy);
+    const unsigned m = corner_mask(tp, g.H, g.W);
+    if (m) {
+      float cw[4];
+      corner_weights(tp, cw);
+      const int base = (tp.y0 * g.W + tp.x0) * g.C + pw.chan_base;
+      if (m & 1u) { e.off[0] = base;                   e.w[0] = cw[0]; }
+      if (m & 2u) { e.off[1] = base + g.C;             e.w[1] = cw[1]; }
+      if (m & 4u) { e.off[2] = base + g.W * g.C;       e.w[2] = cw[2]; }
+      if (m & 8u) { e.off[3] = base + g.W * g.C + g.C; e.w[3] = cw[3]; }
+      e.fx = tp.fx;
+      e.fy = tp.fy;
+      e.gidx = pw.gidx;  // a point with no valid corner has zero coordinate gradient
+    }
+  }
+  return e;
+}
+
+template <int GT>  // channels per class instance in a tile: 16, 32 or 64
+__global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_constant__ Params P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const Geo& g = P.g;
+  // carve-up: [grad_out tile: OB x (hi | lo)] [2 Wm^T stages] [plan x2] [barriers]
+  uint8_t* gtile = smem;
+  uint8_t* wstage = gtile + (size_t)P.OB * 2 * kGImg;
+  ScatEntry* plan = reinterpret_cast<ScatEntry*>(wstage + 2 * (size_t)P.w_stage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(plan + 2 * P.plan_cap);
+  uint64_t* wfull = bars;        // [2]
+  uint64_t* wempty = bars + 2;   // [2]
+  uint64_t* tfull = bars + 4;    // [2]
+  uint64_t* tempty = bars + 6;   // [2]
+  uint64_t* pfull = bars + 8;    // [2]
+  uint64_t* pempty = bars + 10;  // [2]
+  uint64_t* gfull = bars + 12;   // [1]
+  uint64_t* gempty = bars + 13;  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ncols = P.ncols;
+
+  if (tid == 0) {
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&wfull[a], 1);
+      mbar_init(&wempty[a], 1);
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], kScatWarps);
+      mbar_init(&pfull[a], kPlanWarps);
+      mbar_init(&pempty[a], kScatWarps);
+    }
+    mbar_init(gfull, kConvWarps);
+    mbar_init(gempty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(P.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const size_t img_stride = xt_image_stride(g);
+
+  if (warp < kScatWarps) {
+    // ================================================================ scatter + coordinate gradient
+    const int quarter = warp & 3, part = warp >> 2;
+    const int m = quarter * 32 + lane;          // TMEM lane = tile row
+    const int il = m / GT, i_lo = m % GT;       // class instance within the tile, channel
+    const int cols_per_part = ncols >> 2;       // 32 or 16
+    constexpr int RW = GT >= 32 ? 32 : 16;      // lanes that share one sampling point
+    const unsigned grp_mask = RW == 32 ? 0xffffffffu : (0xffffu << (lane & 16));
+    const int gl = lane & (RW - 1);             // lane inside its reduction group
+    int acc = 0, pb = 0;
+    uint32_t acc_phase = 0, pphase = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      const RowInfo ri = decode(P, tile * P.Rt + il);
+      const float* ximg = P.xt + (size_t)ri.b * img_stride + i_lo;
+      float* gimg = P.gxt ? P.gxt + (size_t)ri.b * img_stride + i_lo : nullptr;
+      for (int cb = 0; cb < P.cblocks; ++cb) {
+        mbar_wait_relaxed(&tfull[acc], acc_phase, 32);
+        mbar_wait_relaxed(&pfull[pb], pphase, 32);
+        tc_fence_after();
+        const ScatEntry* pl = plan + pb * P.plan_cap + il * ncols;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ncols);
+        for (int c0 = part * cols_per_part; c0 < (part + 1) * cols_per_part; c0 += 8) {
+          uint32_t raw[8];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]), "=r"(raw[4]), "=r"(raw[5]),
+                         "=r"(raw[6]), "=r"(raw[7])
+                       : "r"(taddr + c0)
+                       : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float part_g[16];  // [0..7] g_ix of the 8 columns, [8..15] g_iy
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float gs = __uint_as_float(raw[u]);
+            const ScatEntry* e = pl + c0 + u;
+            const int4 off = *reinterpret_cast<const int4*>(e->off);
+            const float4 w = *reinterpret_cast<const float4*>(e->w);
+            const float2 f = *reinterpret_cast<const float2*>(&e->fx);
+            const float v0 = __ldg(ximg + off.x), v1 = __ldg(ximg + off.y);
+            const float v2 = __ldg(ximg + off.z), v3 = __ldg(ximg + off.w);
+            if (gimg) {
+              // zero-weight corners are out of the image (or the whole column is padding)
+              if (w.x != 0.f) atomicAdd(gimg + off.x, gs * w.x);
+              if (w.y != 0.f) atomicAdd(gimg + off.y, gs * w.y);
+              if (w.z != 0.f) atomicAdd(gimg + off.z, gs * w.z);
+              if (w.w != 0.f) atomicAdd(gimg + off.w, gs * w.w);
+            }
+            part_g[u] = gs * ((v1 - v0) * (1.f - f.y) + (v3 - v2) * f.y);
+            part_g[8 + u] = gs * ((v2 - v0) * (1.f - f.x) + (v3 - v1) * f.x);
+          }
+          // butterfly reduce-scatter over the RW lanes that share the sampling points:
+          // afterwards lane gl (< 16) holds the total of value index gl
+          if (RW == 32) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) part_g[k] += __shfl_xor_sync(0xffffffffu, part_g[k], 16);
+          }
+#pragma unroll
+          for (int s = 8, n = 8; s >= 1; s >>= 1, n >>= 1) {
+            const bool up = (lane & s) != 0;
+#pragma unroll
+            for (int k = 0; k < n; ++k) {
+              const float send = up ? part_g[k] : part_g[k + n];
+              const float keep = up ? part_g[k + n] : part_g[k];
+              part_g[k] = keep + __shfl_xor_sync(grp_mask, send, s);
+            }
+          }
+          if (gl < 16 && (RW == 16 || lane < 16)) {
+            const int vi = gl & 15, col = vi & 7;
+            const int gidx = pl[c0 + col].gidx;
+            // value 0..7: g_ix -> "y" offset channel (N + n); 8..15: g_iy -> "x" offset channel n
+            if (gidx >= 0 && part_g[0] != 0.f)
+              atomicAdd(P.goff + (size_t)gidx + (vi < 8 ? (size_t)g.N * g.HW : 0), part_g[0]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&tempty[acc]);
+          mbar_arrive(&pempty[pb]);
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        pb ^= 1;
+        if (pb == 0) pphase ^= 1;
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, ncols, false, false);
+      int s = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0, gphase = 0;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        mbar_wait_relaxed(gfull, gphase, 32);
+        gphase ^= 1;
+        for (int cb = 0; cb < P.cblocks; ++cb) {
+          mbar_wait_relaxed(&tempty[acc], acc_phase ^ 1, 32);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ncols);
+          for (int ob = 0; ob < P.OB; ++ob) {
+            mbar_wait_relaxed(&wfull[s], phase, 32);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(gtile + (size_t)ob * 2 * kGImg);
+            const uint32_t a_lo = a_hi + kGImg;
+            const uint32_t b_hi = smem_u32(wstage + (size_t)s * P.w_stage);
+            const uint32_t b_lo = b_hi + (uint32_t)ncols * 128;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t dah = make_sdesc_sw128(a_hi + k4 * 32, 16, 1024);
+              const uint64_t dal = make_sdesc_sw128(a_lo + k4 * 32, 16, 1024);
+              const uint64_t dbh = make_sdesc_sw128(b_hi + k4 * 32, 16, 1024);
+              const uint64_t dbl = make_sdesc_sw128(b_lo + k4 * 32, 16, 1024);
+              umma_bf16(d_tmem, dah, dbh, idesc, (ob | k4) ? 1u : 0u);
+              umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+              umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+            }
+            umma_commit(&wempty[s]);
+            s ^= 1;
+            if (s == 0) phase ^= 1;
+          }
+          umma_commit(&tfull[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+        umma_commit(gempty);  // grad_out tile may be overwritten
+      }
+    }
+  } else if (warp == kLoadWarp) {
+    // ================================================================ Wm^T tile loader
+    if (lane == 0) {
+      int s = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        for (int cb = 0; cb < P.cblocks; ++cb)
+          for (int ob = 0; ob < P.OB; ++ob) {
+            mbar_wait_relaxed(&wempty[s], phase ^ 1, 32);
+            mbar_arrive_expect_tx(&wfull[s], P.w_stage);
+            bulk_g2s(wstage + (size_t)s * P.w_stage, P.wtiles + (size_t)(cb * P.OB + ob) * P.w_stage,
+                     P.w_stage, &wfull[s]);
+            s ^= 1;
+            if (s == 0) phase ^= 1;
+          }
+      }
+    }
+  } else if (warp < kFirstPlanWarp) {
+    // ================================================================ grad_out converter
+    // A operand of GEMM-1: g[row m, o] = gout[b, o, r0 + (chunk*Gt + i_lo)*R], K-major, per 64 o's
+    const int ct = tid - kFirstConvWarp * 32;  // 0..63
+    uint32_t gphase = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      mbar_wait_relaxed(gempty, gphase ^ 1, 64);
+      gphase ^= 1;
+      const int groups = P.OB * 8;  // groups of 8 output channels
+      for (int item = ct; item < 128 * groups; item += kConvWarps * 32) {
+        const int mm = item & 127, og = item >> 7;  // lanes run along the rows
+        const int il2 = mm / GT, i2 = mm % GT;
+        const RowInfo ri = decode(P, tile * P.Rt + il2);
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0.f;
+        if (ri.valid) {
+          const float* src = P.gout + ((size_t)ri.b * g.O + og * 8) * g.HW + ri.r0 +
+                             (size_t)(ri.chunk * P.Gt + i2) * P.t.R;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (og * 8 + k < g.O) v[k] = __ldg(src + (size_t)k * g.HW);
+        }
+        uint4 hi, lo;
+        split_pair(v[0], v[1], hi.x, lo.x);
+        split_pair(v[2], v[3], hi.y, lo.y);
+        split_pair(v[4], v[5], hi.z, lo.z);
+        split_pair(v[6], v[7], hi.w, lo.w);
+        uint8_t* img = gtile + (size_t)(og >> 3) * 2 * kGImg;
+        const uint32_t so = kmajor_sw128_off(mm, (og & 7) * 8);
+        *reinterpret_cast<uint4*>(img + so) = hi;
+        *reinterpret_cast<uint4*>(img + kGImg + so) = lo;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(gfull);
+    }
+  } else {
+    // ================================================================ plan warps
+    const int pt = tid - kFirstPlanWarp * 32;  // 0..127
+    const int n_ent = P.Rt * ncols;
+    int pb = 0;
+    uint32_t pphase = 0;
+    PlanWork pw[kPlanPerThread];
+    if ((int)blockIdx.x < P.num_tiles) {
+#pragma unroll
+      for (int u = 0; u < kPlanPerThread; ++u)
+        if (pt + u * kPlanThreads < n_ent) plan_prepare(P, blockIdx.x, 0, pt + u * kPlanThreads, pw[u]);
+    }
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      for (int cb = 0; cb < P.cblocks; ++cb) {
+        ScatEntry* pl = plan + pb * P.plan_cap;
+        mbar_wait_relaxed(&pempty[pb], pphase ^ 1, 64);
+#pragma unroll
+        for (int u = 0; u < kPlanPerThread; ++u)
+          if (pt + u * kPlanThreads < n_ent) pl[pt + u * kPlanThreads] = plan_finish(g, pw[u]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pfull[pb]);
+        int ntile = tile, ncb = cb + 1;
+        if (ncb == P.cblocks) {
+          ncb = 0;
+          ntile = tile + gridDim.x;
+        }
+        if (ntile < P.num_tiles) {
+#pragma unroll
+          for (int u = 0; u < kPlanPerThread; ++u)
+            if (pt + u * kPlanThreads < n_ent) plan_prepare(P, ntile, ncb, pt + u * kPlanThreads, pw[u]);
+        }
+        pb ^= 1;
+        if (pb == 0) pphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols)
+                 : "memory");
+  }
+}
+
+// Wm^T images: tiles[cb][ob][hl][K-major SW128 image of ncols rows (j) x 64 (o)]
+__global__ void __launch_bounds__(256) weight_tiles_bwd_kernel(Geo g, int ncols, int cblocks, int OB,
+                                                               const float* __restrict__ wt,
+                                                               uint8_t* __restrict__ tiles) {
+  const int total = cblocks * ncols * OB * 64;
+  const uint32_t img = (uint32_t)ncols * 128;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int o = i % (OB * 64), jj = i / (OB * 64);  // lanes along o: Wm[o, j] strided reads, small
+    const int cb = jj / ncols, jl = jj - cb * ncols, ob = o >> 6, ol = o & 63;
+    const float v = (o < g.O && jj < g.K) ? __ldg(wt + (size_t)o * g.K + jj) : 0.f;
+    __nv_bfloat16 hi, lo;
+    ptx::split_bf16(v, hi, lo);
+    uint8_t* base = tiles + (size_t)(cb * OB + ob) * 2 * img + ptx::kmajor_sw128_off(jl, ol);
+    *reinterpret_cast<__nv_bfloat16*>(base) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(base + img) = lo;
+  }
+}
+
+}  // namespace bd
+
+// ---------------------------------------------------------------------------- host side
+static bool bwd_data_tiling(const Geo& g, bd::Params* P) {
+  if (g.variant != DCN_VARIANT_TORCH) return false;
+  if (!make_tiling(g, &P->t)) return false;
+  const int G = P->t.G;
+  P->Gt = (G % 64 == 0) ? 64 : ((G % 32 == 0) ? 32 : 16);
+  P->Rt = 128 / P->Gt;
+  P->chunks = G / P->Gt;
+  const long long inst = (long long)g.B * P->chunks * P->t.R;
+  if (inst > 0x7fffffffLL) return false;
+  if ((long long)g.B * 2 * g.N * g.HW > 0x7fffffffLL) return false;
+  P->num_inst = (int)inst;
+  P->num_tiles = (int)((inst + P->Rt - 1) / P->Rt);
+  P->divR = FastDiv::make(P->t.R);
+  P->divChunks = FastDiv::make(P->chunks);
+  P->OB = (g.O + 63) / 64;
+  if (P->OB > 4) return false;
+  // columns per accumulator block: 128 unless the plan ring / operand tiles would not fit
+  for (int ncols : {128, 64}) {
+    const size_t plan = 2 * (size_t)P->Rt * ncols * sizeof(bd::ScatEntry);
+    const size_t smem = (size_t)P->OB * 2 * bd::kGImg + 2 * (size_t)(2 * ncols * 128) + plan + 256 + 1024;
+    if (P->Rt * ncols <= bd::kPlanMax && smem <= 227 * 1024) {
+      P->ncols = ncols;
+      P->cblocks = (g.K + ncols - 1) / ncols;
+      P->plan_cap = P->Rt * ncols;
+      P->w_stage = 2u * ncols * 128;
+      P->tmem_cols = 2 * ncols;
+      return true;
+    }
+  }
+  return false;
+}
+
+bool umma_bwd_data_supported(const Geo& g, int operand) {
+  if (operand != DCN_OPERAND_FP32) return false;
+  bd::Params P;
+  P.g = g;
+  return bwd_data_tiling(g, &P);
+}
+
+size_t umma_bwd_data_wtile_bytes(const Geo& g) {
+  bd::Params P;
+  P.g = g;
+  if (!bwd_data_tiling(g, &P)) return 0;
+  return align_up((size_t)P.cblocks * P.OB * P.w_stage, 1024);
+}
+
+// gxt (channels-last grad_x, may be null) and goff must be zero on entry.
+int umma_bwd_data_fp32(const Geo& g, const float* xt, float* gxt, const float* off, const float* wt,
+                       const float* gout, float* goff, uint8_t* wtiles, cudaStream_t st) {
+  bd::Params P;
+  P.g = g;
+  if (!bwd_data_tiling(g, &P)) {
+    set_error("umma bwd_data: shape not tileable");
+    return DCN_ERR_UNSUPPORTED;
+  }
+  {
+    const int total = P.cblocks * P.ncols * P.OB * 64;
+    KernelScope scope("weight_tiles_bwd_kernel", st);
+    bd::weight_tiles_bwd_kernel<<<min((total + 255) / 256, 2048), 256, 0, st>>>(g, P.ncols, P.cblocks, P.OB, wt,
+                                                                              wtiles);
+    DCN_KERNEL_CHECK("weight_tiles_bwd_kernel");
+  }
+  P.xt = xt;
+  P.gxt = gxt;
+  P.off = off;
+  P.gout = gout;
+  P.wtiles = wtiles;
+  P.goff = goff;
+  const size_t smem = (size_t)P.OB * 2 * bd::kGImg + 2 * (size_t)P.w_stage +
+                      2 * (size_t)P.plan_cap * sizeof(bd::ScatEntry) + 256 + 1024;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = P.num_tiles < sms ? P.num_tiles : sms;
+  KernelScope scope("umma_bwd_data_kernel", st);
+#define DCN_LAUNCH_BD(GT)                                                                                    \
+  do {                                                                                                       \
+    DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<GT>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                      (int)smem));                                                           \
+    bd::bwd_data_kernel<GT><<<grid, bd::kThreads, smem, st>>>(P);                                            \
+  } while (0)
+  if (P.Gt == 64) DCN_LAUNCH_BD(64);
+  else if (P.Gt == 32) DCN_LAUNCH_BD(32);
+  else DCN_LAUNCH_BD(16);
+#undef DCN_LAUNCH_BD
+  DCN_KERNEL_CHECK("umma_bwd_data_kernel");
+  return DCN_OK;
+}
+
+}  // namespace dcn

@@ -101,6 +101,22 @@ __host__ inline bool make_tiling(const Geo& g, Tiling* t) {
   return true;
 }
 
+struct TileRowInfo {  // what a Torch-layout tile row needs
+  int b, r0, chunk, valid;
+};
+
+__device__ __forceinline__ TileRowInfo decode_inst(const Tiling& t, int inst) {
+  TileRowInfo ri;
+  ri.valid = inst < t.num_inst;
+  uint32_t bc, r0, b, ch;
+  t.divR.divmod((uint32_t)(ri.valid ? inst : 0), bc, r0);
+  t.divChunks.divmod(bc, b, ch);
+  ri.b = (int)b;
+  ri.r0 = (int)r0;
+  ri.chunk = (int)ch;
+  return ri;
+}
+
 // channel permutation of the channels-last staging copy
 __host__ __device__ inline int perm_channel(int c, int variant, int G, int Cs) {
   return variant == DCN_VARIANT_TORCH ? (c % Cs) * G + c / Cs : c;

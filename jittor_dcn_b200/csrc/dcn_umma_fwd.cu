@@ -67,22 +67,6 @@ struct FwdParams {
   uint32_t tmem_cols;  // 2*O rounded to a power of two >= 32
 };
 
-struct TileRowInfo {  // what a Torch-layout tile row needs
-  int b, r0, chunk, valid;
-};
-
-__device__ __forceinline__ TileRowInfo decode_inst(const Tiling& t, int inst) {
-  TileRowInfo ri;
-  ri.valid = inst < t.num_inst;
-  uint32_t bc, r0, b, ch;
-  t.divR.divmod((uint32_t)(ri.valid ? inst : 0), bc, r0);
-  t.divChunks.divmod(bc, b, ch);
-  ri.b = (int)b;
-  ri.r0 = (int)r0;
-  ri.chunk = (int)ch;
-  return ri;
-}
-
 // One plan entry in the making: the index math is done and the two offset loads are in
 // flight (issued one K block ahead so that their latency hides behind the gather phase).
 struct PlanWork {
