@@ -395,14 +395,25 @@ __global__ void __launch_bounds__(256) bwd_weight_kernel(Geo g, int chunks_per_s
   }
 }
 
-// grad_bias[o] = sum_{b, r} gout[b, o, r]
-__global__ void __launch_bounds__(256) bias_grad_kernel(Geo g, const float* __restrict__ gout,
+// grad_bias[o] = sum_{b, r} gout[b, o, r]: one block per (o, batch slice), float4 streaming
+// reads, block reduction, one red.global.add per block into a zeroed grad_bias.
+__global__ void __launch_bounds__(256) bias_grad_kernel(Geo g, int b_per_block,
+                                                        const float* __restrict__ gout,
                                                         float* __restrict__ gb) {
-  const int o = blockIdx.x;
+  const int o = blockIdx.x, b0 = blockIdx.y * b_per_block, b1 = min(g.B, b0 + b_per_block);
   float s = 0.f;
-  for (int b = 0; b < g.B; ++b) {
+  const bool vec = (g.HW & 3) == 0;
+  for (int b = b0; b < b1; ++b) {
     const float* row = gout + ((size_t)b * g.O + o) * g.HW;
-    for (int r = threadIdx.x; r < g.HW; r += blockDim.x) s += __ldg(row + r);
+    if (vec) {
+      const float4* r4 = reinterpret_cast<const float4*>(row);
+      for (int r = threadIdx.x; r < (g.HW >> 2); r += blockDim.x) {
+        const float4 v = __ldg(r4 + r);
+        s += (v.x + v.y) + (v.z + v.w);
+      }
+    } else {
+      for (int r = threadIdx.x; r < g.HW; r += blockDim.x) s += __ldg(row + r);
+    }
   }
   __shared__ float red[8];
   for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
@@ -411,7 +422,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(Geo g, const float* __re
   if (threadIdx.x < 8) {
     s = red[threadIdx.x];
     for (int d = 4; d; d >>= 1) s += __shfl_xor_sync(0xffu, s, d);
-    if (threadIdx.x == 0) gb[o] = s;
+    if (threadIdx.x == 0) atomicAdd(gb + o, s);
   }
 }
 
@@ -462,7 +473,13 @@ int simt_backward(const Geo& g, int flags, const float* x, const Tap* plan, cons
     DCN_KERNEL_CHECK("bwd_weight_kernel");
   }
   if (gb && (parts & SIMT_BWD_BIAS)) {
-    bias_grad_kernel<<<g.O, 256, 0, st>>>(g, gout, gb);
+    DCN_CUDA_TRY(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)g.O, st));
+    // enough blocks to stream gout at full bandwidth: ~8 per SM
+    int slices = max(1, min(g.B, (148 * 8 + g.O - 1) / g.O));
+    const int bpb = (g.B + slices - 1) / slices;
+    slices = (g.B + bpb - 1) / bpb;
+    KernelScope scope("bias_grad_kernel", st);
+    bias_grad_kernel<<<dim3(g.O, slices), 256, 0, st>>>(g, bpb, gout, gb);
     DCN_KERNEL_CHECK("bias_grad_kernel");
   }
   return DCN_OK;

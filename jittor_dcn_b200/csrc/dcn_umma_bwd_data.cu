@@ -39,7 +39,7 @@ constexpr uint32_t kGImg = 128 * 64 * 2;                 // one bf16 image of a 
 
 // what the scatter warps need for one (class instance, column): 48 bytes
 struct __align__(16) ScatEntry {
-  int off[4];   // corner offsets inside image b of the channels-last copies (pad pixel if invalid)
+  uint32_t off[4];  // corner BYTE offsets inside image b of the channels-last copies (pad pixel if invalid)
   float w[4];   // corner weights, 0 for invalid corners
   float fx, fy;
   int gidx;     // index of grad_offset[b, n, p] (the "x" offset); "y" is N*HW further; -1 = none
@@ -64,6 +64,16 @@ struct Params {
   uint32_t w_stage;      // bytes of one Wm^T stage = 2 * ncols * 128
   uint32_t tmem_cols;
 };
+
+// red.global.add.f32 [addr], val  executed only where gate != 0 (one predicated instruction)
+__device__ __forceinline__ void red_add_if(char* addr, float val, float gate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.neu.f32 p, %2, 0f00000000;\n\t"
+      "@p red.global.add.f32 [%0], %1;\n\t}" ::"l"(addr),
+      "f"(val), "f"(gate)
+      : "memory");
+}
 
 struct RowInfo {
   int b, r0, chunk, valid;
@@ -110,7 +120,7 @@ __device__ __forceinline__ void plan_prepare(const Params& P, int tile, int cb, 
 
 __device__ __forceinline__ ScatEntry plan_finish(const Geo& g, const PlanWork& pw) {
   ScatEntry e;
-  const int pad = g.H * g.W * g.C + pw.chan_base;
+  const uint32_t pad = 4u * (uint32_t)(g.H * g.W * g.C + pw.chan_base);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     e.off[k] = pad;
@@ -125,11 +135,11 @@ __device__ __forceinline__ ScatEntry plan_finish(const Geo& g, const PlanWork& p
     if (m) {
       float cw[4];
       corner_weights(tp, cw);
-      const int base = (tp.y0 * g.W + tp.x0) * g.C + pw.chan_base;
-      if (m & 1u) { e.off[0] = base;                   e.w[0] = cw[0]; }
-      if (m & 2u) { e.off[1] = base + g.C;             e.w[1] = cw[1]; }
-      if (m & 4u) { e.off[2] = base + g.W * g.C;       e.w[2] = cw[2]; }
-      if (m & 8u) { e.off[3] = base + g.W * g.C + g.C; e.w[3] = cw[3]; }
+      const int base = (tp.y0 * g.W + tp.x0) * g.C + pw.chan_base;  // may be < 0 only for masked corners
+      if (m & 1u) { e.off[0] = 4u * (uint32_t)base;                     e.w[0] = cw[0]; }
+      if (m & 2u) { e.off[1] = 4u * (uint32_t)(base + g.C);             e.w[1] = cw[1]; }
+      if (m & 4u) { e.off[2] = 4u * (uint32_t)(base + g.W * g.C);       e.w[2] = cw[2]; }
+      if (m & 8u) { e.off[3] = 4u * (uint32_t)(base + g.W * g.C + g.C); e.w[3] = cw[3]; }
       e.fx = tp.fx;
       e.fy = tp.fy;
       e.gidx = pw.gidx;  // a point with no valid corner has zero coordinate gradient
@@ -200,8 +210,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
     uint32_t acc_phase = 0, pphase = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
       const RowInfo ri = decode(P, tile * P.Rt + il);
-      const float* ximg = P.xt + (size_t)ri.b * img_stride + i_lo;
-      float* gimg = P.gxt ? P.gxt + (size_t)ri.b * img_stride + i_lo : nullptr;
+      // byte-addressed image bases: address = base + zero-extended 32-bit offset (2 instructions)
+      const char* ximg = reinterpret_cast<const char*>(P.xt + (size_t)ri.b * img_stride + i_lo);
+      char* gimg = P.gxt ? reinterpret_cast<char*>(P.gxt + (size_t)ri.b * img_stride + i_lo) : nullptr;
       for (int cb = 0; cb < P.cblocks; ++cb) {
         mbar_wait_relaxed(&tfull[acc], acc_phase, 32);
         mbar_wait_relaxed(&pfull[pb], pphase, 32);
@@ -221,17 +232,20 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
           for (int u = 0; u < 8; ++u) {
             const float gs = __uint_as_float(raw[u]);
             const ScatEntry* e = pl + c0 + u;
-            const int4 off = *reinterpret_cast<const int4*>(e->off);
+            const uint4 off = *reinterpret_cast<const uint4*>(e->off);
             const float4 w = *reinterpret_cast<const float4*>(e->w);
             const float2 f = *reinterpret_cast<const float2*>(&e->fx);
-            const float v0 = __ldg(ximg + off.x), v1 = __ldg(ximg + off.y);
-            const float v2 = __ldg(ximg + off.z), v3 = __ldg(ximg + off.w);
+            const float v0 = __ldg(reinterpret_cast<const float*>(ximg + off.x));
+            const float v1 = __ldg(reinterpret_cast<const float*>(ximg + off.y));
+            const float v2 = __ldg(reinterpret_cast<const float*>(ximg + off.z));
+            const float v3 = __ldg(reinterpret_cast<const float*>(ximg + off.w));
             if (gimg) {
-              // zero-weight corners are out of the image (or the whole column is padding)
-              if (w.x != 0.f) atomicAdd(gimg + off.x, gs * w.x);
-              if (w.y != 0.f) atomicAdd(gimg + off.y, gs * w.y);
-              if (w.z != 0.f) atomicAdd(gimg + off.z, gs * w.z);
-              if (w.w != 0.f) atomicAdd(gimg + off.w, gs * w.w);
+              // zero-weight corners are out of the image (or the whole column is padding):
+              // predicated red.global, no branches
+              red_add_if(gimg + off.x, gs * w.x, w.x);
+              red_add_if(gimg + off.y, gs * w.y, w.y);
+              red_add_if(gimg + off.z, gs * w.z, w.z);
+              red_add_if(gimg + off.w, gs * w.w, w.w);
             }
             part_g[u] = gs * ((v1 - v0) * (1.f - f.y) + (v3 - v2) * f.y);
             part_g[8 + u] = gs * ((v2 - v0) * (1.f - f.x) + (v3 - v1) * f.x);
@@ -443,6 +457,7 @@ static bool bwd_data_tiling(const Geo& g, bd::Params* P) {
   const long long inst = (long long)g.B * P->chunks * P->t.R;
   if (inst > 0x7fffffffLL) return false;
   if ((long long)g.B * 2 * g.N * g.HW > 0x7fffffffLL) return false;
+  if ((long long)(g.H * g.W + 1) * g.C >= (1LL << 30)) return false;  // 32-bit byte offsets inside an image
   P->num_inst = (int)inst;
   P->num_tiles = (int)((inst + P->Rt - 1) / P->Rt);
   P->divR = FastDiv::make(P->t.R);

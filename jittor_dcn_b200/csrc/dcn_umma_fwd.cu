@@ -60,7 +60,6 @@ struct FwdParams {
   int n_gbuf;                          // 1 or 2 buffers for the converted grad_out tile
   uint32_t g_img;                      // bytes of one bf16 image of the grad_out tile: o_blocks*128 rows x 128 B
   int stages;
-  int dbg;             // DCN_FWD_DBG timing experiments (results invalid when non-zero)
   int plan_cap;        // plan entries per buffer (n_ent rounded up to 256)
   uint32_t b_tile;     // bytes of one bf16 B image = O*128
   uint32_t stage_bytes;
@@ -244,7 +243,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       for (int c0 = 0; c0 < O; c0 += 16) {
         float v[16];
         tmem_ld16(taddr + c0, v);
-        if (valid && !(P.dbg & 16)) {
+        if (valid) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float bv = P.bias ? __ldg(P.bias + c0 + i) : 0.f;
@@ -359,7 +358,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
           const uint32_t b_lo = b_hi + P.b_tile;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
-            if (P.dbg & 8) break;
             uint64_t dah, dal;
             if (VARIANT == DCN_VARIANT_TORCH) {
               dah = make_sdesc_sw128(a_hi + k4 * 2 * kAMnSbo, kAMnLbo, kAMnSbo);
@@ -484,16 +482,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         // finish this K block's entries (their offset loads were issued one block ago) ...
 #pragma unroll
         for (int u = 0; u < kPlanPerThread; ++u)
-          if (pt + u * kPlanThreads < n_ent) {
-            if (P.dbg & 2) {
-              PlanEntry pe;
-              pe.off[0] = pe.off[1] = pe.off[2] = pe.off[3] = (pt & 63) * g.C;
-              pe.w[0] = pe.w[1] = pe.w[2] = pe.w[3] = 0.25f;
-              pl[pt + u * kPlanThreads] = pe;
-            } else {
-              pl[pt + u * kPlanThreads] = plan_finish(g, pw[u]);
-            }
-          }
+          if (pt + u * kPlanThreads < n_ent) pl[pt + u * kPlanThreads] = plan_finish(g, pw[u]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&pfull[pbuf]);
         // ... and start the next block's
@@ -502,7 +491,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
           nkb = kb0;
           ntile = tile + tile_step;
         }
-        if (ntile < t.num_tiles && !(P.dbg & 2)) {
+        if (ntile < t.num_tiles) {
 #pragma unroll
           for (int u = 0; u < kPlanPerThread; ++u)
             if (pt + u * kPlanThreads < n_ent)
@@ -586,15 +575,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       }
       const int4 off = *reinterpret_cast<const int4*>(pl[ent_idx[it]].off);
       const float* base = img[it] + jc;
-      if (P.dbg & 1) {
-        v[buf][0] = v[buf][1] = v[buf][2] = v[buf][3] =
-            make_float4((float)off.x, (float)off.y, (float)off.z, (float)off.w);
-      } else {
-        v[buf][0] = __ldg(reinterpret_cast<const float4*>(base + off.x));
-        v[buf][1] = __ldg(reinterpret_cast<const float4*>(base + off.y));
-        v[buf][2] = __ldg(reinterpret_cast<const float4*>(base + off.z));
-        v[buf][3] = __ldg(reinterpret_cast<const float4*>(base + off.w));
-      }
+      v[buf][0] = __ldg(reinterpret_cast<const float4*>(base + off.x));
+      v[buf][1] = __ldg(reinterpret_cast<const float4*>(base + off.y));
+      v[buf][2] = __ldg(reinterpret_cast<const float4*>(base + off.z));
+      v[buf][3] = __ldg(reinterpret_cast<const float4*>(base + off.w));
     };
     Pos cur{tile0, kb0, 0, 0, 0u, 0u};
     if (cur.tile < t.num_tiles) {
@@ -636,10 +620,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         r.w = fmaf(c4[3].w, w.w, fmaf(c4[2].w, w.z, fmaf(c4[1].w, w.y, c4[0].w * w.x)));
         uint2 hi, lo;
         split4(r, hi, lo);
-        if (!(P.dbg & 4) || hi.x == 0x12345678u) {
-          *reinterpret_cast<uint2*>(a_hi + st_off[it]) = hi;
-          *reinterpret_cast<uint2*>(a_lo + st_off[it]) = lo;
-        }
+        *reinterpret_cast<uint2*>(a_hi + st_off[it]) = hi;
+        *reinterpret_cast<uint2*>(a_lo + st_off[it]) = lo;
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -706,8 +688,6 @@ size_t umma_fwd_workspace(const Geo& g) {
 static void common_params(const Geo& g, FwdParams& P) {
   const int n_ent = g.variant == DCN_VARIANT_TORCH ? P.t.Rt * 64 : 128 * P.t.taps_per_kb;
   P.plan_cap = (n_ent + 255) / 256 * 256;
-  P.dbg = 0;
-  if (const char* e = getenv("DCN_FWD_DBG")) P.dbg = atoi(e);
   P.gout = nullptr;
   P.gw = nullptr;
   P.nslices = P.nchunks = P.kb_per_slice = 1;
