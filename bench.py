@@ -253,18 +253,8 @@ def main():
     comm = None
     allreduce_kind = "none"
     if world > 1:
-        import ctypes
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            buf = ctypes.create_string_buffer(128)
-            _lib.check(lib.dcn_comm_unique_id(buf), "dcn_comm_unique_id")
-            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-        uid = uid.to(dev)
-        dist.broadcast(uid, 0)
-        handle = ctypes.c_void_p()
-        raw = bytes(uid.cpu().numpy().tobytes())
-        _lib.check(lib.dcn_comm_init(rank, world, raw, ctypes.byref(handle)), "dcn_comm_init")
-        comm = handle
+        from jittor_dcn_b200 import dp
+        comm = dp.DcnComm(rank, world, dev)       # NCCL communicator behind the C ABI
         allreduce_kind = "dcn_allreduce_sum_f32 (NCCL, one flat bucket)"
 
     import ctypes
@@ -276,9 +266,7 @@ def main():
         if comm is not None:
             bucket[:n_w].copy_(gw.view(-1))
             bucket[n_w:n_w + n_b].copy_(gb)
-            _lib.check(lib.dcn_allreduce_sum_f32(comm, ctypes.c_void_p(bucket.data_ptr()), bucket.numel(),
-                                                 1.0 / world, ctypes.c_void_p(stream.cuda_stream)),
-                       "dcn_allreduce_sum_f32")
+            comm.allreduce_mean_(bucket)
         return out, gx, goff
 
     def barrier():
@@ -432,7 +420,7 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if comm is not None:
-        lib.dcn_comm_destroy(comm)
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

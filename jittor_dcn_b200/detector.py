@@ -1,0 +1,56 @@
+"""Harness model for BASELINE configs 1 and 5: the reference's toy detector topology
+(`TorchEDNetDetection`, train.py:142-175) with its four DeformConv2d layers running on the B200
+engine.  Only the DCN layers are ours; conv1 / BatchNorm / ReLU / pooling / the two heads are
+stock framework ops, as in the reference.  Module and parameter names follow the reference so
+that its checkpoints (train.py:293, test.py:17-22) load unchanged.
+"""
+import torch
+import torch.nn as nn
+
+from .torch_module import TorchDeformConv2d
+
+# (name suffix, in, out) of the stride-2 DCN stages, train.py:149-158
+_DCN_STAGES = ((2, 16, 32), (3, 32, 64), (4, 64, 128), (5, 128, 256))
+
+
+class EDNetDetection(nn.Module):
+    def __init__(self, num_classes=10, groups=2, dcn_cls=TorchDeformConv2d):
+        super().__init__()
+        del groups  # dead argument in the reference too (train.py:143,145)
+        self.conv1 = nn.Conv2d(1, 16, 3, 1, 1)
+        self.bn1 = nn.BatchNorm2d(16)
+        self.relu = nn.ReLU(inplace=True)
+        for idx, cin, cout in _DCN_STAGES:
+            setattr(self, f"conv{idx}", dcn_cls(cin, cout, 3, 2, 1))
+            setattr(self, f"bn{idx}", nn.BatchNorm2d(cout))
+        self.gap = nn.AdaptiveAvgPool2d(1)
+        self.fc_cls = nn.Linear(256, num_classes)
+        self.fc_bbox = nn.Linear(256, 4)
+
+    def forward(self, x):
+        x = self.relu(self.bn1(self.conv1(x)))
+        for idx, _, _ in _DCN_STAGES:
+            x = self.relu(getattr(self, f"bn{idx}")(getattr(self, f"conv{idx}")(x)))
+        feat = self.gap(x).flatten(1)
+        return self.fc_cls(feat), torch.sigmoid(self.fc_bbox(feat))
+
+
+def detection_loss(cls_logits, bbox, labels, boxes):
+    """CE + 5 * smooth-L1(beta=1), the recipe of train.py:195-199,247."""
+    return nn.functional.cross_entropy(cls_logits, labels) + \
+        5.0 * nn.functional.smooth_l1_loss(bbox, boxes, beta=1.0)
+
+
+def synthetic_canvases(batch, generator=None, device="cpu"):
+    """MNISTDet-shaped synthetic data (prepare_data.py:8-29): a 28x28 patch of U(0,1) noise on a
+    zero 1x128x128 canvas, label in [0,10), box = [x, y, x+28, y+28] / 128."""
+    g = generator
+    x = torch.zeros(batch, 1, 128, 128)
+    pos = torch.randint(0, 101, (batch, 2), generator=g)
+    patch = torch.rand(batch, 28, 28, generator=g)
+    for i in range(batch):
+        px, py = int(pos[i, 0]), int(pos[i, 1])
+        x[i, 0, py:py + 28, px:px + 28] = patch[i]
+    labels = torch.randint(0, 10, (batch,), generator=g)
+    boxes = torch.stack([pos[:, 0], pos[:, 1], pos[:, 0] + 28, pos[:, 1] + 28], 1).float() / 128.0
+    return x.to(device), labels.to(device), boxes.to(device)

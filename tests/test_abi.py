@@ -105,3 +105,17 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no CPU fallback", ""), os.path.join(dirpath, f)
+
+
+def test_detector_harness_keeps_reference_parameter_names():
+    """state_dict keys/shapes of train.py:142-175 (435,862 parameters, SURVEY 2 #6)."""
+    from jittor_dcn_b200.detector import EDNetDetection
+    from tests.util import golden
+    m = EDNetDetection()
+    g = golden("detector_eval")
+    ref = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    sd = m.state_dict()
+    assert list(sd) == list(ref)
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+    assert sum(p.numel() for p in m.parameters()) == 435862

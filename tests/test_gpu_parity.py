@@ -198,3 +198,32 @@ def test_error_path_reports_small_workspace():
     t = torch.zeros(4096, device="cuda")
     p = ctypes.c_void_p(t.data_ptr())
     assert lib.dcn_forward(ctypes.byref(s), p, p, p, None, p, p, 16, None) == -4
+
+
+def test_detector_forward_matches_reference():
+    """The reference's toy detector (train.py:142-175, eval mode) with its checkpoint loaded into
+    the harness model whose four DCN layers run on the engine."""
+    from jittor_dcn_b200.detector import EDNetDetection
+    g = golden("detector_eval")
+    m = EDNetDetection().cuda().eval()
+    m.load_state_dict({k[3:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("sd.")})
+    with torch.no_grad():
+        cls, bbox = m(_cuda(g["x"]))
+    assert rel_err(cls.cpu().numpy(), g["cls"]) < 1e-3
+    assert rel_err(bbox.cpu().numpy(), g["bbox"]) < 1e-3
+
+
+def test_detector_train_step_runs_and_learns():
+    from jittor_dcn_b200.detector import EDNetDetection, detection_loss, synthetic_canvases
+    torch.manual_seed(0)
+    m = EDNetDetection().cuda()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-4)   # train.py:187-191
+    x, labels, boxes = synthetic_canvases(16, torch.Generator().manual_seed(0), "cuda")
+    losses = []
+    for _ in range(8):
+        opt.zero_grad()
+        loss = detection_loss(*m(x), labels, boxes)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
