@@ -229,6 +229,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL's own banner / debug lines go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = dcn.load()
 
@@ -313,6 +315,21 @@ def main():
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
+
+    # ---- forward only (BASELINE configs[1] is quoted "fwd only"): same inputs, K timed calls --
+    fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    fe0.record(stream)
+    for _ in range(args.steps):
+        dcn.dcn_forward(x, off, wt, bias, k, s, p, variant, flags=flags)
+    fe1.record(stream)
+    barrier()
+    fwd_ms = fe0.elapsed_time(fe1) / args.steps
+    if world > 1:
+        t = torch.tensor([fwd_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        fwd_ms = float(t.item())
+    fwd_only = {"value": world * B / (fwd_ms * 1e-3), "unit": "images/s", "ms_per_step": fwd_ms}
 
     # ---- roofline of the dominant kernel ------------------------------------------------
     pk = peaks()
@@ -415,7 +432,7 @@ def main():
                               "inputs (x %.0f MB + gout %.0f MB) exceed the 126 MB L2; no flush needed"
                               % (x.numel() * 4 / 1e6, gout.numel() * 4 / 1e6)),
                        "allreduce": allreduce_kind, "parallelism": f"dp{world}"},
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "kernels": kernels, "fwd_only": fwd_only, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

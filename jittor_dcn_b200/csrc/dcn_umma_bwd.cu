@@ -3,8 +3,7 @@
 //   grad_x, grad_offset   dcn_umma_bwd_data.cu: tcgen05 GEMM gA = gout * Wm whose TMEM accumulator is
 //                 consumed in place by the bilinear col2im scatter (red.global.add.f32 into a
 //                 channels-last grad copy) and the warp-shuffle coordinate-gradient reduction
-//                 (Torch column layout).  The Jittor column layout still uses the generic
-//                 CUDA-core kernel (dcn_simt.cu:bwd_data_kernel) for this part.
+//                 (both column layouts; shapes it cannot tile use dcn_simt.cu:bwd_data_kernel).
 //   grad_weight   dcn_umma_fwd.cu (MODE_WGRAD): tcgen05 GEMM gW = gout^T * S, S re-sampled by the
 //                 forward's plan / gather warps; nothing is materialised.
 //   grad_bias     column sums of gout (dcn_simt.cu:bias_grad_kernel).

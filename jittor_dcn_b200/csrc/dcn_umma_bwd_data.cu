@@ -1,4 +1,4 @@
-// dcn_umma_bwd_data.cu — grad_x and grad_offset on the tensor path (Torch column layout).
+// dcn_umma_bwd_data.cu — grad_x and grad_offset on the tensor path (both column layouts).
 //
 // The autograd of train.py:102-134 as ONE kernel per 128-row tile:
 //   GEMM-1    gA[rows, j] = gout[rows, :] * Wm[:, j]              (tcgen05.mma, TMEM accumulator)
@@ -8,9 +8,15 @@
 //   coord     g_ix, g_iy = sum_c gA * d(sample)/d(ix, iy)         (butterfly warp-shuffle
 //                                                                   reduce-scatter, then one
 //                                                                   red.global per column)
-// gA never leaves TMEM/registers.  Tile rows are ordered (class instance, channel) so that a
-// TMEM lane IS a channel: lane l of warp-quarter q holds, for every column j, the gradient of
-// the sample (channel base(j) + l, sampling point q(r0, j)) — see dcn_umma_common.cuh:Tiling.
+// gA never leaves TMEM/registers, and a TMEM lane IS a channel:
+//   Torch layout  (train.py:129-131): D[rows, j] = g[rows, :] * Wm^T; tile rows are ordered
+//                 (class instance, channel), so lane l holds, for every column j, the gradient of
+//                 sample (channel base(j) + l, sampling point q(r0, j)) — dcn_umma_common.cuh:Tiling.
+//                 Resident operand A = converted grad_out rows, streamed operand B = Wm^T.
+//   Jittor layout (deform_conv.py:72-73): the transposed product D[j, pixels] = Wm^T * g^T; lane l
+//                 of column block jb is column j = 128*jb + l = (tap j / C, channel j % C), the
+//                 TMEM columns are 128 consecutive output pixels.  Streamed operand A = Wm^T,
+//                 resident operand B = converted grad_out pixels.
 //
 // Warp roles (768 threads, 1 CTA / SM, persistent over row tiles):
 //   warps  0-15  scatter / coord-grad epilogue (quarter = w % 4 of the TMEM lanes, w / 4 = column part)
@@ -57,11 +63,13 @@ struct Params {
   float* goff;           // raw g_iy / g_ix accumulators (zeroed); scaled afterwards
   int Gt, Rt, chunks, num_inst, num_tiles;  // backward tiling (rows = (instance, channel))
   FastDiv divR, divChunks;
-  int ncols;             // columns (j) per accumulator block: 128 or 64
-  int cblocks;           // ceil(K / ncols)
+  int pix_blocks;        // Jittor: ceil(HW / ncols) pixel blocks per image
+  int ncols;             // TMEM columns per accumulator block: 128 or 64 (Torch: j's; Jittor: pixels)
+  int cblocks;           // blocks per tile: Torch ceil(K / ncols) column blocks, Jittor ceil(K / 128) lane blocks
   int OB;                // ceil(O / 64) K blocks of the GEMM
   int plan_cap;          // entries per plan buffer = Rt * ncols
-  uint32_t w_stage;      // bytes of one Wm^T stage = 2 * ncols * 128
+  uint32_t g_img;        // bytes of one bf16 image of the resident grad_out operand (rows x 128 B)
+  uint32_t w_stage;      // bytes of one Wm^T stage (hi | lo)
   uint32_t tmem_cols;
 };
 
@@ -95,24 +103,37 @@ struct PlanWork {
   int h, w, chan_base, gidx, valid;
 };
 
+template <int VARIANT>
 __device__ __forceinline__ void plan_prepare(const Params& P, int tile, int cb, int e, PlanWork& pw) {
   const Geo& g = P.g;
   pw.valid = 0;
   pw.ox = pw.oy = 0.f;
   pw.h = pw.w = pw.chan_base = 0;
   pw.gidx = -1;
-  const int il = e / P.ncols, cc = e - il * P.ncols, j = cb * P.ncols + cc;
-  const RowInfo ri = decode(P, tile * P.Rt + il);
-  if (!ri.valid || j >= g.K) return;
-  uint32_t cbase, q, p, n, h, w;
-  P.t.divP.divmod((uint32_t)(ri.r0 * g.K + j), cbase, q);
-  P.t.divN.divmod(q, p, n);
+  uint32_t p, n, h, w;
+  int b;
+  if (VARIANT == DCN_VARIANT_TORCH) {
+    const int il = e / P.ncols, cc = e - il * P.ncols, j = cb * P.ncols + cc;
+    const RowInfo ri = decode(P, tile * P.Rt + il);
+    if (!ri.valid || j >= g.K) return;
+    uint32_t cbase, q;
+    P.t.divP.divmod((uint32_t)(ri.r0 * g.K + j), cbase, q);
+    P.t.divN.divmod(q, p, n);
+    pw.chan_base = (int)cbase * P.t.G + ri.chunk * P.Gt;
+    b = ri.b;
+  } else {
+    // entry (tap slot tl of lane block cb, pixel column cc)
+    const int tl = e / P.ncols, cc = e - tl * P.ncols;
+    b = tile / P.pix_blocks;
+    p = (uint32_t)((tile - b * P.pix_blocks) * P.ncols + cc);
+    n = (uint32_t)((cb * 128) / g.C + tl);
+    if ((int)p >= g.HW || (int)n >= g.N) return;
+  }
   P.t.divWo.divmod(p, h, w);
-  pw.chan_base = (int)cbase * P.t.G + ri.chunk * P.Gt;
   pw.h = (int)h;
   pw.w = (int)w;
-  pw.gidx = (ri.b * 2 * g.N + (int)n) * g.HW + (int)p;
-  const float* ob = P.off + (size_t)ri.b * 2 * g.N * g.HW;
+  pw.gidx = (b * 2 * g.N + (int)n) * g.HW + (int)p;
+  const float* ob = P.off + (size_t)b * 2 * g.N * g.HW;
   pw.ox = __ldg(ob + (size_t)n * g.HW + p);
   pw.oy = __ldg(ob + (size_t)(g.N + n) * g.HW + p);
   pw.valid = 1;
@@ -148,14 +169,15 @@ __device__ __forceinline__ ScatEntry plan_finish(const Geo& g, const PlanWork& p
   return e;
 }
 
-template <int GT>  // channels per class instance in a tile: 16, 32 or 64
+// RW = lanes that share one sampling point (32, or 16 when only 16 channels do)
+template <int VARIANT, int RW>
 __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const Geo& g = P.g;
   // carve-up: [grad_out tile: OB x (hi | lo)] [2 Wm^T stages] [plan x2] [barriers]
   uint8_t* gtile = smem;
-  uint8_t* wstage = gtile + (size_t)P.OB * 2 * kGImg;
+  uint8_t* wstage = gtile + (size_t)P.OB * 2 * P.g_img;
   ScatEntry* plan = reinterpret_cast<ScatEntry*>(wstage + 2 * (size_t)P.w_stage);
   uint64_t* bars = reinterpret_cast<uint64_t*>(plan + 2 * P.plan_cap);
   uint64_t* wfull = bars;        // [2]
@@ -200,24 +222,36 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
   if (warp < kScatWarps) {
     // ================================================================ scatter + coordinate gradient
     const int quarter = warp & 3, part = warp >> 2;
-    const int m = quarter * 32 + lane;          // TMEM lane = tile row
-    const int il = m / GT, i_lo = m % GT;       // class instance within the tile, channel
+    const int m = quarter * 32 + lane;          // TMEM lane
     const int cols_per_part = ncols >> 2;       // 32 or 16
-    constexpr int RW = GT >= 32 ? 32 : 16;      // lanes that share one sampling point
     const unsigned grp_mask = RW == 32 ? 0xffffffffu : (0xffffu << (lane & 16));
     const int gl = lane & (RW - 1);             // lane inside its reduction group
     int acc = 0, pb = 0;
     uint32_t acc_phase = 0, pphase = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-      const RowInfo ri = decode(P, tile * P.Rt + il);
-      // byte-addressed image bases: address = base + zero-extended 32-bit offset (2 instructions)
-      const char* ximg = reinterpret_cast<const char*>(P.xt + (size_t)ri.b * img_stride + i_lo);
-      char* gimg = P.gxt ? reinterpret_cast<char*>(P.gxt + (size_t)ri.b * img_stride + i_lo) : nullptr;
+      // Torch: lane = (class instance il, channel i_lo) for the whole tile
+      int slot = 0, chan = 0, bimg = 0;
+      if (VARIANT == DCN_VARIANT_TORCH) {
+        slot = m / P.Gt;
+        chan = m - slot * P.Gt;
+        bimg = decode(P, tile * P.Rt + slot).b;
+      } else {
+        bimg = tile / P.pix_blocks;
+      }
       for (int cb = 0; cb < P.cblocks; ++cb) {
+        if (VARIANT != DCN_VARIANT_TORCH) {
+          // Jittor: lane = column j = 128*cb + m = (tap j / C, channel j % C); slot = tap inside the block
+          const int j = cb * 128 + m, n = j / g.C;
+          chan = j - n * g.C;
+          slot = n - (cb * 128) / g.C;
+        }
+        // byte-addressed image bases: address = base + zero-extended 32-bit offset (2 instructions)
+        const char* ximg = reinterpret_cast<const char*>(P.xt + (size_t)bimg * img_stride + chan);
+        char* gimg = P.gxt ? reinterpret_cast<char*>(P.gxt + (size_t)bimg * img_stride + chan) : nullptr;
         mbar_wait_relaxed(&tfull[acc], acc_phase, 32);
         mbar_wait_relaxed(&pfull[pb], pphase, 32);
         tc_fence_after();
-        const ScatEntry* pl = plan + pb * P.plan_cap + il * ncols;
+        const ScatEntry* pl = plan + pb * P.plan_cap + slot * ncols;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ncols);
         for (int c0 = part * cols_per_part; c0 < (part + 1) * cols_per_part; c0 += 8) {
           uint32_t raw[8];
@@ -302,10 +336,16 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
           for (int ob = 0; ob < P.OB; ++ob) {
             mbar_wait_relaxed(&wfull[s], phase, 32);
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(gtile + (size_t)ob * 2 * kGImg);
-            const uint32_t a_lo = a_hi + kGImg;
-            const uint32_t b_hi = smem_u32(wstage + (size_t)s * P.w_stage);
-            const uint32_t b_lo = b_hi + (uint32_t)ncols * 128;
+            // resident converted grad_out image and streamed Wm^T image; Torch: A = grad_out rows,
+            // B = Wm^T columns; Jittor: A = Wm^T lanes, B = grad_out pixels
+            const uint32_t r_hi = smem_u32(gtile + (size_t)ob * 2 * P.g_img);
+            const uint32_t r_lo = r_hi + P.g_img;
+            const uint32_t w_hi = smem_u32(wstage + (size_t)s * P.w_stage);
+            const uint32_t w_lo = w_hi + (P.w_stage >> 1);
+            const uint32_t a_hi = VARIANT == DCN_VARIANT_TORCH ? r_hi : w_hi;
+            const uint32_t a_lo = VARIANT == DCN_VARIANT_TORCH ? r_lo : w_lo;
+            const uint32_t b_hi = VARIANT == DCN_VARIANT_TORCH ? w_hi : r_hi;
+            const uint32_t b_lo = VARIANT == DCN_VARIANT_TORCH ? w_lo : r_lo;
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               const uint64_t dah = make_sdesc_sw128(a_hi + k4 * 32, 16, 1024);
@@ -353,16 +393,23 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
       mbar_wait_relaxed(gempty, gphase ^ 1, 64);
       gphase ^= 1;
       const int groups = P.OB * 8;  // groups of 8 output channels
-      for (int item = ct; item < 128 * groups; item += kConvWarps * 32) {
-        const int mm = item & 127, og = item >> 7;  // lanes run along the rows
-        const int il2 = mm / GT, i2 = mm % GT;
-        const RowInfo ri = decode(P, tile * P.Rt + il2);
+      const int rows = VARIANT == DCN_VARIANT_TORCH ? 128 : ncols;  // rows of the resident operand
+      for (int item = ct; item < rows * groups; item += kConvWarps * 32) {
+        const int mm = item % rows, og = item / rows;  // lanes run along the rows
         float v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = 0.f;
-        if (ri.valid) {
-          const float* src = P.gout + ((size_t)ri.b * g.O + og * 8) * g.HW + ri.r0 +
-                             (size_t)(ri.chunk * P.Gt + i2) * P.t.R;
+        const float* src = nullptr;
+        if (VARIANT == DCN_VARIANT_TORCH) {
+          const int il2 = mm / P.Gt, i2 = mm - il2 * P.Gt;
+          const RowInfo ri = decode(P, tile * P.Rt + il2);
+          if (ri.valid)
+            src = P.gout + ((size_t)ri.b * g.O + og * 8) * g.HW + ri.r0 + (size_t)(ri.chunk * P.Gt + i2) * P.t.R;
+        } else {
+          const int b = tile / P.pix_blocks, p = (tile - b * P.pix_blocks) * ncols + mm;
+          if (p < g.HW) src = P.gout + ((size_t)b * g.O + og * 8) * g.HW + p;
+        }
+        if (src) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             if (og * 8 + k < g.O) v[k] = __ldg(src + (size_t)k * g.HW);
@@ -372,10 +419,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
         split_pair(v[2], v[3], hi.y, lo.y);
         split_pair(v[4], v[5], hi.z, lo.z);
         split_pair(v[6], v[7], hi.w, lo.w);
-        uint8_t* img = gtile + (size_t)(og >> 3) * 2 * kGImg;
+        uint8_t* img = gtile + (size_t)(og >> 3) * 2 * P.g_img;
         const uint32_t so = kmajor_sw128_off(mm, (og & 7) * 8);
         *reinterpret_cast<uint4*>(img + so) = hi;
-        *reinterpret_cast<uint4*>(img + kGImg + so) = lo;
+        *reinterpret_cast<uint4*>(img + P.g_img + so) = lo;
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -384,14 +431,14 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
   } else {
     // ================================================================ plan warps
     const int pt = tid - kFirstPlanWarp * 32;  // 0..127
-    const int n_ent = P.Rt * ncols;
+    const int n_ent = P.plan_cap;
     int pb = 0;
     uint32_t pphase = 0;
     PlanWork pw[kPlanPerThread];
     if ((int)blockIdx.x < P.num_tiles) {
 #pragma unroll
       for (int u = 0; u < kPlanPerThread; ++u)
-        if (pt + u * kPlanThreads < n_ent) plan_prepare(P, blockIdx.x, 0, pt + u * kPlanThreads, pw[u]);
+        if (pt + u * kPlanThreads < n_ent) plan_prepare<VARIANT>(P, blockIdx.x, 0, pt + u * kPlanThreads, pw[u]);
     }
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
       for (int cb = 0; cb < P.cblocks; ++cb) {
@@ -410,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
         if (ntile < P.num_tiles) {
 #pragma unroll
           for (int u = 0; u < kPlanPerThread; ++u)
-            if (pt + u * kPlanThreads < n_ent) plan_prepare(P, ntile, ncb, pt + u * kPlanThreads, pw[u]);
+            if (pt + u * kPlanThreads < n_ent) plan_prepare<VARIANT>(P, ntile, ncb, pt + u * kPlanThreads, pw[u]);
         }
         pb ^= 1;
         if (pb == 0) pphase ^= 1;
@@ -448,31 +495,56 @@ __global__ void __launch_bounds__(256) weight_tiles_bwd_kernel(Geo g, int ncols,
 
 // ---------------------------------------------------------------------------- host side
 static bool bwd_data_tiling(const Geo& g, bd::Params* P) {
-  if (g.variant != DCN_VARIANT_TORCH) return false;
   if (!make_tiling(g, &P->t)) return false;
-  const int G = P->t.G;
-  P->Gt = (G % 64 == 0) ? 64 : ((G % 32 == 0) ? 32 : 16);
-  P->Rt = 128 / P->Gt;
-  P->chunks = G / P->Gt;
-  const long long inst = (long long)g.B * P->chunks * P->t.R;
-  if (inst > 0x7fffffffLL) return false;
   if ((long long)g.B * 2 * g.N * g.HW > 0x7fffffffLL) return false;
   if ((long long)(g.H * g.W + 1) * g.C >= (1LL << 30)) return false;  // 32-bit byte offsets inside an image
-  P->num_inst = (int)inst;
-  P->num_tiles = (int)((inst + P->Rt - 1) / P->Rt);
-  P->divR = FastDiv::make(P->t.R);
-  P->divChunks = FastDiv::make(P->chunks);
   P->OB = (g.O + 63) / 64;
   if (P->OB > 4) return false;
-  // columns per accumulator block: 128 unless the plan ring / operand tiles would not fit
+  P->Gt = P->Rt = P->chunks = P->num_inst = 1;
+  P->divR = FastDiv::make(1);
+  P->divChunks = FastDiv::make(1);
+  P->pix_blocks = 1;
+  if (g.variant == DCN_VARIANT_TORCH) {
+    const int G = P->t.G;
+    P->Gt = (G % 64 == 0) ? 64 : ((G % 32 == 0) ? 32 : 16);
+    P->Rt = 128 / P->Gt;
+    P->chunks = G / P->Gt;
+    const long long inst = (long long)g.B * P->chunks * P->t.R;
+    if (inst > 0x7fffffffLL) return false;
+    P->num_inst = (int)inst;
+    P->num_tiles = (int)((inst + P->Rt - 1) / P->Rt);
+    P->divR = FastDiv::make(P->t.R);
+    P->divChunks = FastDiv::make(P->chunks);
+    // columns per accumulator block: 128 unless the plan ring / operand tiles would not fit
+    for (int ncols : {128, 64}) {
+      const size_t plan = 2 * (size_t)P->Rt * ncols * sizeof(bd::ScatEntry);
+      const size_t smem = (size_t)P->OB * 2 * bd::kGImg + 2 * (size_t)(2 * ncols * 128) + plan + 256 + 1024;
+      if (P->Rt * ncols <= bd::kPlanMax && smem <= 227 * 1024) {
+        P->ncols = ncols;
+        P->cblocks = (g.K + ncols - 1) / ncols;
+        P->plan_cap = P->Rt * ncols;
+        P->g_img = bd::kGImg;
+        P->w_stage = 2u * ncols * 128;
+        P->tmem_cols = 2 * ncols;
+        return true;
+      }
+    }
+    return false;
+  }
+  // Jittor: a lane block of 128 columns must hold whole taps
+  if (!(g.C % 128 == 0 || g.C == 64 || g.C == 32 || g.C == 16)) return false;
+  const int taps = g.C >= 128 ? 1 : 128 / g.C;
   for (int ncols : {128, 64}) {
-    const size_t plan = 2 * (size_t)P->Rt * ncols * sizeof(bd::ScatEntry);
-    const size_t smem = (size_t)P->OB * 2 * bd::kGImg + 2 * (size_t)(2 * ncols * 128) + plan + 256 + 1024;
-    if (P->Rt * ncols <= bd::kPlanMax && smem <= 227 * 1024) {
+    const size_t plan = 2 * (size_t)taps * ncols * sizeof(bd::ScatEntry);
+    const size_t smem = (size_t)P->OB * 2 * (ncols * 128) + 2 * (size_t)(2 * 128 * 128) + plan + 256 + 1024;
+    if (taps * ncols <= bd::kPlanMax && smem <= 227 * 1024) {
       P->ncols = ncols;
-      P->cblocks = (g.K + ncols - 1) / ncols;
-      P->plan_cap = P->Rt * ncols;
-      P->w_stage = 2u * ncols * 128;
+      P->pix_blocks = (g.HW + ncols - 1) / ncols;
+      P->num_tiles = g.B * P->pix_blocks;
+      P->cblocks = (g.K + 127) / 128;
+      P->plan_cap = taps * ncols;
+      P->g_img = (uint32_t)ncols * 128;
+      P->w_stage = 2u * 128 * 128;
       P->tmem_cols = 2 * ncols;
       return true;
     }
@@ -504,9 +576,11 @@ int umma_bwd_data_fp32(const Geo& g, const float* xt, float* gxt, const float* o
     return DCN_ERR_UNSUPPORTED;
   }
   {
-    const int total = P.cblocks * P.ncols * P.OB * 64;
+    // Wm^T images: rows = the block's columns j (Torch: ncols per block, Jittor: 128 per block)
+    const int rows = g.variant == DCN_VARIANT_TORCH ? P.ncols : 128;
+    const int total = P.cblocks * rows * P.OB * 64;
     KernelScope scope("weight_tiles_bwd_kernel", st);
-    bd::weight_tiles_bwd_kernel<<<min((total + 255) / 256, 2048), 256, 0, st>>>(g, P.ncols, P.cblocks, P.OB, wt,
+    bd::weight_tiles_bwd_kernel<<<min((total + 255) / 256, 2048), 256, 0, st>>>(g, rows, P.cblocks, P.OB, wt,
                                                                               wtiles);
     DCN_KERNEL_CHECK("weight_tiles_bwd_kernel");
   }
@@ -516,22 +590,27 @@ int umma_bwd_data_fp32(const Geo& g, const float* xt, float* gxt, const float* o
   P.gout = gout;
   P.wtiles = wtiles;
   P.goff = goff;
-  const size_t smem = (size_t)P.OB * 2 * bd::kGImg + 2 * (size_t)P.w_stage +
+  const size_t smem = (size_t)P.OB * 2 * P.g_img + 2 * (size_t)P.w_stage +
                       2 * (size_t)P.plan_cap * sizeof(bd::ScatEntry) + 256 + 1024;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = P.num_tiles < sms ? P.num_tiles : sms;
+  const bool narrow = g.variant == DCN_VARIANT_TORCH ? P.Gt == 16 : g.C == 16;  // 16 channels per sampling point
   KernelScope scope("umma_bwd_data_kernel", st);
-#define DCN_LAUNCH_BD(GT)                                                                                    \
-  do {                                                                                                       \
-    DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<GT>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                      (int)smem));                                                           \
-    bd::bwd_data_kernel<GT><<<grid, bd::kThreads, smem, st>>>(P);                                            \
+#define DCN_LAUNCH_BD(V, RW)                                                                                  \
+  do {                                                                                                        \
+    DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<V, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem));                                                            \
+    bd::bwd_data_kernel<V, RW><<<grid, bd::kThreads, smem, st>>>(P);                                          \
   } while (0)
-  if (P.Gt == 64) DCN_LAUNCH_BD(64);
-  else if (P.Gt == 32) DCN_LAUNCH_BD(32);
-  else DCN_LAUNCH_BD(16);
+  if (g.variant == DCN_VARIANT_TORCH) {
+    if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 16);
+    else DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32);
+  } else {
+    if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 16);
+    else DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 32);
+  }
 #undef DCN_LAUNCH_BD
   DCN_KERNEL_CHECK("umma_bwd_data_kernel");
   return DCN_OK;
