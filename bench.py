@@ -341,6 +341,8 @@ def main():
     if ranked:
         top = ranked[0]
         role = KERNEL_ROLE[top]
+        if top == "umma_bwd_data_kernel" and "umma_bwd_weight_kernel" not in prof and "bwd_weight_kernel" not in prof:
+            role = "bwd"   # fused backward: this launch also produces grad_weight (SURVEY 8d backward total)
         avg_s = prof[top][1] / prof[top][0] * 1e-3
         hbm_floor = work[role]["bytes"] / (pk["hbm"] * 1e9)
         tc_floor = work[role]["flops"] / (pk["bf16_sustained"] * 1e12)

@@ -4,8 +4,11 @@
 //                 consumed in place by the bilinear col2im scatter (red.global.add.f32 into a
 //                 channels-last grad copy) and the warp-shuffle coordinate-gradient reduction
 //                 (both column layouts; shapes it cannot tile use dcn_simt.cu:bwd_data_kernel).
-//   grad_weight   dcn_umma_fwd.cu (MODE_WGRAD): tcgen05 GEMM gW = gout^T * S, S re-sampled by the
-//                 forward's plan / gather warps; nothing is materialised.
+//   grad_weight   Torch layout, O <= 128: FUSED into the kernel above — its scatter warps already
+//                 hold every sample's four corner values, so they also emit the blended sample as
+//                 a bf16 hi/lo operand and a second TMEM accumulator set collects gW = gout^T * S:
+//                 the whole backward touches x once.  Otherwise dcn_umma_fwd.cu (MODE_WGRAD):
+//                 S re-sampled by the forward's plan / gather warps; nothing is materialised.
 //   grad_bias     column sums of gout (dcn_simt.cu:bias_grad_kernel).
 #include <cstdlib>
 
@@ -20,8 +23,9 @@ int umma_wgrad_fp32(const Geo& g, const float* xt, const float* off, const float
                     cudaStream_t st);
 bool umma_bwd_data_supported(const Geo& g, int operand);
 size_t umma_bwd_data_wtile_bytes(const Geo& g);
+bool umma_bwd_data_fuses_wgrad(const Geo& g);
 int umma_bwd_data_fp32(const Geo& g, const float* xt, float* gxt, const float* off, const float* wt,
-                       const float* gout, float* goff, uint8_t* wtiles, cudaStream_t st);
+                       const float* gout, float* goff, float* gw, uint8_t* wtiles, cudaStream_t st);
 
 static size_t plan_bytes(const Geo& g) { return align_up(sizeof(Tap) * (size_t)g.B * g.P, 1024); }
 
@@ -58,11 +62,14 @@ int umma_backward_fp32(const Geo& g, int flags, const float* x, const float* off
     uint8_t* wtiles = rest + umma_xt_bytes(g);
     if (want_gx) DCN_CUDA_TRY(cudaMemsetAsync(gxt, 0, sizeof(float) * (size_t)g.B * xt_image_stride(g), st));
     DCN_CUDA_TRY(cudaMemsetAsync(goff, 0, sizeof(float) * (size_t)g.B * 2 * g.N * g.HW, st));
-    if ((rc = umma_bwd_data_fp32(g, xt, want_gx ? gxt : nullptr, off, wt, gout, goff, wtiles, st))) return rc;
+    const bool fused = umma_bwd_data_fuses_wgrad(g);  // one pass over the samples yields gW as well
+    if (fused) DCN_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.O * g.K, st));
+    if ((rc = umma_bwd_data_fp32(g, xt, want_gx ? gxt : nullptr, off, wt, gout, goff, gw, wtiles, st))) return rc;
     if ((rc = launch_offset_scale(g, goff, st))) return rc;
     if (want_gx && (rc = launch_nhwc_to_nchw_add(g, t, gxt, gx, (flags & DCN_FLAG_ACCUM_GRAD_X) ? 1 : 0, st)))
       return rc;
     if ((rc = simt_backward(g, flags, x, nullptr, wt, gout, gx, goff, gw, gb, st, SIMT_BWD_BIAS))) return rc;
+    if (fused) return DCN_OK;
   } else {
     Tap* plan = (Tap*)rest;
     if ((rc = launch_plan(g, off, plan, st))) return rc;

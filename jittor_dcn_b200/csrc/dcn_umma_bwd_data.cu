@@ -68,6 +68,13 @@ struct Params {
   int cblocks;           // blocks per tile: Torch ceil(K / ncols) column blocks, Jittor ceil(K / 128) lane blocks
   int OB;                // ceil(O / 64) K blocks of the GEMM
   int plan_cap;          // entries per plan buffer = Rt * ncols
+  // fused weight gradient (Torch layout, O <= 128): the scatter warps also form the blended
+  // sample S = sum_k w_k v_k they already hold the corners of, store it as a bf16 hi/lo B
+  // operand, and a second accumulator set collects gW[o, j] += g^T S over all tiles of the CTA
+  int fuse_w;            // 0 / 1
+  float* gw;             // [O, K], zeroed
+  int nslices, nchunks, cb_per_slice;  // CTA = (slice of column blocks, chunk of tiles)
+  int g_imgs;            // grad_out images kept per tile: OB, or 2 when fused (M = 128 of the o axis)
   uint32_t g_img;        // bytes of one bf16 image of the resident grad_out operand (rows x 128 B)
   uint32_t w_stage;      // bytes of one Wm^T stage (hi | lo)
   uint32_t tmem_cols;
@@ -170,15 +177,19 @@ __device__ __forceinline__ ScatEntry plan_finish(const Geo& g, const PlanWork& p
 }
 
 // RW = lanes that share one sampling point (32, or 16 when only 16 channels do)
-template <int VARIANT, int RW>
+template <int VARIANT, int RW, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const Geo& g = P.g;
   // carve-up: [grad_out tile: OB x (hi | lo)] [2 Wm^T stages] [plan x2] [barriers]
   uint8_t* gtile = smem;
-  uint8_t* wstage = gtile + (size_t)P.OB * 2 * P.g_img;
-  ScatEntry* plan = reinterpret_cast<ScatEntry*>(wstage + 2 * (size_t)P.w_stage);
+  uint8_t* wstage = gtile + (size_t)P.g_imgs * 2 * P.g_img;
+  // fused: 2 buffers of the sample operand S, each [hi | lo][128 tile rows x 64 columns], MN-major
+  // (the 64 columns of a block are contiguous in a row, so a lane stores 8 columns with one STS.128)
+  uint8_t* sbuf = wstage + 2 * (size_t)P.w_stage;
+  const uint32_t s_img = 128u * 128u, s_buf = FUSE ? 2u * s_img : 0u;
+  ScatEntry* plan = reinterpret_cast<ScatEntry*>(sbuf + 2 * (size_t)s_buf);
   uint64_t* bars = reinterpret_cast<uint64_t*>(plan + 2 * P.plan_cap);
   uint64_t* wfull = bars;        // [2]
   uint64_t* wempty = bars + 2;   // [2]
@@ -188,7 +199,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
   uint64_t* pempty = bars + 10;  // [2]
   uint64_t* gfull = bars + 12;   // [1]
   uint64_t* gempty = bars + 13;  // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* sfull = bars + 14;   // [2] sample operand written (fused)
+  uint64_t* sempty = bars + 16;  // [2]
+  uint64_t* dfull = bars + 18;   // [1] weight-gradient accumulators final
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ncols = P.ncols;
@@ -204,6 +218,11 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
     }
     mbar_init(gfull, kConvWarps);
     mbar_init(gempty, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&sfull[a], kScatWarps);
+      mbar_init(&sempty[a], 1);
+    }
+    mbar_init(dfull, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -218,6 +237,22 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const size_t img_stride = xt_image_stride(g);
+  // (tile, block) pairs of this CTA: all blocks of every gridDim-th tile, or — fused — one slice
+  // of the column blocks for one chunk of the tiles (the gW accumulators live in TMEM throughout)
+  int tile0, tile_step, cb0, cb1;
+  if (!FUSE) {
+    tile0 = blockIdx.x;
+    tile_step = gridDim.x;
+    cb0 = 0;
+    cb1 = P.cblocks;
+  } else {
+    const int slice = blockIdx.x % P.nslices;
+    tile0 = blockIdx.x / P.nslices;
+    tile_step = P.nchunks;
+    cb0 = slice * P.cb_per_slice;
+    cb1 = min(P.cblocks, cb0 + P.cb_per_slice);
+  }
+  const uint32_t d2_base = tmem_base + 2u * (uint32_t)P.ncols;  // gW accumulators after the 2 gA buffers
 
   if (warp < kScatWarps) {
     // ================================================================ scatter + coordinate gradient
@@ -226,9 +261,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
     const int cols_per_part = ncols >> 2;       // 32 or 16
     const unsigned grp_mask = RW == 32 ? 0xffffffffu : (0xffffu << (lane & 16));
     const int gl = lane & (RW - 1);             // lane inside its reduction group
-    int acc = 0, pb = 0;
-    uint32_t acc_phase = 0, pphase = 0;
-    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+    int acc = 0, pb = 0, sb = 0;
+    uint32_t acc_phase = 0, pphase = 0, sphase = 0;
+    for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
       // Torch: lane = (class instance il, channel i_lo) for the whole tile
       int slot = 0, chan = 0, bimg = 0;
       if (VARIANT == DCN_VARIANT_TORCH) {
@@ -238,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
       } else {
         bimg = tile / P.pix_blocks;
       }
-      for (int cb = 0; cb < P.cblocks; ++cb) {
+      for (int cb = cb0; cb < cb1; ++cb) {
         if (VARIANT != DCN_VARIANT_TORCH) {
           // Jittor: lane = column j = 128*cb + m = (tap j / C, channel j % C); slot = tap inside the block
           const int j = cb * 128 + m, n = j / g.C;
@@ -250,7 +285,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
         char* gimg = P.gxt ? reinterpret_cast<char*>(P.gxt + (size_t)bimg * img_stride + chan) : nullptr;
         mbar_wait_relaxed(&tfull[acc], acc_phase, 32);
         mbar_wait_relaxed(&pfull[pb], pphase, 32);
+        if (FUSE) mbar_wait_relaxed(&sempty[sb], sphase ^ 1, 32);
         tc_fence_after();
+        // fused: this lane's row m of the sample operand (8-row groups of 1024 B, 128 B per row)
+        uint8_t* s_row = sbuf + (size_t)sb * s_buf + (size_t)(m >> 3) * 1024 + (m & 7) * 128;
         const ScatEntry* pl = plan + pb * P.plan_cap + slot * ncols;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ncols);
         for (int c0 = part * cols_per_part; c0 < (part + 1) * cols_per_part; c0 += 8) {
@@ -262,6 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
                        : "memory");
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           float part_g[16];  // [0..7] g_ix of the 8 columns, [8..15] g_iy
+          float smp8[8];     // fused: the 8 samples of this row
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const float gs = __uint_as_float(raw[u]);
@@ -283,6 +322,19 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
             }
             part_g[u] = gs * ((v1 - v0) * (1.f - f.y) + (v3 - v2) * f.y);
             part_g[8 + u] = gs * ((v2 - v0) * (1.f - f.x) + (v3 - v1) * f.x);
+            // the sample itself (same blend order as the forward pass)
+            if (FUSE) smp8[u] = fmaf(v3, w.w, fmaf(v2, w.z, fmaf(v1, w.y, v0 * w.x)));
+          }
+          if (FUSE) {
+            // columns c0..c0+7 of row m: one 16-byte chunk of the MN-major operand, swizzled by m % 8
+            uint4 hi, lo;
+            split_pair(smp8[0], smp8[1], hi.x, lo.x);
+            split_pair(smp8[2], smp8[3], hi.y, lo.y);
+            split_pair(smp8[4], smp8[5], hi.z, lo.z);
+            split_pair(smp8[6], smp8[7], hi.w, lo.w);
+            const uint32_t so = (uint32_t)((((c0 >> 3) ^ m) & 7) << 4);
+            *reinterpret_cast<uint4*>(s_row + so) = hi;
+            *reinterpret_cast<uint4*>(s_row + s_img + so) = lo;
           }
           // butterfly reduce-scatter over the RW lanes that share the sampling points:
           // afterwards lane gl (< 16) holds the total of value index gl
@@ -309,27 +361,82 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
           }
         }
         tc_fence_before();
+        if (FUSE) fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&tempty[acc]);
           mbar_arrive(&pempty[pb]);
+          if (FUSE) mbar_arrive(&sfull[sb]);
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
         pb ^= 1;
         if (pb == 0) pphase ^= 1;
+        if (FUSE) {
+          sb ^= 1;
+          if (sb == 0) sphase ^= 1;
+        }
       }
+    }
+    if (FUSE) {
+      // ---- one-shot epilogue of the weight gradient: accumulators -> gW (red.global.add)
+      mbar_wait_relaxed(dfull, 0);
+      tc_fence_after();
+      const int o = quarter * 32 + lane;
+      const int wcols = (cb1 - cb0) * ncols, per_part = (wcols + 3) >> 2;
+      const uint32_t taddr = d2_base + ((uint32_t)(quarter * 32) << 16);
+      for (int c0 = part * per_part; c0 < min(wcols, (part + 1) * per_part); c0 += 8) {
+        uint32_t raw[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]), "=r"(raw[4]), "=r"(raw[5]),
+                       "=r"(raw[6]), "=r"(raw[7])
+                     : "r"(taddr + c0)
+                     : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (o < g.O) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int j = cb0 * ncols + c0 + u;
+            if (j < g.K) atomicAdd(P.gw + (size_t)o * g.K + j, __uint_as_float(raw[u]));
+          }
+        }
+      }
+      tc_fence_before();
     }
   } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, ncols, false, false);
-      int s = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0, gphase = 0;
-      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      const uint32_t idesc_w = make_idesc_bf16(128, ncols, true, true);  // A = g^T and B = S, both MN-major
+      int s = 0, acc = 0, sb = 0;
+      uint32_t phase = 0, acc_phase = 0, gphase = 0, sphase = 0;
+      bool first_tile = true;
+      // gW[o, cols of block] += g^T[o, 128 rows] * S[128 rows, cols]; A = the resident grad_out
+      // images read MN-major (o contiguous, 64-o atoms = consecutive images), B = sample operand
+      auto wgrad_mmas = [&](int cb, bool first) {
+        mbar_wait_relaxed(&sfull[sb], sphase, 32);
+        tc_fence_after();
+        const uint32_t g_hi = smem_u32(gtile), g_lo = g_hi + P.g_img;
+        const uint32_t sbase = smem_u32(sbuf + (size_t)sb * s_buf);
+        const uint32_t d_tmem = d2_base + (uint32_t)((cb - cb0) * ncols);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {  // 8 steps of 16 tile rows
+          const uint64_t dgh = make_sdesc_sw128(g_hi + ks * 2048, 2 * P.g_img, 1024);
+          const uint64_t dgl = make_sdesc_sw128(g_lo + ks * 2048, 2 * P.g_img, 1024);
+          const uint64_t dsh = make_sdesc_sw128(sbase + ks * 2048, 1024, 1024);
+          const uint64_t dsl = make_sdesc_sw128(sbase + s_img + ks * 2048, 1024, 1024);
+          umma_bf16(d_tmem, dgh, dsh, idesc_w, (first && ks == 0) ? 0u : 1u);
+          umma_bf16(d_tmem, dgh, dsl, idesc_w, 1u);
+          umma_bf16(d_tmem, dgl, dsh, idesc_w, 1u);
+        }
+        umma_commit(&sempty[sb]);
+        sb ^= 1;
+        if (sb == 0) sphase ^= 1;
+      };
+      for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
         mbar_wait_relaxed(gfull, gphase, 32);
         gphase ^= 1;
-        for (int cb = 0; cb < P.cblocks; ++cb) {
+        for (int cb = cb0; cb < cb1; ++cb) {
           mbar_wait_relaxed(&tempty[acc], acc_phase ^ 1, 32);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ncols);
@@ -363,17 +470,22 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
           umma_commit(&tfull[acc]);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
+          // the weight-gradient MMAs trail GEMM-1 by one block so the scatter warps never wait
+          if (FUSE && cb > cb0) wgrad_mmas(cb - 1, first_tile);
         }
+        if (FUSE) wgrad_mmas(cb1 - 1, first_tile);
         umma_commit(gempty);  // grad_out tile may be overwritten
+        first_tile = false;
       }
+      if (FUSE) umma_commit(dfull);
     }
   } else if (warp == kLoadWarp) {
     // ================================================================ Wm^T tile loader
     if (lane == 0) {
       int s = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-        for (int cb = 0; cb < P.cblocks; ++cb)
+      for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
+        for (int cb = cb0; cb < cb1; ++cb)
           for (int ob = 0; ob < P.OB; ++ob) {
             mbar_wait_relaxed(&wempty[s], phase ^ 1, 32);
             mbar_arrive_expect_tx(&wfull[s], P.w_stage);
@@ -389,7 +501,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
     // A operand of GEMM-1: g[row m, o] = gout[b, o, r0 + (chunk*Gt + i_lo)*R], K-major, per 64 o's
     const int ct = tid - kFirstConvWarp * 32;  // 0..63
     uint32_t gphase = 0;
-    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+    if (FUSE) {
+      // images beyond OB (the o >= 64*OB half of the M = 128 weight-gradient MMA) stay zero
+      for (uint32_t i = (uint32_t)P.OB * 2 * P.g_img + ct * 16; i < (uint32_t)P.g_imgs * 2 * P.g_img;
+           i += kConvWarps * 32 * 16)
+        *reinterpret_cast<uint4*>(gtile + i) = make_uint4(0, 0, 0, 0);
+    }
+    for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
       mbar_wait_relaxed(gempty, gphase ^ 1, 64);
       gphase ^= 1;
       const int groups = P.OB * 8;  // groups of 8 output channels
@@ -435,13 +553,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
     int pb = 0;
     uint32_t pphase = 0;
     PlanWork pw[kPlanPerThread];
-    if ((int)blockIdx.x < P.num_tiles) {
+    if (tile0 < P.num_tiles) {
 #pragma unroll
       for (int u = 0; u < kPlanPerThread; ++u)
-        if (pt + u * kPlanThreads < n_ent) plan_prepare<VARIANT>(P, blockIdx.x, 0, pt + u * kPlanThreads, pw[u]);
+        if (pt + u * kPlanThreads < n_ent) plan_prepare<VARIANT>(P, tile0, cb0, pt + u * kPlanThreads, pw[u]);
     }
-    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-      for (int cb = 0; cb < P.cblocks; ++cb) {
+    for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
+      for (int cb = cb0; cb < cb1; ++cb) {
         ScatEntry* pl = plan + pb * P.plan_cap;
         mbar_wait_relaxed(&pempty[pb], pphase ^ 1, 64);
 #pragma unroll
@@ -450,9 +568,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&pfull[pb]);
         int ntile = tile, ncb = cb + 1;
-        if (ncb == P.cblocks) {
-          ncb = 0;
-          ntile = tile + gridDim.x;
+        if (ncb == cb1) {
+          ncb = cb0;
+          ntile = tile + tile_step;
         }
         if (ntile < P.num_tiles) {
 #pragma unroll
@@ -494,8 +612,12 @@ __global__ void __launch_bounds__(256) weight_tiles_bwd_kernel(Geo g, int ncols,
 }  // namespace bd
 
 // ---------------------------------------------------------------------------- host side
-static bool bwd_data_tiling(const Geo& g, bd::Params* P) {
+static bool bwd_data_tiling(const Geo& g, bd::Params* P, bool allow_fuse = true) {
   if (!make_tiling(g, &P->t)) return false;
+  P->fuse_w = 0;
+  P->gw = nullptr;
+  P->nslices = P->nchunks = 1;
+  P->cb_per_slice = 0;
   if ((long long)g.B * 2 * g.N * g.HW > 0x7fffffffLL) return false;
   if ((long long)(g.H * g.W + 1) * g.C >= (1LL << 30)) return false;  // 32-bit byte offsets inside an image
   P->OB = (g.O + 63) / 64;
@@ -515,6 +637,30 @@ static bool bwd_data_tiling(const Geo& g, bd::Params* P) {
     P->num_tiles = (int)((inst + P->Rt - 1) / P->Rt);
     P->divR = FastDiv::make(P->t.R);
     P->divChunks = FastDiv::make(P->chunks);
+    P->g_imgs = P->OB;
+    // fused weight gradient: 64-column blocks, <= 6 blocks of gW accumulators next to the 2 gA buffers
+    if (allow_fuse && g.O <= 128) {
+      const int ncols = 64;
+      const size_t plan = 2 * (size_t)P->Rt * ncols * sizeof(bd::ScatEntry);
+      const size_t smem = 2 * 2 * (size_t)bd::kGImg + 2 * (size_t)(2 * ncols * 128) + 2 * 2 * (size_t)(128 * 128) +
+                          plan + 256 + 1024;
+      if (P->Rt * ncols <= bd::kPlanMax && smem <= 227 * 1024) {
+        P->fuse_w = 1;
+        P->g_imgs = 2;
+        P->ncols = ncols;
+        P->cblocks = (g.K + ncols - 1) / ncols;
+        P->plan_cap = P->Rt * ncols;
+        P->g_img = bd::kGImg;
+        P->w_stage = 2u * ncols * 128;
+        P->tmem_cols = 512;
+        int max_cb = 6;  // 512 TMEM columns - 2 gA buffers
+        if (const char* e = getenv("DCN_BWD_SLICE_CB")) max_cb = atoi(e) < 1 ? 1 : (atoi(e) > 6 ? 6 : atoi(e));
+        P->nslices = (P->cblocks + max_cb - 1) / max_cb;
+        P->cb_per_slice = (P->cblocks + P->nslices - 1) / P->nslices;
+        P->nslices = (P->cblocks + P->cb_per_slice - 1) / P->cb_per_slice;
+        return true;
+      }
+    }
     // columns per accumulator block: 128 unless the plan ring / operand tiles would not fit
     for (int ncols : {128, 64}) {
       const size_t plan = 2 * (size_t)P->Rt * ncols * sizeof(bd::ScatEntry);
@@ -531,6 +677,7 @@ static bool bwd_data_tiling(const Geo& g, bd::Params* P) {
     }
     return false;
   }
+  P->g_imgs = P->OB;
   // Jittor: a lane block of 128 columns must hold whole taps
   if (!(g.C % 128 == 0 || g.C == 64 || g.C == 32 || g.C == 16)) return false;
   const int taps = g.C >= 128 ? 1 : 128 / g.C;
@@ -552,26 +699,40 @@ static bool bwd_data_tiling(const Geo& g, bd::Params* P) {
   return false;
 }
 
+static bool fuse_allowed() {
+  if (const char* e = getenv("DCN_BWD_NO_FUSE"))
+    if (atoi(e)) return false;
+  return true;
+}
+
 bool umma_bwd_data_supported(const Geo& g, int operand) {
   if (operand != DCN_OPERAND_FP32) return false;
   bd::Params P;
   P.g = g;
-  return bwd_data_tiling(g, &P);
+  return bwd_data_tiling(g, &P, fuse_allowed());
+}
+
+// does umma_bwd_data_fp32 also produce grad_weight for this shape?
+bool umma_bwd_data_fuses_wgrad(const Geo& g) {
+  bd::Params P;
+  P.g = g;
+  return bwd_data_tiling(g, &P, fuse_allowed()) && P.fuse_w;
 }
 
 size_t umma_bwd_data_wtile_bytes(const Geo& g) {
   bd::Params P;
   P.g = g;
-  if (!bwd_data_tiling(g, &P)) return 0;
+  if (!bwd_data_tiling(g, &P, fuse_allowed())) return 0;
   return align_up((size_t)P.cblocks * P.OB * P.w_stage, 1024);
 }
 
-// gxt (channels-last grad_x, may be null) and goff must be zero on entry.
+// gxt (channels-last grad_x, may be null), goff and — when the shape fuses the weight gradient
+// (umma_bwd_data_fuses_wgrad) — gw must be zero on entry.
 int umma_bwd_data_fp32(const Geo& g, const float* xt, float* gxt, const float* off, const float* wt,
-                       const float* gout, float* goff, uint8_t* wtiles, cudaStream_t st) {
+                       const float* gout, float* goff, float* gw, uint8_t* wtiles, cudaStream_t st) {
   bd::Params P;
   P.g = g;
-  if (!bwd_data_tiling(g, &P)) {
+  if (!bwd_data_tiling(g, &P, fuse_allowed())) {
     set_error("umma bwd_data: shape not tileable");
     return DCN_ERR_UNSUPPORTED;
   }
@@ -590,26 +751,39 @@ int umma_bwd_data_fp32(const Geo& g, const float* xt, float* gxt, const float* o
   P.gout = gout;
   P.wtiles = wtiles;
   P.goff = goff;
-  const size_t smem = (size_t)P.OB * 2 * P.g_img + 2 * (size_t)P.w_stage +
+  P.gw = gw;
+  const size_t smem = (size_t)P.g_imgs * 2 * P.g_img + 2 * (size_t)P.w_stage +
+                      (P.fuse_w ? 2 * 2 * (size_t)(128 * 128) : 0) +
                       2 * (size_t)P.plan_cap * sizeof(bd::ScatEntry) + 256 + 1024;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = P.num_tiles < sms ? P.num_tiles : sms;
+  int grid = P.num_tiles < sms ? P.num_tiles : sms;
+  if (P.fuse_w) {
+    P.nchunks = sms / P.nslices;
+    if (P.nchunks < 1) P.nchunks = 1;
+    if (P.nchunks > P.num_tiles) P.nchunks = P.num_tiles;
+    grid = P.nslices * P.nchunks;
+  }
   const bool narrow = g.variant == DCN_VARIANT_TORCH ? P.Gt == 16 : g.C == 16;  // 16 channels per sampling point
   KernelScope scope("umma_bwd_data_kernel", st);
-#define DCN_LAUNCH_BD(V, RW)                                                                                  \
-  do {                                                                                                        \
-    DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<V, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      (int)smem));                                                            \
-    bd::bwd_data_kernel<V, RW><<<grid, bd::kThreads, smem, st>>>(P);                                          \
+#define DCN_LAUNCH_BD(V, RW, F)                                                                                  \
+  do {                                                                                                           \
+    DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<V, RW, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem));                                                               \
+    bd::bwd_data_kernel<V, RW, F><<<grid, bd::kThreads, smem, st>>>(P);                                          \
   } while (0)
   if (g.variant == DCN_VARIANT_TORCH) {
-    if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 16);
-    else DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32);
+    if (P.fuse_w) {
+      if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 16, true);
+      else DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32, true);
+    } else {
+      if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 16, false);
+      else DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32, false);
+    }
   } else {
-    if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 16);
-    else DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 32);
+    if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 16, false);
+    else DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 32, false);
   }
 #undef DCN_LAUNCH_BD
   DCN_KERNEL_CHECK("umma_bwd_data_kernel");
