@@ -111,12 +111,12 @@ DCN_API size_t dcn_workspace_bytes(const DcnShape* s, int phase);
 /* Name of the kernel family dcn_forward/dcn_backward will pick for this shape
  * ("umma" = tcgen05 implicit GEMM, "simt" = generic CUDA-core kernels). */
 DCN_API const char* dcn_path_name(const DcnShape* s, int phase);
-/* Number of kernel launches issued by this library on the calling thread since the
+/* Number of kernel launches issued by this library (all threads of the process) since the
  * last reset (bench.py's gpu_launches). */
 DCN_API uint64_t dcn_launch_count(void);
 DCN_API void dcn_launch_count_reset(void);
 /* Per-kernel timing for bench.py's roofline: between begin and end every kernel this
- * library launches on the calling thread is bracketed by CUDA events on its own stream.
+ * library launches (from any thread) is bracketed by CUDA events on its own stream.
  * dcn_profile_end synchronises those events and writes one line per kernel name:
  * "<name> <launches> <total_ms>\n" (NUL terminated, truncated to cap). */
 DCN_API int dcn_profile_begin(void);

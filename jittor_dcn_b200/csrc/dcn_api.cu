@@ -3,7 +3,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -13,7 +15,8 @@
 namespace dcn {
 
 static thread_local char g_err[512] = "";
-static thread_local uint64_t g_launches = 0;
+// process-wide: autograd runs the backward on its own thread, bench.py reads from the main one
+static std::atomic<uint64_t> g_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -27,25 +30,31 @@ int cuda_fail(cudaError_t e, const char* what) {
   return DCN_ERR_CUDA;
 }
 
-void count_launch(int n) { g_launches += (uint64_t)n; }
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 // ---- per-kernel event profiler ------------------------------------------------------
 struct ProfRec {
   const char* name;
   cudaEvent_t a, b;
 };
-static thread_local bool g_prof_on = false;
-static thread_local std::vector<ProfRec>* g_prof = nullptr;
+static std::atomic<bool> g_prof_on{false};
+static std::vector<ProfRec>* g_prof = nullptr;
+static std::mutex g_prof_mu;
+static thread_local int g_prof_slot = -1;  // record opened by this thread's KernelScope
 
 void profile_mark(const char* name, cudaStream_t st, bool begin) {
-  if (!g_prof_on) return;
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (!g_prof) return;
   if (begin) {
     ProfRec r{name, nullptr, nullptr};
     if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
     cudaEventRecord(r.a, st);
     g_prof->push_back(r);
-  } else if (!g_prof->empty()) {
-    cudaEventRecord(g_prof->back().b, st);
+    g_prof_slot = (int)g_prof->size() - 1;
+  } else if (g_prof_slot >= 0 && g_prof_slot < (int)g_prof->size()) {
+    cudaEventRecord((*g_prof)[g_prof_slot].b, st);
+    g_prof_slot = -1;
   }
 }
 
@@ -131,6 +140,7 @@ const char* dcn_path_name(const DcnShape* s, int phase) {
 }
 
 int dcn_profile_begin(void) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   if (!g_prof) g_prof = new std::vector<ProfRec>();
   for (auto& r : *g_prof) {
     cudaEventDestroy(r.a);
@@ -143,12 +153,13 @@ int dcn_profile_begin(void) {
 
 int dcn_profile_end(char* out, size_t cap) {
   g_prof_on = false;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   if (!g_prof) return DCN_OK;
   std::map<std::string, std::pair<int, double>> agg;
   std::vector<std::string> order;
   for (auto& r : *g_prof) {
     float ms = 0.f;
-    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+    if (r.b && cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
       auto it = agg.find(r.name);
       if (it == agg.end()) {
         order.push_back(r.name);
@@ -175,8 +186,8 @@ int dcn_profile_end(char* out, size_t cap) {
   return DCN_OK;
 }
 
-uint64_t dcn_launch_count(void) { return g_launches; }
-void dcn_launch_count_reset(void) { g_launches = 0; }
+uint64_t dcn_launch_count(void) { return g_launches.load(); }
+void dcn_launch_count_reset(void) { g_launches.store(0); }
 
 int dcn_forward(const DcnShape* s, const void* x, const void* offset, const void* weight,
                 const void* bias, void* out, void* workspace, size_t workspace_bytes,
