@@ -11,27 +11,36 @@
 
 namespace dcn {
 
+// Both transposes move 32-channel x 128-pixel panels per block: 16 independent 128-byte-coalesced
+// loads per thread are in flight before the single barrier (4 sub-tiles of 32 x 32 through
+// padded shared memory), then 16 coalesced stores.
+constexpr int kSub = 4;  // 32-pixel sub-tiles per block
+
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(Geo g, int variant, int G, int Cs,
                                                            const float* __restrict__ x,
                                                            float* __restrict__ xt) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[kSub][32][33];
   const int HWi = g.H * g.W;
-  const int b = blockIdx.z, p0 = blockIdx.x * 32, d0 = blockIdx.y * 32;  // d = destination channel
+  const int b = blockIdx.z, p0 = blockIdx.x * (32 * kSub), d0 = blockIdx.y * 32;  // d = destination channel
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int d = d0 + ty + 8 * i, p = p0 + tx;
-    if (d < g.C && p < HWi) {
-      const int c = variant == DCN_VARIANT_TORCH ? (d % G) * Cs + d / G : d;  // inverse permutation
-      tile[ty + 8 * i][tx] = __ldg(x + ((size_t)b * g.C + c) * HWi + p);
+  for (int s = 0; s < kSub; ++s)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int d = d0 + ty + 8 * i, p = p0 + 32 * s + tx;
+      if (d < g.C && p < HWi) {
+        const int c = variant == DCN_VARIANT_TORCH ? (d % G) * Cs + d / G : d;  // inverse permutation
+        tile[s][ty + 8 * i][tx] = __ldg(x + ((size_t)b * g.C + c) * HWi + p);
+      }
     }
-  }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int p = p0 + ty + 8 * i, d = d0 + tx;
-    if (d < g.C && p < HWi) xt[((size_t)b * (HWi + 1) + p) * g.C + d] = tile[tx][ty + 8 * i];
-  }
+  for (int s = 0; s < kSub; ++s)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = p0 + 32 * s + ty + 8 * i, d = d0 + tx;
+      if (d < g.C && p < HWi) xt[((size_t)b * (HWi + 1) + p) * g.C + d] = tile[s][tx][ty + 8 * i];
+    }
   // the zero pad pixel that closes the image (target of out-of-image corners)
   if (blockIdx.x == 0 && threadIdx.x < 32 && d0 + tx < g.C)
     xt[((size_t)b * (HWi + 1) + HWi) * g.C + d0 + tx] = 0.f;
@@ -39,7 +48,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(Geo g, int variant, i
 
 int launch_nchw_to_nhwc(const Geo& g, const Tiling& t, const float* x, float* xt, cudaStream_t st) {
   const int HWi = g.H * g.W;
-  dim3 grid((HWi + 31) / 32, (g.C + 31) / 32, g.B);
+  dim3 grid((HWi + 32 * kSub - 1) / (32 * kSub), (g.C + 31) / 32, g.B);
   KernelScope scope("nchw_to_nhwc_kernel", st);
   nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(g, t.variant, t.G, t.Cs, x, xt);
   DCN_KERNEL_CHECK("nchw_to_nhwc_kernel");
@@ -50,32 +59,36 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(Geo g, int variant, i
                                                            int accumulate,
                                                            const float* __restrict__ gxt,
                                                            float* __restrict__ gx) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[kSub][32][33];
   const int HWi = g.H * g.W;
-  const int b = blockIdx.z, p0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int b = blockIdx.z, p0 = blockIdx.x * (32 * kSub), d0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int p = p0 + ty + 8 * i, d = d0 + tx;
-    if (d < g.C && p < HWi) tile[ty + 8 * i][tx] = __ldg(gxt + ((size_t)b * (HWi + 1) + p) * g.C + d);
-  }
+  for (int s = 0; s < kSub; ++s)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = p0 + 32 * s + ty + 8 * i, d = d0 + tx;
+      if (d < g.C && p < HWi) tile[s][ty + 8 * i][tx] = __ldg(gxt + ((size_t)b * (HWi + 1) + p) * g.C + d);
+    }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int d = d0 + ty + 8 * i, p = p0 + tx;
-    if (d < g.C && p < HWi) {
-      const int c = variant == DCN_VARIANT_TORCH ? (d % G) * Cs + d / G : d;
-      float* dst = gx + ((size_t)b * g.C + c) * HWi + p;
-      const float v = tile[tx][ty + 8 * i];
-      *dst = accumulate ? *dst + v : v;
+  for (int s = 0; s < kSub; ++s)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int d = d0 + ty + 8 * i, p = p0 + 32 * s + tx;
+      if (d < g.C && p < HWi) {
+        const int c = variant == DCN_VARIANT_TORCH ? (d % G) * Cs + d / G : d;
+        float* dst = gx + ((size_t)b * g.C + c) * HWi + p;
+        const float v = tile[s][tx][ty + 8 * i];
+        *dst = accumulate ? *dst + v : v;
+      }
     }
-  }
 }
 
 int launch_nhwc_to_nchw_add(const Geo& g, const Tiling& t, const float* gxt, float* gx, int accumulate,
                             cudaStream_t st) {
   const int HWi = g.H * g.W;
-  dim3 grid((HWi + 31) / 32, (g.C + 31) / 32, g.B);
+  dim3 grid((HWi + 32 * kSub - 1) / (32 * kSub), (g.C + 31) / 32, g.B);
   KernelScope scope("nhwc_to_nchw_kernel", st);
   nhwc_to_nchw_kernel<<<grid, 256, 0, st>>>(g, t.variant, t.G, t.Cs, accumulate, gxt, gx);
   DCN_KERNEL_CHECK("nhwc_to_nchw_kernel");

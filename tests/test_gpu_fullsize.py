@@ -85,16 +85,16 @@ def test_adjoint_identities_and_linearity(name, variant):
 def test_grad_offset_directional_finite_difference(variant):
     (x, off, wt, bias, gout), (k, s, p) = _data("cfg3", seed=2, sigma=1.0)
     _, goff, _, _ = dcn.dcn_backward(x, off, wt, gout, False, k, s, p, variant)
-    d = torch.randn_like(off)
-    # The float32 coordinate chain rounds at ~2e-6 px, so a central difference with eps = 1e-3 px
-    # is only good to a few percent (the CPU oracle shows the same 3 %): this is a gross check of
-    # sign / scale / channel order; precision is pinned by the small-size oracle tests.
+    # Direction ALIGNED with the analytic gradient, so <goff, d> is a sum of positive terms.  (With
+    # a random direction the sum cancels to ~sqrt(numel) and the ~0.3 % of samples that cross a
+    # cell boundary within +-eps — where the sample has a kink — alone move it by ~5 %.)
+    d = goff / goff.abs().max()
     eps = 1e-3
     fp = _dot(dcn.dcn_forward(x, off + eps * d, wt, None, k, s, p, variant), gout)
     fm = _dot(dcn.dcn_forward(x, off - eps * d, wt, None, k, s, p, variant), gout)
     fd = (fp - fm) / (2 * eps)
     an = _dot(goff, d)
-    assert abs(fd - an) < 8e-2 * max(abs(an), 1.0), (fd, an)
+    assert an > 0 and abs(fd - an) < 3e-2 * an, (fd, an)
 
 
 def test_zero_offset_closed_form_torch_variant():
