@@ -18,9 +18,9 @@
 namespace dcn {
 
 bool umma_wgrad_supported(const Geo& g, int operand);
-size_t umma_xt_bytes(const Geo& g);
-int umma_wgrad_fp32(const Geo& g, const float* xt, const float* off, const float* gout, float* gw,
-                    cudaStream_t st);
+size_t umma_xt_bytes(const Geo& g, int operand);
+int umma_wgrad_any(const Geo& g, int operand, const void* xt, const float* off, const void* gout, float* gw,
+                   cudaStream_t st);
 bool umma_bwd_data_supported(const Geo& g, int operand);
 size_t umma_bwd_data_wtile_bytes(const Geo& g);
 bool umma_bwd_data_fuses_wgrad(const Geo& g);
@@ -35,31 +35,41 @@ static bool use_umma_data(const Geo& g, int operand) {
   return umma_bwd_data_supported(g, operand);
 }
 
-bool umma_bwd_supported(const Geo& g, int operand) { return umma_wgrad_supported(g, operand); }
-
-size_t umma_bwd_workspace(const Geo& g) {
-  // [xt] then either [gxt | Wm^T tiles] (tensor-path data gradient) or [sampling plan] (generic)
-  const size_t a = umma_xt_bytes(g) + umma_bwd_data_wtile_bytes(g);
-  const size_t b = plan_bytes(g);
-  return umma_xt_bytes(g) + (a > b ? a : b);
+bool umma_bwd_supported(const Geo& g, int operand) {
+  if (operand != DCN_OPERAND_FP32) return false;  // bf16 backward: not yet
+  return umma_wgrad_supported(g, operand);
 }
 
-int umma_backward_fp32(const Geo& g, int flags, const float* x, const float* off, const float* wt,
-                       const float* gout, float* gx, float* goff, float* gw, float* gb, void* workspace,
-                       cudaStream_t st) {
+size_t umma_bwd_workspace(const Geo& g, int operand) {
+  // [xt] then either [gxt | Wm^T tiles] (tensor-path data gradient) or [sampling plan] (generic)
+  const size_t a = umma_xt_bytes(g, DCN_OPERAND_FP32) + umma_bwd_data_wtile_bytes(g);
+  const size_t b = plan_bytes(g);
+  return umma_xt_bytes(g, operand) + (a > b ? a : b);
+}
+
+int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, const float* off, const void* wtv,
+                      const void* goutv, float* gx, float* goff, float* gw, float* gb, void* workspace,
+                      cudaStream_t st) {
+  if (operand != DCN_OPERAND_FP32) {
+    set_error("umma backward: operand mode %d not implemented", operand);
+    return DCN_ERR_UNSUPPORTED;
+  }
+  const float* x = (const float*)xv;
+  const float* wt = (const float*)wtv;
+  const float* gout = (const float*)goutv;
   float* xt = (float*)workspace;
-  uint8_t* rest = (uint8_t*)workspace + umma_xt_bytes(g);
+  uint8_t* rest = (uint8_t*)workspace + umma_xt_bytes(g, operand);
   Tiling t;
   if (!make_tiling(g, &t)) {
     set_error("umma backward: shape not tileable");
     return DCN_ERR_UNSUPPORTED;
   }
   int rc;
-  if ((rc = launch_nchw_to_nhwc(g, t, x, xt, st))) return rc;
+  if ((rc = launch_nchw_to_nhwc(g, t, x, xt, operand, st))) return rc;
   const bool want_gx = !(flags & DCN_FLAG_NO_GRAD_X) && gx != nullptr;
   if (use_umma_data(g, DCN_OPERAND_FP32)) {
     float* gxt = (float*)rest;
-    uint8_t* wtiles = rest + umma_xt_bytes(g);
+    uint8_t* wtiles = rest + umma_xt_bytes(g, DCN_OPERAND_FP32);
     if (want_gx) DCN_CUDA_TRY(cudaMemsetAsync(gxt, 0, sizeof(float) * (size_t)g.B * xt_image_stride(g), st));
     DCN_CUDA_TRY(cudaMemsetAsync(goff, 0, sizeof(float) * (size_t)g.B * 2 * g.N * g.HW, st));
     const bool fused = umma_bwd_data_fuses_wgrad(g);  // one pass over the samples yields gW as well
@@ -76,7 +86,7 @@ int umma_backward_fp32(const Geo& g, int flags, const float* x, const float* off
     if ((rc = simt_backward(g, flags, x, plan, wt, gout, gx, goff, gw, gb, st, SIMT_BWD_DATA | SIMT_BWD_BIAS)))
       return rc;
   }
-  return umma_wgrad_fp32(g, xt, off, gout, gw, st);
+  return umma_wgrad_any(g, operand, xt, off, gout, gw, st);
 }
 
 }  // namespace dcn

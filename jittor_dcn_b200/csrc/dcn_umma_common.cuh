@@ -135,10 +135,12 @@ struct __align__(16) PlanEntry {
 // channels-last staging copy: [B][H*W + 1][C]; pixel H*W of every image is zero
 __host__ __device__ inline size_t xt_image_stride(const Geo& g) { return (size_t)(g.H * g.W + 1) * g.C; }
 
-int launch_nchw_to_nhwc(const Geo& g, const Tiling& t, const float* x, float* xt, cudaStream_t st);
+// x / xt: float (DCN_OPERAND_FP32) or bfloat16 (DCN_OPERAND_BF16)
+int launch_nchw_to_nhwc(const Geo& g, const Tiling& t, const void* x, void* xt, int operand, cudaStream_t st);
 int launch_nhwc_to_nchw_add(const Geo& g, const Tiling& t, const float* gxt, float* gx, int accumulate,
                             cudaStream_t st);
 // weight images for the forward GEMM: per K block [hi: O x 64 K-major SW128][lo: same]
-int launch_weight_tiles_fwd(const Geo& g, const Tiling& t, const float* wt, uint8_t* tiles, cudaStream_t st);
+int launch_weight_tiles_fwd(const Geo& g, const Tiling& t, const void* wt, uint8_t* tiles, int operand,
+                            cudaStream_t st);
 
 }  // namespace dcn

@@ -22,6 +22,7 @@
 // fp32 parity: every fp32 operand v is split as hi = bf16(v), lo = bf16(v - hi) and the product
 // is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation (relative error ~5e-6, measured).
 #include <cstdlib>
+#include <type_traits>
 
 #include "dcn_umma.h"
 #include "dcn_umma_common.cuh"
@@ -36,7 +37,6 @@ constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kFirstPlanWarp = kEpiWarps + 2, kFirstProdWarp = kFirstPlanWarp + kPlanWarps;
 constexpr int kFwdThreads = (kFirstProdWarp + kProdWarps) * 32;  // 832
 constexpr int kPlanPerThread = 4;                                // kPlanMax / kPlanThreads
-constexpr int kItems = 128 * 16 / kProdThreads;                  // float4 items per thread and K block (4)
 constexpr int kPlanMax = 512;                                    // plan entries per K block (32 B each)
 constexpr uint32_t kATile = 128 * 64 * 2;                        // one bf16 A image (16 KB)
 constexpr uint32_t kAMnLbo = 1024, kAMnSbo = 2048;               // MN-major A: atom strides
@@ -47,13 +47,13 @@ enum { MODE_FWD = 0, MODE_WGRAD = 1 };
 struct FwdParams {
   Geo g;
   Tiling t;
-  const float* xt;
+  const void* xt;      // channels-last staging copy: float (fp32 mode) or bfloat16 (bf16 mode)
   const float* off;
   const uint8_t* wtiles;
   const float* bias;
   float* out;
   // weight-gradient mode (MODE_WGRAD): gW[o, j] += sum_rows gout[row, o] * S[row, j]
-  const float* gout;
+  const void* gout;    // float or bfloat16
   float* gw;
   int nslices, nchunks, kb_per_slice;  // CTA = (K slice, chunk of row tiles)
   int o_blocks;                        // ceil(O / 128) accumulators
@@ -148,8 +148,15 @@ __device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
   split_pair(v.z, v.w, hi.y, lo.y);
 }
 
-template <int VARIANT, int MODE>
+// BF = bf16 operand mode (DCN_OPERAND_BF16): x / weight / grad_out are bfloat16 in HBM, every
+// operand is ONE bf16 image and every K step ONE MMA; otherwise fp32 with the hi/lo split (two
+// images, three MMAs).  A gather item is one 16-byte load per corner: V = 4 fp32 or 8 bf16 channels.
+template <int VARIANT, int MODE, bool BF>
 __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_constant__ FwdParams P) {
+  constexpr int V = BF ? 8 : 4;
+  constexpr int NIMG = BF ? 1 : 2;
+  constexpr int kIt = 128 * 64 / V / kProdThreads;  // gather items per thread and K block: 4 or 2
+  typedef typename std::conditional<BF, __nv_bfloat16, float>::type XT;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic (a uintptr_t round trip would lose the shared
   // address space and turn every LDS/STS below into a slow generic LD/ST)
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
   // carve-up: [stages x (A_hi | A_lo | B_hi | B_lo)] [grad_out tile buffers (WGRAD)] [plan x2] [barriers]
   uint8_t* stage_base = smem;
   uint8_t* gbuf_base = smem + (size_t)P.stages * P.stage_bytes;
-  const uint32_t gbuf_bytes = MODE == MODE_WGRAD ? 4u * P.g_img : 0u;  // 2 row halves x (hi | lo)
+  const uint32_t gbuf_bytes = MODE == MODE_WGRAD ? 2u * NIMG * P.g_img : 0u;  // 2 row halves x (hi | lo)
   PlanEntry* plan = reinterpret_cast<PlanEntry*>(gbuf_base + (size_t)(MODE == MODE_WGRAD ? P.n_gbuf : 0) * gbuf_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(plan + 2 * P.plan_cap);
   uint64_t* full = bars;                   // [stages]
@@ -227,10 +234,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       size_t out_off = 0;
       bool valid;
       if (VARIANT == DCN_VARIANT_TORCH) {
-        const int quad = m / (4 * t.Rt), il = (m >> 2) % t.Rt, chq = m & 3;
+        // tile row m = grp*(V*Rt) + il*V + ch: V channels of class instance il are V consecutive rows
+        const int grp = m / (V * t.Rt), il = (m / V) % t.Rt, ch = m % V;
         const TileRowInfo ri = decode_inst(t, tile * t.Rt + il);
         valid = ri.valid;
-        const int i = ri.chunk * t.Gt + 4 * quad + chq;
+        const int i = ri.chunk * t.Gt + V * grp + ch;
         out_off = (size_t)ri.b * O * g.HW + (size_t)(ri.r0 + i * t.R);
       } else {
         const int b = tile / t.pix_blocks, p = (tile - b * t.pix_blocks) * 128 + m;
@@ -274,37 +282,37 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (o < O) {
           if (VARIANT == DCN_VARIANT_TORCH) {
-            // rows m..m+3 = channels 4*quad..+3 of class instance il (dcn_umma_common.cuh:Tiling)
-            const int quad = m / (4 * t.Rt), il = (m >> 2) % t.Rt;
+            // rows m..m+3 = 4 consecutive channels of class instance il (dcn_umma_common.cuh:Tiling)
+            const int grp = m / (V * t.Rt), il = (m / V) % t.Rt, ch0 = m % V;
             const TileRowInfo ri = decode_inst(t, tile * t.Rt + il);
             if (ri.valid) {
-              const float* src = P.gout + ((size_t)ri.b * O + o) * g.HW + ri.r0 +
-                                 (size_t)(ri.chunk * t.Gt + 4 * quad) * t.R;
-              v.x = __ldg(src);
-              v.y = __ldg(src + t.R);
-              v.z = __ldg(src + 2 * (size_t)t.R);
-              v.w = __ldg(src + 3 * (size_t)t.R);
+              const XT* src = reinterpret_cast<const XT*>(P.gout) + ((size_t)ri.b * O + o) * g.HW + ri.r0 +
+                              (size_t)(ri.chunk * t.Gt + V * grp + ch0) * t.R;
+              v.x = (float)__ldg(src);
+              v.y = (float)__ldg(src + t.R);
+              v.z = (float)__ldg(src + 2 * (size_t)t.R);
+              v.w = (float)__ldg(src + 3 * (size_t)t.R);
             }
           } else {
             const int b = tile / t.pix_blocks, p = (tile - b * t.pix_blocks) * 128 + m;
-            const float* src = P.gout + ((size_t)b * O + o) * g.HW + p;
-            if (p + 3 < g.HW && (g.HW & 3) == 0) {
+            const XT* src = reinterpret_cast<const XT*>(P.gout) + ((size_t)b * O + o) * g.HW + p;
+            if (!BF && p + 3 < g.HW && (g.HW & 3) == 0) {
               v = __ldg(reinterpret_cast<const float4*>(src));
             } else {
-              if (p < g.HW) v.x = __ldg(src);
-              if (p + 1 < g.HW) v.y = __ldg(src + 1);
-              if (p + 2 < g.HW) v.z = __ldg(src + 2);
-              if (p + 3 < g.HW) v.w = __ldg(src + 3);
+              if (p < g.HW) v.x = (float)__ldg(src);
+              if (p + 1 < g.HW) v.y = (float)__ldg(src + 1);
+              if (p + 2 < g.HW) v.z = (float)__ldg(src + 2);
+              if (p + 3 < g.HW) v.w = (float)__ldg(src + 3);
             }
           }
         }
         uint2 hi, lo;
-        split4(v, hi, lo);
+        split4(v, hi, lo);  // bf16 mode: the inputs are bf16 already, hi is exact and lo unused
         // image of row half h: [hi: O_pad x 64][lo: O_pad x 64]
-        uint8_t* img_h = gb + (size_t)(m >> 6) * 2 * P.g_img;
+        uint8_t* img_h = gb + (size_t)(m >> 6) * NIMG * P.g_img;
         const uint32_t so = kmajor_sw128_off(o, m & 63);
         *reinterpret_cast<uint2*>(img_h + so) = hi;
-        *reinterpret_cast<uint2*>(img_h + P.g_img + so) = lo;
+        if (!BF) *reinterpret_cast<uint2*>(img_h + P.g_img + so) = lo;
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
           tc_fence_after();
           const uint32_t a_hi = smem_u32(stage_base + (size_t)s * P.stage_bytes);
           const uint32_t a_lo = a_hi + kATile;
-          const uint32_t b_hi = a_hi + 2 * kATile;
+          const uint32_t b_hi = a_hi + NIMG * kATile;
           const uint32_t b_lo = b_hi + P.b_tile;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
@@ -369,8 +377,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
             const uint64_t dbh = make_sdesc_sw128(b_hi + k4 * 32, 16, 1024);
             const uint64_t dbl = make_sdesc_sw128(b_lo + k4 * 32, 16, 1024);
             umma_bf16(d_tmem, dah, dbh, idesc, (kb | k4) ? 1u : 0u);
-            umma_bf16(d_tmem, dah, dbl, idesc, 1u);
-            umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+            if (!BF) {
+              umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+              umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+            }
           }
           umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
           if (kb == t.KB - 1) umma_commit(&tfull[acc]);
@@ -416,14 +426,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
               dsl = make_sdesc_sw128(s_lo + ks * 2048, 1024, 1024);
             }
             for (int ob = 0; ob < P.o_blocks; ++ob) {
-              const uint32_t g_hi = gb + h * 2 * P.g_img + ob * (128 * 128) + k4 * 32;
+              const uint32_t g_hi = gb + h * NIMG * P.g_img + ob * (128 * 128) + k4 * 32;
               const uint32_t g_lo = g_hi + P.g_img;
               const uint64_t dgh = make_sdesc_sw128(g_hi, 16, 1024);
               const uint64_t dgl = make_sdesc_sw128(g_lo, 16, 1024);
               const uint32_t d_tmem = tmem_base + (uint32_t)(ob * ncols + (kb - kb0) * 64);
               umma_bf16(d_tmem, dgh, dsh, idesc, (first_tile && ks == 0) ? 0u : 1u);
-              umma_bf16(d_tmem, dgh, dsl, idesc, 1u);
-              umma_bf16(d_tmem, dgl, dsh, idesc, 1u);
+              if (!BF) {
+                umma_bf16(d_tmem, dgh, dsl, idesc, 1u);
+                umma_bf16(d_tmem, dgl, dsh, idesc, 1u);
+              }
             }
           }
           umma_commit(&empty[s]);
@@ -452,9 +464,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       for (int tile = tile0; tile < t.num_tiles; tile += tile_step) {
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_relaxed(&empty[s], phase ^ 1);
-          uint8_t* dst = stage_base + (size_t)s * P.stage_bytes + 2 * kATile;
-          mbar_arrive_expect_tx(&full[s], 2 * P.b_tile);
-          bulk_g2s(dst, P.wtiles + (size_t)kb * 2 * P.b_tile, 2 * P.b_tile, &full[s]);
+          uint8_t* dst = stage_base + (size_t)s * P.stage_bytes + NIMG * kATile;
+          mbar_arrive_expect_tx(&full[s], NIMG * P.b_tile);
+          bulk_g2s(dst, P.wtiles + (size_t)kb * NIMG * P.b_tile, NIMG * P.b_tile, &full[s]);
           if (++s == P.stages) {
             s = 0;
             phase ^= 1;
@@ -503,30 +515,31 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     }
   } else {
     // ================================================================ gather warps
-    // kItems (4) float4 items per thread and K block, software pipelined one item deep: the 4
-    // LDG.128 of item i+1 (possibly the first item of the NEXT K block) are issued before item
-    // i is blended, so every warp always has gathers in flight.
+    // kIt items (one 16-byte load per corner: 4 fp32 or 8 bf16 channels) per thread and K block,
+    // software pipelined one item deep: the 4 LDG.128 of item i+1 (possibly the first item of the
+    // NEXT K block) are issued before item i is blended, so every warp always has gathers in flight.
     const int pt = tid - kFirstProdWarp * 32;  // 0..511
     const size_t img_stride = xt_image_stride(g);
-    // `quads` lanes share one sampling point; a "pair" is one (class instance, column) of the
+    const XT* xt = reinterpret_cast<const XT*>(P.xt);
+    // `groups` lanes share one sampling point; a "pair" is one (class instance, column) of the
     // Torch tile or one row of the Jittor tile
-    const int quads = VARIANT == DCN_VARIANT_TORCH ? (t.Gt >> 2) : 16;
-    const int quad = pt % quads, slot = pt / quads;
-    const int pairs_per_pass = kProdThreads / quads;
-    int ent_idx[kItems], item_il[kItems];
-    uint32_t st_off[kItems];
+    const int groups = VARIANT == DCN_VARIANT_TORCH ? (t.Gt / V) : (64 / V);
+    const int grp = pt % groups, slot = pt / groups;
+    const int pairs_per_pass = kProdThreads / groups;
+    int ent_idx[kIt], item_il[kIt];
+    uint32_t st_off[kIt];
 #pragma unroll
-    for (int it = 0; it < kItems; ++it) {
+    for (int it = 0; it < kIt; ++it) {
       const int pair = slot + it * pairs_per_pass;
       if (VARIANT == DCN_VARIANT_TORCH) {
         const int il = pair >> 6, kk = pair & 63;
         item_il[it] = il;
         ent_idx[it] = pair;  // = il * 64 + kk
-        st_off[it] = mnmajor_sw128_off(quad * (4 * t.Rt) + il * 4, kk, kAMnLbo, kAMnSbo);
+        st_off[it] = mnmajor_sw128_off(grp * (V * t.Rt) + il * V, kk, kAMnLbo, kAMnSbo);
       } else {
         item_il[it] = 0;
         ent_idx[it] = pair;  // row m
-        st_off[it] = kmajor_sw128_off(pair, quad * 4);
+        st_off[it] = kmajor_sw128_off(pair, grp * V);
       }
     }
     // position of one K block in the three rings it touches
@@ -546,25 +559,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       q.pbuf ^= 1;
       if (q.pbuf == 0) q.pphase ^= 1;
     };
-    const float* img[kItems];  // load side: image base (+ channel quad) of each item's rows
+    const XT* img[kIt];  // load side: image base (+ channel group) of each item's rows
     auto set_images = [&](int tile) {
 #pragma unroll
-      for (int it = 0; it < kItems; ++it) {
+      for (int it = 0; it < kIt; ++it) {
         if (VARIANT == DCN_VARIANT_TORCH)
-          img[it] = P.xt + (size_t)decode_inst(t, tile * t.Rt + item_il[it]).b * img_stride + quad * 4;
+          img[it] = xt + (size_t)decode_inst(t, tile * t.Rt + item_il[it]).b * img_stride + grp * V;
         else
-          img[it] = P.xt + (size_t)(tile / t.pix_blocks) * img_stride;
+          img[it] = xt + (size_t)(tile / t.pix_blocks) * img_stride;
       }
     };
-    // Jittor layout: channel offset / tap slot of this thread's 4 columns inside K block kb
+    // Jittor layout: channel offset / tap slot of this thread's V columns inside K block kb
     auto jit_cols = [&](int kb, int& c, int& tl, bool& ok) {
-      const int j = kb * 64 + quad * 4;
+      const int j = kb * 64 + grp * V;
       const int n = j / g.C;
       c = j - n * g.C;
       tl = n - (kb * 64) / g.C;
       ok = j < g.K;
     };
-    float4 v[2][4];  // [buffer][corner]
+    uint4 v[2][4];  // [buffer][corner], 16 raw bytes each
     auto issue = [&](const Pos& q, int it, int buf) {
       const PlanEntry* pl = plan + q.pbuf * P.plan_cap;
       int jc = 0, tl = 0;
@@ -574,11 +587,26 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         pl += tl * 128;
       }
       const int4 off = *reinterpret_cast<const int4*>(pl[ent_idx[it]].off);
-      const float* base = img[it] + jc;
-      v[buf][0] = __ldg(reinterpret_cast<const float4*>(base + off.x));
-      v[buf][1] = __ldg(reinterpret_cast<const float4*>(base + off.y));
-      v[buf][2] = __ldg(reinterpret_cast<const float4*>(base + off.z));
-      v[buf][3] = __ldg(reinterpret_cast<const float4*>(base + off.w));
+      const XT* base = img[it] + jc;
+      v[buf][0] = __ldg(reinterpret_cast<const uint4*>(base + off.x));
+      v[buf][1] = __ldg(reinterpret_cast<const uint4*>(base + off.y));
+      v[buf][2] = __ldg(reinterpret_cast<const uint4*>(base + off.z));
+      v[buf][3] = __ldg(reinterpret_cast<const uint4*>(base + off.w));
+    };
+    // blend one pair of channels held as the two bf16 halves of a word (bf16 mode)
+    auto blend_bf = [](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, const float4& w) {
+      const float lo = fmaf(__uint_as_float(a3 << 16), w.w,
+                            fmaf(__uint_as_float(a2 << 16), w.z,
+                                 fmaf(__uint_as_float(a1 << 16), w.y, __uint_as_float(a0 << 16) * w.x)));
+      const float hi = fmaf(__uint_as_float(a3 & 0xffff0000u), w.w,
+                            fmaf(__uint_as_float(a2 & 0xffff0000u), w.z,
+                                 fmaf(__uint_as_float(a1 & 0xffff0000u), w.y,
+                                      __uint_as_float(a0 & 0xffff0000u) * w.x)));
+      return pack_bf16x2(lo, hi);
+    };
+    auto blend_f = [](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, const float4& w) {
+      return fmaf(__uint_as_float(a3), w.w,
+                  fmaf(__uint_as_float(a2), w.z, fmaf(__uint_as_float(a1), w.y, __uint_as_float(a0) * w.x)));
     };
     Pos cur{tile0, kb0, 0, 0, 0u, 0u};
     if (cur.tile < t.num_tiles) {
@@ -600,9 +628,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       uint8_t* a_hi = stage_base + (size_t)cur.s * P.stage_bytes;
       uint8_t* a_lo = a_hi + kATile;
 #pragma unroll
-      for (int it = 0; it < kItems; ++it) {
+      for (int it = 0; it < kIt; ++it) {
         // keep the L1 fed: next item first
-        if (it < kItems - 1) {
+        if (it < kIt - 1) {
           issue(cur, it + 1, (it + 1) & 1);
         } else if (nxt.tile < t.num_tiles) {
           if (nxt.tile != cur.tile) set_images(nxt.tile);
@@ -612,16 +640,26 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         }
         float4 w = *reinterpret_cast<const float4*>(pl[ent_idx[it]].w);
         if (VARIANT != DCN_VARIANT_TORCH && !col_ok) w = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4* c4 = v[it & 1];
-        float4 r;
-        r.x = fmaf(c4[3].x, w.w, fmaf(c4[2].x, w.z, fmaf(c4[1].x, w.y, c4[0].x * w.x)));
-        r.y = fmaf(c4[3].y, w.w, fmaf(c4[2].y, w.z, fmaf(c4[1].y, w.y, c4[0].y * w.x)));
-        r.z = fmaf(c4[3].z, w.w, fmaf(c4[2].z, w.z, fmaf(c4[1].z, w.y, c4[0].z * w.x)));
-        r.w = fmaf(c4[3].w, w.w, fmaf(c4[2].w, w.z, fmaf(c4[1].w, w.y, c4[0].w * w.x)));
-        uint2 hi, lo;
-        split4(r, hi, lo);
-        *reinterpret_cast<uint2*>(a_hi + st_off[it]) = hi;
-        *reinterpret_cast<uint2*>(a_lo + st_off[it]) = lo;
+        const uint4* c4 = v[it & 1];
+        if (BF) {
+          // 8 channels: blend in fp32, ONE bf16 rounding of the sample, one 16-byte store
+          uint4 r;
+          r.x = blend_bf(c4[0].x, c4[1].x, c4[2].x, c4[3].x, w);
+          r.y = blend_bf(c4[0].y, c4[1].y, c4[2].y, c4[3].y, w);
+          r.z = blend_bf(c4[0].z, c4[1].z, c4[2].z, c4[3].z, w);
+          r.w = blend_bf(c4[0].w, c4[1].w, c4[2].w, c4[3].w, w);
+          *reinterpret_cast<uint4*>(a_hi + st_off[it]) = r;
+        } else {
+          float4 r;
+          r.x = blend_f(c4[0].x, c4[1].x, c4[2].x, c4[3].x, w);
+          r.y = blend_f(c4[0].y, c4[1].y, c4[2].y, c4[3].y, w);
+          r.z = blend_f(c4[0].z, c4[1].z, c4[2].z, c4[3].z, w);
+          r.w = blend_f(c4[0].w, c4[1].w, c4[2].w, c4[3].w, w);
+          uint2 hi, lo;
+          split4(r, hi, lo);
+          *reinterpret_cast<uint2*>(a_hi + st_off[it]) = hi;
+          *reinterpret_cast<uint2*>(a_lo + st_off[it]) = lo;
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -664,25 +702,32 @@ static bool tiling_ok(const Geo& g, Tiling* t) {
 }
 
 bool umma_fwd_supported(const Geo& g, int operand) {
-  if (operand != DCN_OPERAND_FP32) return false;
+  if (operand != DCN_OPERAND_FP32 && operand != DCN_OPERAND_BF16) return false;
   if (g.O % 16 || g.O < 16 || g.O > 256) return false;
+  if (operand == DCN_OPERAND_BF16 && g.C % 8) return false;
   Tiling t;
   return tiling_ok(g, &t);
 }
 
 bool umma_wgrad_supported(const Geo& g, int operand) {
-  if (operand != DCN_OPERAND_FP32) return false;
+  if (operand != DCN_OPERAND_FP32 && operand != DCN_OPERAND_BF16) return false;
   if (g.O > 256) return false;
+  if (operand == DCN_OPERAND_BF16 && g.C % 8) return false;
   Tiling t;
   return tiling_ok(g, &t);
 }
 
-size_t umma_xt_bytes(const Geo& g) { return align_up(sizeof(float) * (size_t)g.B * xt_image_stride(g), 1024); }
+static size_t elem_bytes(int operand) { return operand == DCN_OPERAND_BF16 ? 2 : 4; }
 
-size_t umma_fwd_workspace(const Geo& g) {
+size_t umma_xt_bytes(const Geo& g, int operand) {
+  return align_up(elem_bytes(operand) * (size_t)g.B * xt_image_stride(g), 1024);
+}
+
+size_t umma_fwd_workspace(const Geo& g, int operand) {
   Tiling t;
   make_tiling(g, &t);
-  return umma_xt_bytes(g) + align_up((size_t)t.KB * 2 * g.O * 128, 1024);
+  const int nimg = operand == DCN_OPERAND_BF16 ? 1 : 2;
+  return umma_xt_bytes(g, operand) + align_up((size_t)t.KB * nimg * g.O * 128, 1024);
 }
 
 static void common_params(const Geo& g, FwdParams& P) {
@@ -696,8 +741,28 @@ static void common_params(const Geo& g, FwdParams& P) {
   P.g_img = 0;
 }
 
-int umma_forward_fp32(const Geo& g, const float* x, const float* off, const float* wt, const float* bias,
-                      float* out, void* workspace, cudaStream_t st) {
+template <int MODE>
+static int launch_gemm(const Geo& g, int operand, const FwdParams& P, int grid, size_t smem, cudaStream_t st) {
+#define DCN_GEMM_CASE(V, BFV)                                                                              \
+  do {                                                                                                     \
+    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<V, MODE, BFV>,                                      \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    umma_gemm_kernel<V, MODE, BFV><<<grid, kFwdThreads, smem, st>>>(P);                                    \
+  } while (0)
+  const bool bf = operand == DCN_OPERAND_BF16;
+  if (g.variant == DCN_VARIANT_TORCH) {
+    if (bf) DCN_GEMM_CASE(DCN_VARIANT_TORCH, true);
+    else DCN_GEMM_CASE(DCN_VARIANT_TORCH, false);
+  } else {
+    if (bf) DCN_GEMM_CASE(DCN_VARIANT_JITTOR, true);
+    else DCN_GEMM_CASE(DCN_VARIANT_JITTOR, false);
+  }
+#undef DCN_GEMM_CASE
+  return DCN_OK;
+}
+
+int umma_forward_any(const Geo& g, int operand, const void* x, const float* off, const void* wt,
+                     const float* bias, float* out, void* workspace, cudaStream_t st) {
   FwdParams P;
   P.g = g;
   if (!make_tiling(g, &P.t)) {
@@ -705,18 +770,19 @@ int umma_forward_fp32(const Geo& g, const float* x, const float* off, const floa
     return DCN_ERR_UNSUPPORTED;
   }
   common_params(g, P);
-  float* xt = (float*)workspace;
-  uint8_t* wtiles = (uint8_t*)workspace + umma_xt_bytes(g);
+  const int nimg = operand == DCN_OPERAND_BF16 ? 1 : 2;
+  void* xt = workspace;
+  uint8_t* wtiles = (uint8_t*)workspace + umma_xt_bytes(g, operand);
   int rc;
-  if ((rc = launch_nchw_to_nhwc(g, P.t, x, xt, st))) return rc;
-  if ((rc = launch_weight_tiles_fwd(g, P.t, wt, wtiles, st))) return rc;
+  if ((rc = launch_nchw_to_nhwc(g, P.t, x, xt, operand, st))) return rc;
+  if ((rc = launch_weight_tiles_fwd(g, P.t, wt, wtiles, operand, st))) return rc;
   P.xt = xt;
   P.off = off;
   P.wtiles = wtiles;
   P.bias = bias;
   P.out = out;
   P.b_tile = (uint32_t)g.O * 128;
-  P.stage_bytes = 2 * kATile + 2 * P.b_tile;
+  P.stage_bytes = nimg * (kATile + P.b_tile);
   const size_t fixed = 2 * (size_t)P.plan_cap * sizeof(PlanEntry) + 256 + 1024;  // plan ring, barriers, align slack
   int stages = (int)((227 * 1024 - fixed) / P.stage_bytes);
   // A few stages are enough to overlap the (fast) MMAs with the (slow) gather; every KB of
@@ -735,23 +801,15 @@ int umma_forward_fp32(const Geo& g, const float* x, const float* off, const floa
   const int sms = num_sms();
   const int grid = P.t.num_tiles < sms ? P.t.num_tiles : sms;
   KernelScope scope("umma_fwd_kernel", st);
-  if (g.variant == DCN_VARIANT_TORCH) {
-    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<DCN_VARIANT_TORCH, MODE_FWD>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_gemm_kernel<DCN_VARIANT_TORCH, MODE_FWD><<<grid, kFwdThreads, smem, st>>>(P);
-  } else {
-    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<DCN_VARIANT_JITTOR, MODE_FWD>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_gemm_kernel<DCN_VARIANT_JITTOR, MODE_FWD><<<grid, kFwdThreads, smem, st>>>(P);
-  }
+  if ((rc = launch_gemm<MODE_FWD>(g, operand, P, grid, smem, st))) return rc;
   DCN_KERNEL_CHECK("umma_fwd_kernel");
   return DCN_OK;
 }
 
 // grad_weight[O, K] (zeroed here) = sum over all rows of gout^T * S, S re-sampled by the same
 // plan / gather warps as the forward pass.  xt = channels-last staging copy (already built).
-int umma_wgrad_fp32(const Geo& g, const float* xt, const float* off, const float* gout, float* gw,
-                    cudaStream_t st) {
+int umma_wgrad_any(const Geo& g, int operand, const void* xt, const float* off, const void* gout, float* gw,
+                   cudaStream_t st) {
   FwdParams P;
   P.g = g;
   if (!make_tiling(g, &P.t)) {
@@ -759,6 +817,7 @@ int umma_wgrad_fp32(const Geo& g, const float* xt, const float* off, const float
     return DCN_ERR_UNSUPPORTED;
   }
   common_params(g, P);
+  const int nimg = operand == DCN_OPERAND_BF16 ? 1 : 2;
   DCN_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.O * g.K, st));
   P.xt = xt;
   P.off = off;
@@ -769,7 +828,6 @@ int umma_wgrad_fp32(const Geo& g, const float* xt, const float* off, const float
   P.gw = gw;
   P.o_blocks = (g.O + 127) / 128;
   P.g_img = (uint32_t)P.o_blocks * 128 * 128;
-  P.n_gbuf = P.o_blocks == 1 ? 2 : 1;
   const int kb_max = 8 / P.o_blocks;  // 512 TMEM columns
   P.nslices = (P.t.KB + kb_max - 1) / kb_max;
   P.kb_per_slice = (P.t.KB + P.nslices - 1) / P.nslices;
@@ -779,26 +837,21 @@ int umma_wgrad_fp32(const Geo& g, const float* xt, const float* off, const float
   if (P.nchunks < 1) P.nchunks = 1;
   if (P.nchunks > P.t.num_tiles) P.nchunks = P.t.num_tiles;
   P.b_tile = 0;
-  P.stage_bytes = 2 * kATile;
+  P.stage_bytes = nimg * kATile;
   P.stages = 2;
   P.tmem_cols = pow2_cols(P.o_blocks * P.kb_per_slice * 64);
   const size_t fixed = 2 * (size_t)P.plan_cap * sizeof(PlanEntry) + 256 + 1024;
-  const size_t smem = (size_t)P.stages * P.stage_bytes + (size_t)P.n_gbuf * 4 * P.g_img + fixed;
+  const size_t gbuf = 2 * (size_t)nimg * P.g_img;
+  P.n_gbuf = ((size_t)P.stages * P.stage_bytes + 2 * gbuf + fixed <= 227 * 1024) ? 2 : 1;
+  const size_t smem = (size_t)P.stages * P.stage_bytes + (size_t)P.n_gbuf * gbuf + fixed;
   if (smem > 227 * 1024) {
     set_error("umma wgrad: %zu bytes of shared memory needed", smem);
     return DCN_ERR_UNSUPPORTED;
   }
   const int grid = P.nslices * P.nchunks;
   KernelScope scope("umma_bwd_weight_kernel", st);
-  if (g.variant == DCN_VARIANT_TORCH) {
-    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<DCN_VARIANT_TORCH, MODE_WGRAD>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_gemm_kernel<DCN_VARIANT_TORCH, MODE_WGRAD><<<grid, kFwdThreads, smem, st>>>(P);
-  } else {
-    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<DCN_VARIANT_JITTOR, MODE_WGRAD>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_gemm_kernel<DCN_VARIANT_JITTOR, MODE_WGRAD><<<grid, kFwdThreads, smem, st>>>(P);
-  }
+  int rc;
+  if ((rc = launch_gemm<MODE_WGRAD>(g, operand, P, grid, smem, st))) return rc;
   DCN_KERNEL_CHECK("umma_bwd_weight_kernel");
   return DCN_OK;
 }

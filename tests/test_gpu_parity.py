@@ -227,3 +227,39 @@ def test_detector_train_step_runs_and_learns():
         opt.step()
         losses.append(float(loss))
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+# ---- bf16 operand mode (BASELINE configs[3]: bf16 operands, fp32 accumulate) -------------------
+# Reference = the fp32 oracle evaluated on the bf16-ROUNDED x / weight / grad_out.  The engine adds
+# one bf16 rounding of each blended sample (relative 2^-9, random sign) before the MMA, hence the
+# looser, stated tolerances: forward 1e-2, gradients 2e-2 (max-abs error over max-abs value).
+BF16_FWD_TOL = 1e-2
+BF16_GRAD_TOL = 2e-2
+BF16_CASES = [
+    (2, 64, 64, 16, 16, 3, 1, 1, 1.5),
+    (2, 16, 32, 32, 32, 3, 2, 1, 1.0),
+    (2, 64, 128, 12, 20, 3, 1, 1, 2.0),
+    (1, 128, 128, 16, 16, 3, 1, 1, 1.0),
+]
+
+
+def _bf16_round(a):
+    return torch.as_tensor(a).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("variant", [dcn.VARIANT_TORCH, dcn.VARIANT_JITTOR])
+@pytest.mark.parametrize("case", BF16_CASES)
+def test_bf16_operand_forward(case, variant):
+    B, C, O, H, W, k, s, p, sigma = case
+    rng = np.random.default_rng(11)
+    sh = orc.make_shape(B, C, O, H, W, k, s, p, variant)
+    Ho, Wo = orc.out_hw(sh)
+    x = _bf16_round(rng.standard_normal((B, C, H, W)).astype(np.float32))
+    off = (rng.standard_normal((B, 18, Ho, Wo)) * sigma).astype(np.float32)
+    wt = _bf16_round((rng.standard_normal((O, C, 3, 3)) * (2.0 / (C * 9)) ** 0.5).astype(np.float32))
+    bias = rng.standard_normal(O).astype(np.float32)
+    ref = orc.forward(sh, x, off, wt, bias)
+    out = dcn.dcn_forward(_cuda(x).bfloat16(), _cuda(off), _cuda(wt).bfloat16(), _cuda(bias), k, s, p, variant,
+                          operand=dcn.OPERAND_BF16)
+    assert out.dtype == torch.float32
+    assert rel_err(out.cpu().numpy(), ref) < BF16_FWD_TOL
