@@ -161,6 +161,7 @@ int launch_corners(const Geo& g, const float* off, int32_t* y0, int32_t* x0, flo
 int simt_forward(const Geo& g, const float* x, const Tap* plan, const float* wt, const float* bias,
                  float* out, cudaStream_t st);
 int launch_offset_scale(const Geo& g, float* goff, cudaStream_t st);
+int launch_bias_grad(const Geo& g, const void* gout, int operand, float* gb, cudaStream_t st);
 enum { SIMT_BWD_DATA = 1, SIMT_BWD_WEIGHT = 2, SIMT_BWD_BIAS = 4, SIMT_BWD_ALL = 7 };
 int simt_backward(const Geo& g, int flags, const float* x, const Tap* plan, const float* wt,
                   const float* gout, float* gx, float* goff, float* gw, float* gb, cudaStream_t st,

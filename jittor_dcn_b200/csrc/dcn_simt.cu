@@ -12,6 +12,8 @@
 //                        coordinate-gradient reduction                (autograd, A.4)
 //   bwd_weight_kernel    gW = g^T * A with A re-sampled                (autograd, A.4)
 //   bias_grad / offset_scale kernels
+#include <cuda_bf16.h>
+
 #include "dcn_common.cuh"
 
 namespace dcn {
@@ -397,14 +399,14 @@ __global__ void __launch_bounds__(256) bwd_weight_kernel(Geo g, int chunks_per_s
 
 // grad_bias[o] = sum_{b, r} gout[b, o, r]: one block per (o, batch slice), float4 streaming
 // reads, block reduction, one red.global.add per block into a zeroed grad_bias.
-__global__ void __launch_bounds__(256) bias_grad_kernel(Geo g, int b_per_block,
-                                                        const float* __restrict__ gout,
+template <typename T>
+__global__ void __launch_bounds__(256) bias_grad_kernel(Geo g, int b_per_block, const T* __restrict__ gout,
                                                         float* __restrict__ gb) {
   const int o = blockIdx.x, b0 = blockIdx.y * b_per_block, b1 = min(g.B, b0 + b_per_block);
   float s = 0.f;
-  const bool vec = (g.HW & 3) == 0;
+  const bool vec = sizeof(T) == 4 && (g.HW & 3) == 0;
   for (int b = b0; b < b1; ++b) {
-    const float* row = gout + ((size_t)b * g.O + o) * g.HW;
+    const T* row = gout + ((size_t)b * g.O + o) * g.HW;
     if (vec) {
       const float4* r4 = reinterpret_cast<const float4*>(row);
       for (int r = threadIdx.x; r < (g.HW >> 2); r += blockDim.x) {
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(Geo g, int b_per_block,
         s += (v.x + v.y) + (v.z + v.w);
       }
     } else {
-      for (int r = threadIdx.x; r < g.HW; r += blockDim.x) s += __ldg(row + r);
+      for (int r = threadIdx.x; r < g.HW; r += blockDim.x) s += (float)row[r];
     }
   }
   __shared__ float red[8];
@@ -424,6 +426,23 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(Geo g, int b_per_block,
     for (int d = 4; d; d >>= 1) s += __shfl_xor_sync(0xffu, s, d);
     if (threadIdx.x == 0) atomicAdd(gb + o, s);
   }
+}
+
+// grad_bias (may be null) from float or bfloat16 grad_out
+int launch_bias_grad(const Geo& g, const void* gout, int operand, float* gb, cudaStream_t st) {
+  if (!gb) return DCN_OK;
+  DCN_CUDA_TRY(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)g.O, st));
+  // enough blocks to stream gout at full bandwidth: ~8 per SM
+  int slices = max(1, min(g.B, (148 * 8 + g.O - 1) / g.O));
+  const int bpb = (g.B + slices - 1) / slices;
+  slices = (g.B + bpb - 1) / bpb;
+  KernelScope scope("bias_grad_kernel", st);
+  if (operand == DCN_OPERAND_BF16)
+    bias_grad_kernel<__nv_bfloat16><<<dim3(g.O, slices), 256, 0, st>>>(g, bpb, (const __nv_bfloat16*)gout, gb);
+  else
+    bias_grad_kernel<float><<<dim3(g.O, slices), 256, 0, st>>>(g, bpb, (const float*)gout, gb);
+  DCN_KERNEL_CHECK("bias_grad_kernel");
+  return DCN_OK;
 }
 
 int launch_offset_scale(const Geo& g, float* goff, cudaStream_t st) {
@@ -473,14 +492,8 @@ int simt_backward(const Geo& g, int flags, const float* x, const Tap* plan, cons
     DCN_KERNEL_CHECK("bwd_weight_kernel");
   }
   if (gb && (parts & SIMT_BWD_BIAS)) {
-    DCN_CUDA_TRY(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)g.O, st));
-    // enough blocks to stream gout at full bandwidth: ~8 per SM
-    int slices = max(1, min(g.B, (148 * 8 + g.O - 1) / g.O));
-    const int bpb = (g.B + slices - 1) / slices;
-    slices = (g.B + bpb - 1) / bpb;
-    KernelScope scope("bias_grad_kernel", st);
-    bias_grad_kernel<<<dim3(g.O, slices), 256, 0, st>>>(g, bpb, gout, gb);
-    DCN_KERNEL_CHECK("bias_grad_kernel");
+    int rc = launch_bias_grad(g, gout, DCN_OPERAND_FP32, gb, st);
+    if (rc) return rc;
   }
   return DCN_OK;
 }

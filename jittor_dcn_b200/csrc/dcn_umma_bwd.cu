@@ -22,10 +22,10 @@ size_t umma_xt_bytes(const Geo& g, int operand);
 int umma_wgrad_any(const Geo& g, int operand, const void* xt, const float* off, const void* gout, float* gw,
                    cudaStream_t st);
 bool umma_bwd_data_supported(const Geo& g, int operand);
-size_t umma_bwd_data_wtile_bytes(const Geo& g);
-bool umma_bwd_data_fuses_wgrad(const Geo& g);
-int umma_bwd_data_fp32(const Geo& g, const float* xt, float* gxt, const float* off, const float* wt,
-                       const float* gout, float* goff, float* gw, uint8_t* wtiles, cudaStream_t st);
+size_t umma_bwd_data_wtile_bytes(const Geo& g, int operand);
+bool umma_bwd_data_fuses_wgrad(const Geo& g, int operand);
+int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, const float* off, const void* wt,
+                      const void* gout, float* goff, float* gw, uint8_t* wtiles, cudaStream_t st);
 
 static size_t plan_bytes(const Geo& g) { return align_up(sizeof(Tap) * (size_t)g.B * g.P, 1024); }
 
@@ -36,28 +36,25 @@ static bool use_umma_data(const Geo& g, int operand) {
 }
 
 bool umma_bwd_supported(const Geo& g, int operand) {
-  if (operand != DCN_OPERAND_FP32) return false;  // bf16 backward: not yet
-  return umma_wgrad_supported(g, operand);
+  if (!umma_wgrad_supported(g, operand)) return false;
+  // the generic data-gradient kernel is fp32 only: bf16 needs the tensor-path one
+  return operand == DCN_OPERAND_FP32 || umma_bwd_data_supported(g, operand);
 }
 
 size_t umma_bwd_workspace(const Geo& g, int operand) {
   // [xt] then either [gxt | Wm^T tiles] (tensor-path data gradient) or [sampling plan] (generic)
-  const size_t a = umma_xt_bytes(g, DCN_OPERAND_FP32) + umma_bwd_data_wtile_bytes(g);
-  const size_t b = plan_bytes(g);
+  const size_t a = umma_xt_bytes(g, DCN_OPERAND_FP32) + umma_bwd_data_wtile_bytes(g, operand);
+  const size_t b = operand == DCN_OPERAND_FP32 ? plan_bytes(g) : 0;
   return umma_xt_bytes(g, operand) + (a > b ? a : b);
 }
 
 int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, const float* off, const void* wtv,
                       const void* goutv, float* gx, float* goff, float* gw, float* gb, void* workspace,
                       cudaStream_t st) {
-  if (operand != DCN_OPERAND_FP32) {
-    set_error("umma backward: operand mode %d not implemented", operand);
-    return DCN_ERR_UNSUPPORTED;
-  }
-  const float* x = (const float*)xv;
-  const float* wt = (const float*)wtv;
-  const float* gout = (const float*)goutv;
-  float* xt = (float*)workspace;
+  const void* x = xv;
+  const void* wt = wtv;
+  const void* gout = goutv;
+  void* xt = workspace;
   uint8_t* rest = (uint8_t*)workspace + umma_xt_bytes(g, operand);
   Tiling t;
   if (!make_tiling(g, &t)) {
@@ -67,23 +64,25 @@ int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, cons
   int rc;
   if ((rc = launch_nchw_to_nhwc(g, t, x, xt, operand, st))) return rc;
   const bool want_gx = !(flags & DCN_FLAG_NO_GRAD_X) && gx != nullptr;
-  if (use_umma_data(g, DCN_OPERAND_FP32)) {
+  if (operand != DCN_OPERAND_FP32 || use_umma_data(g, operand)) {
     float* gxt = (float*)rest;
     uint8_t* wtiles = rest + umma_xt_bytes(g, DCN_OPERAND_FP32);
     if (want_gx) DCN_CUDA_TRY(cudaMemsetAsync(gxt, 0, sizeof(float) * (size_t)g.B * xt_image_stride(g), st));
     DCN_CUDA_TRY(cudaMemsetAsync(goff, 0, sizeof(float) * (size_t)g.B * 2 * g.N * g.HW, st));
-    const bool fused = umma_bwd_data_fuses_wgrad(g);  // one pass over the samples yields gW as well
+    const bool fused = umma_bwd_data_fuses_wgrad(g, operand);  // one pass over the samples yields gW as well
     if (fused) DCN_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.O * g.K, st));
-    if ((rc = umma_bwd_data_fp32(g, xt, want_gx ? gxt : nullptr, off, wt, gout, goff, gw, wtiles, st))) return rc;
+    if ((rc = umma_bwd_data_any(g, operand, xt, want_gx ? gxt : nullptr, off, wt, gout, goff, gw, wtiles, st)))
+      return rc;
     if ((rc = launch_offset_scale(g, goff, st))) return rc;
     if (want_gx && (rc = launch_nhwc_to_nchw_add(g, t, gxt, gx, (flags & DCN_FLAG_ACCUM_GRAD_X) ? 1 : 0, st)))
       return rc;
-    if ((rc = simt_backward(g, flags, x, nullptr, wt, gout, gx, goff, gw, gb, st, SIMT_BWD_BIAS))) return rc;
+    if ((rc = launch_bias_grad(g, gout, operand, gb, st))) return rc;
     if (fused) return DCN_OK;
   } else {
     Tap* plan = (Tap*)rest;
     if ((rc = launch_plan(g, off, plan, st))) return rc;
-    if ((rc = simt_backward(g, flags, x, plan, wt, gout, gx, goff, gw, gb, st, SIMT_BWD_DATA | SIMT_BWD_BIAS)))
+    if ((rc = simt_backward(g, flags, (const float*)x, plan, (const float*)wt, (const float*)gout, gx, goff, gw,
+                            gb, st, SIMT_BWD_DATA | SIMT_BWD_BIAS)))
       return rc;
   }
   return umma_wgrad_any(g, operand, xt, off, gout, gw, st);

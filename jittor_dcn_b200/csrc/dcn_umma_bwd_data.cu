@@ -24,6 +24,7 @@
 //   warps 18-19  grad_out converter (fp32 -> bf16 hi/lo, K-major A operand, once per tile)
 //   warps 20-23  plan: offsets -> bit-exact coordinate chain -> scatter entries (2-deep ring)
 #include <cstdlib>
+#include <type_traits>
 
 #include "dcn_umma.h"
 #include "dcn_umma_common.cuh"
@@ -55,10 +56,10 @@ struct __align__(16) ScatEntry {
 struct Params {
   Geo g;
   Tiling t;
-  const float* xt;       // channels-last x (coordinate gradient needs the corner values)
+  const void* xt;        // channels-last x, float or bfloat16 (coordinate gradient needs the corner values)
   float* gxt;            // channels-last grad_x accumulator (zeroed), may be null
   const float* off;
-  const float* gout;
+  const void* gout;      // float or bfloat16
   const uint8_t* wtiles; // [cblocks][OB][hi|lo][ncols x 64] K-major SW128 images of Wm^T
   float* goff;           // raw g_iy / g_ix accumulators (zeroed); scaled afterwards
   int Gt, Rt, chunks, num_inst, num_tiles;  // backward tiling (rows = (instance, channel))
@@ -177,18 +178,21 @@ __device__ __forceinline__ ScatEntry plan_finish(const Geo& g, const PlanWork& p
 }
 
 // RW = lanes that share one sampling point (32, or 16 when only 16 channels do)
-template <int VARIANT, int RW, bool FUSE>
+// BF  = bf16 operand mode: x / weight / grad_out are bfloat16, one image per operand, one MMA per K step
+template <int VARIANT, int RW, bool FUSE, bool BF>
 __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_constant__ Params P) {
+  constexpr int NIMG = BF ? 1 : 2;
+  typedef typename std::conditional<BF, __nv_bfloat16, float>::type XT;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const Geo& g = P.g;
   // carve-up: [grad_out tile: OB x (hi | lo)] [2 Wm^T stages] [plan x2] [barriers]
   uint8_t* gtile = smem;
-  uint8_t* wstage = gtile + (size_t)P.g_imgs * 2 * P.g_img;
+  uint8_t* wstage = gtile + (size_t)P.g_imgs * NIMG * P.g_img;
   // fused: 2 buffers of the sample operand S, each [hi | lo][128 tile rows x 64 columns], MN-major
   // (the 64 columns of a block are contiguous in a row, so a lane stores 8 columns with one STS.128)
   uint8_t* sbuf = wstage + 2 * (size_t)P.w_stage;
-  const uint32_t s_img = 128u * 128u, s_buf = FUSE ? 2u * s_img : 0u;
+  const uint32_t s_img = 128u * 128u, s_buf = FUSE ? NIMG * s_img : 0u;
   ScatEntry* plan = reinterpret_cast<ScatEntry*>(sbuf + 2 * (size_t)s_buf);
   uint64_t* bars = reinterpret_cast<uint64_t*>(plan + 2 * P.plan_cap);
   uint64_t* wfull = bars;        // [2]
@@ -281,7 +285,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
           slot = n - (cb * 128) / g.C;
         }
         // byte-addressed image bases: address = base + zero-extended 32-bit offset (2 instructions)
-        const char* ximg = reinterpret_cast<const char*>(P.xt + (size_t)bimg * img_stride + chan);
+        const char* ximg =
+            reinterpret_cast<const char*>(reinterpret_cast<const XT*>(P.xt) + (size_t)bimg * img_stride + chan);
         char* gimg = P.gxt ? reinterpret_cast<char*>(P.gxt + (size_t)bimg * img_stride + chan) : nullptr;
         mbar_wait_relaxed(&tfull[acc], acc_phase, 32);
         mbar_wait_relaxed(&pfull[pb], pphase, 32);
@@ -308,10 +313,12 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
             const uint4 off = *reinterpret_cast<const uint4*>(e->off);
             const float4 w = *reinterpret_cast<const float4*>(e->w);
             const float2 f = *reinterpret_cast<const float2*>(&e->fx);
-            const float v0 = __ldg(reinterpret_cast<const float*>(ximg + off.x));
-            const float v1 = __ldg(reinterpret_cast<const float*>(ximg + off.y));
-            const float v2 = __ldg(reinterpret_cast<const float*>(ximg + off.z));
-            const float v3 = __ldg(reinterpret_cast<const float*>(ximg + off.w));
+            // entry offsets are bytes of the float grad image; the bf16 x image is half as wide
+            constexpr int XS = BF ? 1 : 0;
+            const float v0 = (float)__ldg(reinterpret_cast<const XT*>(ximg + (off.x >> XS)));
+            const float v1 = (float)__ldg(reinterpret_cast<const XT*>(ximg + (off.y >> XS)));
+            const float v2 = (float)__ldg(reinterpret_cast<const XT*>(ximg + (off.z >> XS)));
+            const float v3 = (float)__ldg(reinterpret_cast<const XT*>(ximg + (off.w >> XS)));
             if (gimg) {
               // zero-weight corners are out of the image (or the whole column is padding):
               // predicated red.global, no branches
@@ -334,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
             split_pair(smp8[6], smp8[7], hi.w, lo.w);
             const uint32_t so = (uint32_t)((((c0 >> 3) ^ m) & 7) << 4);
             *reinterpret_cast<uint4*>(s_row + so) = hi;
-            *reinterpret_cast<uint4*>(s_row + s_img + so) = lo;
+            if (!BF) *reinterpret_cast<uint4*>(s_row + s_img + so) = lo;
           }
           // butterfly reduce-scatter over the RW lanes that share the sampling points:
           // afterwards lane gl (< 16) holds the total of value index gl
@@ -421,13 +428,15 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
         const uint32_t d_tmem = d2_base + (uint32_t)((cb - cb0) * ncols);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // 8 steps of 16 tile rows
-          const uint64_t dgh = make_sdesc_sw128(g_hi + ks * 2048, 2 * P.g_img, 1024);
-          const uint64_t dgl = make_sdesc_sw128(g_lo + ks * 2048, 2 * P.g_img, 1024);
+          const uint64_t dgh = make_sdesc_sw128(g_hi + ks * 2048, NIMG * P.g_img, 1024);
+          const uint64_t dgl = make_sdesc_sw128(g_lo + ks * 2048, NIMG * P.g_img, 1024);
           const uint64_t dsh = make_sdesc_sw128(sbase + ks * 2048, 1024, 1024);
           const uint64_t dsl = make_sdesc_sw128(sbase + s_img + ks * 2048, 1024, 1024);
           umma_bf16(d_tmem, dgh, dsh, idesc_w, (first && ks == 0) ? 0u : 1u);
-          umma_bf16(d_tmem, dgh, dsl, idesc_w, 1u);
-          umma_bf16(d_tmem, dgl, dsh, idesc_w, 1u);
+          if (!BF) {
+            umma_bf16(d_tmem, dgh, dsl, idesc_w, 1u);
+            umma_bf16(d_tmem, dgl, dsh, idesc_w, 1u);
+          }
         }
         umma_commit(&sempty[sb]);
         sb ^= 1;
@@ -445,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
             tc_fence_after();
             // resident converted grad_out image and streamed Wm^T image; Torch: A = grad_out rows,
             // B = Wm^T columns; Jittor: A = Wm^T lanes, B = grad_out pixels
-            const uint32_t r_hi = smem_u32(gtile + (size_t)ob * 2 * P.g_img);
+            const uint32_t r_hi = smem_u32(gtile + (size_t)ob * NIMG * P.g_img);
             const uint32_t r_lo = r_hi + P.g_img;
             const uint32_t w_hi = smem_u32(wstage + (size_t)s * P.w_stage);
             const uint32_t w_lo = w_hi + (P.w_stage >> 1);
@@ -460,8 +469,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
               const uint64_t dbh = make_sdesc_sw128(b_hi + k4 * 32, 16, 1024);
               const uint64_t dbl = make_sdesc_sw128(b_lo + k4 * 32, 16, 1024);
               umma_bf16(d_tmem, dah, dbh, idesc, (ob | k4) ? 1u : 0u);
-              umma_bf16(d_tmem, dah, dbl, idesc, 1u);
-              umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+              if (!BF) {
+                umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+                umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+              }
             }
             umma_commit(&wempty[s]);
             s ^= 1;
@@ -503,7 +514,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
     uint32_t gphase = 0;
     if (FUSE) {
       // images beyond OB (the o >= 64*OB half of the M = 128 weight-gradient MMA) stay zero
-      for (uint32_t i = (uint32_t)P.OB * 2 * P.g_img + ct * 16; i < (uint32_t)P.g_imgs * 2 * P.g_img;
+      for (uint32_t i = (uint32_t)P.OB * NIMG * P.g_img + ct * 16; i < (uint32_t)P.g_imgs * NIMG * P.g_img;
            i += kConvWarps * 32 * 16)
         *reinterpret_cast<uint4*>(gtile + i) = make_uint4(0, 0, 0, 0);
     }
@@ -517,30 +528,31 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
         float v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = 0.f;
-        const float* src = nullptr;
+        const XT* src = nullptr;
+        const XT* gsrc = reinterpret_cast<const XT*>(P.gout);
         if (VARIANT == DCN_VARIANT_TORCH) {
           const int il2 = mm / P.Gt, i2 = mm - il2 * P.Gt;
           const RowInfo ri = decode(P, tile * P.Rt + il2);
           if (ri.valid)
-            src = P.gout + ((size_t)ri.b * g.O + og * 8) * g.HW + ri.r0 + (size_t)(ri.chunk * P.Gt + i2) * P.t.R;
+            src = gsrc + ((size_t)ri.b * g.O + og * 8) * g.HW + ri.r0 + (size_t)(ri.chunk * P.Gt + i2) * P.t.R;
         } else {
           const int b = tile / P.pix_blocks, p = (tile - b * P.pix_blocks) * ncols + mm;
-          if (p < g.HW) src = P.gout + ((size_t)b * g.O + og * 8) * g.HW + p;
+          if (p < g.HW) src = gsrc + ((size_t)b * g.O + og * 8) * g.HW + p;
         }
         if (src) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            if (og * 8 + k < g.O) v[k] = __ldg(src + (size_t)k * g.HW);
+            if (og * 8 + k < g.O) v[k] = (float)__ldg(src + (size_t)k * g.HW);
         }
         uint4 hi, lo;
         split_pair(v[0], v[1], hi.x, lo.x);
         split_pair(v[2], v[3], hi.y, lo.y);
         split_pair(v[4], v[5], hi.z, lo.z);
         split_pair(v[6], v[7], hi.w, lo.w);
-        uint8_t* img = gtile + (size_t)(og >> 3) * 2 * P.g_img;
+        uint8_t* img = gtile + (size_t)(og >> 3) * NIMG * P.g_img;
         const uint32_t so = kmajor_sw128_off(mm, (og & 7) * 8);
         *reinterpret_cast<uint4*>(img + so) = hi;
-        *reinterpret_cast<uint4*>(img + P.g_img + so) = lo;
+        if (!BF) *reinterpret_cast<uint4*>(img + P.g_img + so) = lo;
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -592,27 +604,30 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
 }
 
 // Wm^T images: tiles[cb][ob][hl][K-major SW128 image of ncols rows (j) x 64 (o)]
+template <typename T>
 __global__ void __launch_bounds__(256) weight_tiles_bwd_kernel(Geo g, int ncols, int cblocks, int OB,
-                                                               const float* __restrict__ wt,
+                                                               const T* __restrict__ wt,
                                                                uint8_t* __restrict__ tiles) {
+  constexpr int NIMG = sizeof(T) == 2 ? 1 : 2;
   const int total = cblocks * ncols * OB * 64;
   const uint32_t img = (uint32_t)ncols * 128;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int o = i % (OB * 64), jj = i / (OB * 64);  // lanes along o: Wm[o, j] strided reads, small
     const int cb = jj / ncols, jl = jj - cb * ncols, ob = o >> 6, ol = o & 63;
-    const float v = (o < g.O && jj < g.K) ? __ldg(wt + (size_t)o * g.K + jj) : 0.f;
+    const float v = (o < g.O && jj < g.K) ? (float)wt[(size_t)o * g.K + jj] : 0.f;
     __nv_bfloat16 hi, lo;
     ptx::split_bf16(v, hi, lo);
-    uint8_t* base = tiles + (size_t)(cb * OB + ob) * 2 * img + ptx::kmajor_sw128_off(jl, ol);
+    uint8_t* base = tiles + (size_t)(cb * OB + ob) * NIMG * img + ptx::kmajor_sw128_off(jl, ol);
     *reinterpret_cast<__nv_bfloat16*>(base) = hi;
-    *reinterpret_cast<__nv_bfloat16*>(base + img) = lo;
+    if (NIMG == 2) *reinterpret_cast<__nv_bfloat16*>(base + img) = lo;
   }
 }
 
 }  // namespace bd
 
 // ---------------------------------------------------------------------------- host side
-static bool bwd_data_tiling(const Geo& g, bd::Params* P, bool allow_fuse = true) {
+static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow_fuse = true) {
+  const size_t nimg = operand == DCN_OPERAND_BF16 ? 1 : 2;
   if (!make_tiling(g, &P->t)) return false;
   P->fuse_w = 0;
   P->gw = nullptr;
@@ -642,8 +657,8 @@ static bool bwd_data_tiling(const Geo& g, bd::Params* P, bool allow_fuse = true)
     if (allow_fuse && g.O <= 128) {
       const int ncols = 64;
       const size_t plan = 2 * (size_t)P->Rt * ncols * sizeof(bd::ScatEntry);
-      const size_t smem = 2 * 2 * (size_t)bd::kGImg + 2 * (size_t)(2 * ncols * 128) + 2 * 2 * (size_t)(128 * 128) +
-                          plan + 256 + 1024;
+      const size_t smem = 2 * nimg * (size_t)bd::kGImg + 2 * (size_t)(nimg * ncols * 128) +
+                          2 * nimg * (size_t)(128 * 128) + plan + 256 + 1024;
       if (P->Rt * ncols <= bd::kPlanMax && smem <= 227 * 1024) {
         P->fuse_w = 1;
         P->g_imgs = 2;
@@ -651,7 +666,7 @@ static bool bwd_data_tiling(const Geo& g, bd::Params* P, bool allow_fuse = true)
         P->cblocks = (g.K + ncols - 1) / ncols;
         P->plan_cap = P->Rt * ncols;
         P->g_img = bd::kGImg;
-        P->w_stage = 2u * ncols * 128;
+        P->w_stage = (uint32_t)nimg * ncols * 128;
         P->tmem_cols = 512;
         int max_cb = 6;  // 512 TMEM columns - 2 gA buffers
         if (const char* e = getenv("DCN_BWD_SLICE_CB")) max_cb = atoi(e) < 1 ? 1 : (atoi(e) > 6 ? 6 : atoi(e));
@@ -664,13 +679,13 @@ static bool bwd_data_tiling(const Geo& g, bd::Params* P, bool allow_fuse = true)
     // columns per accumulator block: 128 unless the plan ring / operand tiles would not fit
     for (int ncols : {128, 64}) {
       const size_t plan = 2 * (size_t)P->Rt * ncols * sizeof(bd::ScatEntry);
-      const size_t smem = (size_t)P->OB * 2 * bd::kGImg + 2 * (size_t)(2 * ncols * 128) + plan + 256 + 1024;
+      const size_t smem = (size_t)P->OB * nimg * bd::kGImg + 2 * (size_t)(nimg * ncols * 128) + plan + 256 + 1024;
       if (P->Rt * ncols <= bd::kPlanMax && smem <= 227 * 1024) {
         P->ncols = ncols;
         P->cblocks = (g.K + ncols - 1) / ncols;
         P->plan_cap = P->Rt * ncols;
         P->g_img = bd::kGImg;
-        P->w_stage = 2u * ncols * 128;
+        P->w_stage = (uint32_t)nimg * ncols * 128;
         P->tmem_cols = 2 * ncols;
         return true;
       }
@@ -683,7 +698,7 @@ static bool bwd_data_tiling(const Geo& g, bd::Params* P, bool allow_fuse = true)
   const int taps = g.C >= 128 ? 1 : 128 / g.C;
   for (int ncols : {128, 64}) {
     const size_t plan = 2 * (size_t)taps * ncols * sizeof(bd::ScatEntry);
-    const size_t smem = (size_t)P->OB * 2 * (ncols * 128) + 2 * (size_t)(2 * 128 * 128) + plan + 256 + 1024;
+    const size_t smem = (size_t)P->OB * nimg * (ncols * 128) + 2 * (size_t)(nimg * 128 * 128) + plan + 256 + 1024;
     if (taps * ncols <= bd::kPlanMax && smem <= 227 * 1024) {
       P->ncols = ncols;
       P->pix_blocks = (g.HW + ncols - 1) / ncols;
@@ -691,7 +706,7 @@ static bool bwd_data_tiling(const Geo& g, bd::Params* P, bool allow_fuse = true)
       P->cblocks = (g.K + 127) / 128;
       P->plan_cap = taps * ncols;
       P->g_img = (uint32_t)ncols * 128;
-      P->w_stage = 2u * 128 * 128;
+      P->w_stage = (uint32_t)nimg * 128 * 128;
       P->tmem_cols = 2 * ncols;
       return true;
     }
@@ -706,33 +721,35 @@ static bool fuse_allowed() {
 }
 
 bool umma_bwd_data_supported(const Geo& g, int operand) {
-  if (operand != DCN_OPERAND_FP32) return false;
+  if (operand != DCN_OPERAND_FP32 && operand != DCN_OPERAND_BF16) return false;
   bd::Params P;
   P.g = g;
-  return bwd_data_tiling(g, &P, fuse_allowed());
+  return bwd_data_tiling(g, operand, &P, fuse_allowed());
 }
 
-// does umma_bwd_data_fp32 also produce grad_weight for this shape?
-bool umma_bwd_data_fuses_wgrad(const Geo& g) {
+// does umma_bwd_data_any also produce grad_weight for this shape?
+bool umma_bwd_data_fuses_wgrad(const Geo& g, int operand) {
   bd::Params P;
   P.g = g;
-  return bwd_data_tiling(g, &P, fuse_allowed()) && P.fuse_w;
+  return bwd_data_tiling(g, operand, &P, fuse_allowed()) && P.fuse_w;
 }
 
-size_t umma_bwd_data_wtile_bytes(const Geo& g) {
+size_t umma_bwd_data_wtile_bytes(const Geo& g, int operand) {
   bd::Params P;
   P.g = g;
-  if (!bwd_data_tiling(g, &P, fuse_allowed())) return 0;
+  if (!bwd_data_tiling(g, operand, &P, fuse_allowed())) return 0;
   return align_up((size_t)P.cblocks * P.OB * P.w_stage, 1024);
 }
 
 // gxt (channels-last grad_x, may be null), goff and — when the shape fuses the weight gradient
 // (umma_bwd_data_fuses_wgrad) — gw must be zero on entry.
-int umma_bwd_data_fp32(const Geo& g, const float* xt, float* gxt, const float* off, const float* wt,
-                       const float* gout, float* goff, float* gw, uint8_t* wtiles, cudaStream_t st) {
+int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, const float* off, const void* wt,
+                      const void* gout, float* goff, float* gw, uint8_t* wtiles, cudaStream_t st) {
   bd::Params P;
   P.g = g;
-  if (!bwd_data_tiling(g, &P, fuse_allowed())) {
+  const bool bf = operand == DCN_OPERAND_BF16;
+  const size_t nimg = bf ? 1 : 2;
+  if (!bwd_data_tiling(g, operand, &P, fuse_allowed())) {
     set_error("umma bwd_data: shape not tileable");
     return DCN_ERR_UNSUPPORTED;
   }
@@ -741,8 +758,12 @@ int umma_bwd_data_fp32(const Geo& g, const float* xt, float* gxt, const float* o
     const int rows = g.variant == DCN_VARIANT_TORCH ? P.ncols : 128;
     const int total = P.cblocks * rows * P.OB * 64;
     KernelScope scope("weight_tiles_bwd_kernel", st);
-    bd::weight_tiles_bwd_kernel<<<min((total + 255) / 256, 2048), 256, 0, st>>>(g, rows, P.cblocks, P.OB, wt,
-                                                                              wtiles);
+    if (bf)
+      bd::weight_tiles_bwd_kernel<__nv_bfloat16><<<min((total + 255) / 256, 2048), 256, 0, st>>>(
+          g, rows, P.cblocks, P.OB, (const __nv_bfloat16*)wt, wtiles);
+    else
+      bd::weight_tiles_bwd_kernel<float><<<min((total + 255) / 256, 2048), 256, 0, st>>>(g, rows, P.cblocks, P.OB,
+                                                                                       (const float*)wt, wtiles);
     DCN_KERNEL_CHECK("weight_tiles_bwd_kernel");
   }
   P.xt = xt;
@@ -752,8 +773,8 @@ int umma_bwd_data_fp32(const Geo& g, const float* xt, float* gxt, const float* o
   P.wtiles = wtiles;
   P.goff = goff;
   P.gw = gw;
-  const size_t smem = (size_t)P.g_imgs * 2 * P.g_img + 2 * (size_t)P.w_stage +
-                      (P.fuse_w ? 2 * 2 * (size_t)(128 * 128) : 0) +
+  const size_t smem = (size_t)P.g_imgs * nimg * P.g_img + 2 * (size_t)P.w_stage +
+                      (P.fuse_w ? 2 * nimg * (size_t)(128 * 128) : 0) +
                       2 * (size_t)P.plan_cap * sizeof(bd::ScatEntry) + 256 + 1024;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -767,11 +788,17 @@ int umma_bwd_data_fp32(const Geo& g, const float* xt, float* gxt, const float* o
   }
   const bool narrow = g.variant == DCN_VARIANT_TORCH ? P.Gt == 16 : g.C == 16;  // 16 channels per sampling point
   KernelScope scope("umma_bwd_data_kernel", st);
-#define DCN_LAUNCH_BD(V, RW, F)                                                                                  \
-  do {                                                                                                           \
-    DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<V, RW, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      (int)smem));                                                               \
-    bd::bwd_data_kernel<V, RW, F><<<grid, bd::kThreads, smem, st>>>(P);                                          \
+#define DCN_LAUNCH_BD(V, RW, F)                                                                          \
+  do {                                                                                                   \
+    if (bf) {                                                                                            \
+      DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<V, RW, F, true>,                             \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+      bd::bwd_data_kernel<V, RW, F, true><<<grid, bd::kThreads, smem, st>>>(P);                          \
+    } else {                                                                                             \
+      DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<V, RW, F, false>,                            \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+      bd::bwd_data_kernel<V, RW, F, false><<<grid, bd::kThreads, smem, st>>>(P);                         \
+    }                                                                                                    \
   } while (0)
   if (g.variant == DCN_VARIANT_TORCH) {
     if (P.fuse_w) {

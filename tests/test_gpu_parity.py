@@ -263,3 +263,39 @@ def test_bf16_operand_forward(case, variant):
                           operand=dcn.OPERAND_BF16)
     assert out.dtype == torch.float32
     assert rel_err(out.cpu().numpy(), ref) < BF16_FWD_TOL
+
+
+@pytest.mark.parametrize("variant", [dcn.VARIANT_TORCH, dcn.VARIANT_JITTOR])
+@pytest.mark.parametrize("case", BF16_CASES)
+def test_bf16_operand_backward(case, variant):
+    B, C, O, H, W, k, s, p, sigma = case
+    rng = np.random.default_rng(12)
+    sh = orc.make_shape(B, C, O, H, W, k, s, p, variant)
+    Ho, Wo = orc.out_hw(sh)
+    x = _bf16_round(rng.standard_normal((B, C, H, W)).astype(np.float32))
+    off = (rng.standard_normal((B, 18, Ho, Wo)) * sigma).astype(np.float32)
+    wt = _bf16_round((rng.standard_normal((O, C, 3, 3)) * (2.0 / (C * 9)) ** 0.5).astype(np.float32))
+    gout = _bf16_round(rng.standard_normal((B, O, Ho, Wo)).astype(np.float32))
+    ref = orc.backward(sh, x, off, wt, gout)
+    got = dcn.dcn_backward(_cuda(x).bfloat16(), _cuda(off), _cuda(wt).bfloat16(), _cuda(gout).bfloat16(), True,
+                           k, s, p, variant, operand=dcn.OPERAND_BF16)
+    for g_, r_, nm in zip(got, ref, ("gx", "goff", "gw", "gb")):
+        assert g_.dtype == torch.float32
+        assert rel_err(g_.cpu().numpy(), r_) < BF16_GRAD_TOL, nm
+
+
+def test_bf16_module_autograd():
+    """bf16 operand mode through the module: parameters stay fp32, activations are cast."""
+    torch.manual_seed(0)
+    m = dcn.TorchDeformConv2d(64, 64, 3, 1, 1).cuda()
+    m.operand = dcn.OPERAND_BF16
+    with torch.no_grad():
+        m.offset_conv.bias.normal_(0, 1.0)
+    x = torch.randn(2, 64, 16, 16, device="cuda", requires_grad=True)
+    out = m(x)
+    out.sum().backward()
+    assert out.dtype == torch.float32 and x.grad.dtype == torch.float32 and m.weight.grad.dtype == torch.float32
+    m32 = dcn.TorchDeformConv2d(64, 64, 3, 1, 1).cuda()
+    m32.load_state_dict(m.state_dict())
+    out32 = m32(x.detach())
+    assert rel_err(out.detach().cpu().numpy(), out32.detach().cpu().numpy()) < 2e-2
