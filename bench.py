@@ -39,6 +39,10 @@ WORKLOADS = {
              1024, 16, 32, 128, 128, 3, 2, 1),
     "det5": ("detector conv5 128->256 3x3 s2 p1, 16x16, batch 1024 per GPU (BASELINE configs[4] layer), fwd+bwd",
              1024, 128, 256, 16, 16, 3, 2, 1),
+    "c3": ("ResNet-50 C3 DCN layer 128->128 3x3 s1 p1, 56x56, batch 128 per GPU (BASELINE configs[3] layer), fwd+bwd",
+           128, 128, 128, 56, 56, 3, 1, 1),
+    "c4": ("ResNet-50 C4 DCN layer 256->256 3x3 s1 p1, 28x28, batch 128 per GPU (BASELINE configs[3] layer), fwd+bwd",
+           128, 256, 256, 28, 28, 3, 1, 1),
 }
 # BASELINE configs[4]: whole toy-detector training step, global batch 1024 sharded over the GPUs
 DETECTOR_DESC = ("detector: data-parallel DCN detector training step (train.py:142-175 topology, 4 DeformConv2d "
@@ -55,6 +59,9 @@ def parse_args():
     ap.add_argument("--global-batch", type=int, default=1024, help="detector workload: global batch")
     ap.add_argument("--variant", default="torch", choices=["torch", "jittor"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--operand", default="fp32", choices=["fp32", "bf16"],
+                    help="fp32 (reference parity, bf16 hi/lo split on the tensor cores) or bf16 storage of "
+                         "x / weight / grad_out with fp32 accumulation (BASELINE configs[3])")
     ap.add_argument("--offset-sigma", type=float, default=2.0,
                     help="std (pixels) of the synthetic live offsets (SURVEY 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -120,10 +127,11 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def layer_bytes_flops(B, C, O, H, W, Ho, Wo, N):
-    """Algorithmic work, per launch of each role, float32."""
+def layer_bytes_flops(B, C, O, H, W, Ho, Wo, N, act_bytes=4):
+    """Algorithmic work, per launch of each role; act_bytes = 2 in bf16 operand mode
+    for x, weight and grad_out (out and all gradients stay float32)."""
     K = C * N
-    x, off, out, wgt = 4 * B * C * H * W, 4 * B * 2 * N * Ho * Wo, 4 * B * O * Ho * Wo, 4 * O * K
+    x, off, out, wgt = act_bytes * B * C * H * W, 4 * B * 2 * N * Ho * Wo, 4 * B * O * Ho * Wo, act_bytes * O * K
     flops = 2.0 * B * Ho * Wo * K * O
     return {
         "fwd": dict(bytes=x + off + out + wgt, flops=flops),
@@ -357,17 +365,19 @@ def main():
     desc, B, C, O, H, W, k, s, p = WORKLOADS[args.workload]
     variant = dcn.VARIANT_TORCH if args.variant == "torch" else dcn.VARIANT_JITTOR
     flags = dcn.FLAG_FORCE_SIMT if args.force_simt else 0
+    operand = dcn.OPERAND_BF16 if args.operand == "bf16" else dcn.OPERAND_FP32
+    act = torch.bfloat16 if operand == dcn.OPERAND_BF16 else torch.float32
     N = k * k
-    shp = dcn.make_shape(B, C, O, H, W, k, s, p, variant, flags=flags)
+    shp = dcn.make_shape(B, C, O, H, W, k, s, p, variant, operand=operand, flags=flags)
     Ho, Wo = _lib.output_hw(shp)
 
     # ---- synthetic data, resident in HBM (seeded per rank) ---------------------------
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x = torch.randn(B, C, H, W, device=dev, generator=gen)
+    x = torch.randn(B, C, H, W, device=dev, generator=gen).to(act)
     off = torch.randn(B, 2 * N, Ho, Wo, device=dev, generator=gen) * args.offset_sigma
-    wt = torch.randn(O, C, k, k, device=dev, generator=gen) * (2.0 / (C * N)) ** 0.5
+    wt = (torch.randn(O, C, k, k, device=dev, generator=gen) * (2.0 / (C * N)) ** 0.5).to(act)
     bias = torch.randn(O, device=dev, generator=gen) * 0.1
-    gout = torch.randn(B, O, Ho, Wo, device=dev, generator=gen)
+    gout = torch.randn(B, O, Ho, Wo, device=dev, generator=gen).to(act)
     # flat gradient bucket: [grad_weight | grad_bias | offset_conv.weight.grad | offset_conv.bias.grad]
     n_w, n_b, n_ow, n_ob = O * C * N, O, 2 * N * C * N, 2 * N
     bucket = torch.zeros(n_w + n_b + n_ow + n_ob, device=dev)
@@ -383,8 +393,8 @@ def main():
     stream = torch.cuda.current_stream(dev)
 
     def step():
-        out = dcn.dcn_forward(x, off, wt, bias, k, s, p, variant, flags=flags)
-        gx, goff, gw, gb = dcn.dcn_backward(x, off, wt, gout, True, k, s, p, variant, flags=flags)
+        out = dcn.dcn_forward(x, off, wt, bias, k, s, p, variant, operand=operand, flags=flags)
+        gx, goff, gw, gb = dcn.dcn_backward(x, off, wt, gout, True, k, s, p, variant, operand=operand, flags=flags)
         if comm is not None:
             bucket[:n_w].copy_(gw.view(-1))
             bucket[n_w:n_w + n_b].copy_(gb)
@@ -408,7 +418,7 @@ def main():
     _lib.profile_begin()
     # L2 hygiene: workloads whose inputs fit in the 126 MB L2 get it flushed (a 512 MB write)
     # between timed iterations; the flush is outside the per-step event pairs.
-    needs_flush = (x.numel() + gout.numel()) * 4 < 400e6
+    needs_flush = (x.numel() + gout.numel()) * x.element_size() < 400e6
     flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if needs_flush else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps if needs_flush else 1)]
@@ -441,7 +451,7 @@ def main():
     barrier()
     fe0.record(stream)
     for _ in range(args.steps):
-        dcn.dcn_forward(x, off, wt, bias, k, s, p, variant, flags=flags)
+        dcn.dcn_forward(x, off, wt, bias, k, s, p, variant, operand=operand, flags=flags)
     fe1.record(stream)
     barrier()
     fwd_ms = fe0.elapsed_time(fe1) / args.steps
@@ -453,7 +463,7 @@ def main():
 
     # ---- roofline of the dominant kernel ------------------------------------------------
     pk = peaks()
-    work = layer_bytes_flops(B, C, O, H, W, Ho, Wo, N)
+    work = layer_bytes_flops(B, C, O, H, W, Ho, Wo, N, act_bytes=x.element_size())
     roofline, kernels = None, {}
     for name, (cnt, tot_ms) in prof.items():
         kernels[name] = {"launches": cnt, "avg_ms": tot_ms / max(cnt, 1), "share": tot_ms / max(elapsed_ms, 1e-9)}
@@ -488,6 +498,7 @@ def main():
         cls = dcn.TorchDeformConv2d if args.variant == "torch" else dcn.TorchDeformConv2dJittorSemantics
         layer = cls(C, O, k, s, p).to(dev)
         layer.engine_flags = flags
+        layer.operand = operand
         with torch.no_grad():
             layer.offset_conv.weight.normal_(0, 0.01)
             layer.offset_conv.bias.normal_(0, 1.0)
@@ -564,15 +575,16 @@ def main():
         line = {
             "metric": "DeformConv2d fwd+bwd images/sec", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if operand == dcn.OPERAND_BF16 else "f32",
             "data": "synthetic",
-            "config": {"workload": args.workload + ": " + desc, "variant": args.variant,
+            "config": {"workload": args.workload + ": " + desc, "variant": args.variant, "operand": args.operand,
                        "batch_per_gpu": B, "global_batch": world * B, "offset_sigma_px": args.offset_sigma,
                        "path_fwd": lib.dcn_path_name(ctypes.byref(shp), 0).decode(),
                        "path_bwd": lib.dcn_path_name(ctypes.byref(shp), 1).decode(),
                        "l2": ("L2 flushed (512 MB write) between timed iterations" if needs_flush else
                               "inputs (x %.0f MB + gout %.0f MB) exceed the 126 MB L2; no flush needed"
-                              % (x.numel() * 4 / 1e6, gout.numel() * 4 / 1e6)),
+                              % (x.numel() * x.element_size() / 1e6, gout.numel() * gout.element_size() / 1e6)),
                        "allreduce": allreduce_kind, "parallelism": f"dp{world}"},
             "roofline": roofline, "kernels": kernels, "fwd_only": fwd_only, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
