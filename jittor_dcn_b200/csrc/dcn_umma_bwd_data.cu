@@ -75,7 +75,8 @@ struct Params {
   int fuse_w;            // 0 / 1
   float* gw;             // [O, K], zeroed
   int nslices, nchunks, cb_per_slice;  // CTA = (slice of column blocks, chunk of tiles)
-  int g_imgs;            // grad_out images kept per tile: OB, or 2 when fused (M = 128 of the o axis)
+  int g_imgs;            // grad_out images the MMAs address per tile: OB, or 2 when fused (M = 128 of the o axis)
+  int g_nbuf;            // 1 or 2 buffers of the converted grad_out tile (2 hides the conversion of the next tile)
   uint32_t g_img;        // bytes of one bf16 image of the resident grad_out operand (rows x 128 B)
   uint32_t w_stage;      // bytes of one Wm^T stage (hi | lo)
   uint32_t tmem_cols;
@@ -187,8 +188,11 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const Geo& g = P.g;
   // carve-up: [grad_out tile: OB x (hi | lo)] [2 Wm^T stages] [plan x2] [barriers]
+  // [g_nbuf buffers x OB real images][zero images completing the M = 128 o-axis when fused]
   uint8_t* gtile = smem;
-  uint8_t* wstage = gtile + (size_t)P.g_imgs * NIMG * P.g_img;
+  const uint32_t g_buf = (uint32_t)P.OB * NIMG * P.g_img;
+  const uint32_t g_zero_off = (uint32_t)P.g_nbuf * g_buf;
+  uint8_t* wstage = gtile + g_zero_off + (size_t)(P.g_imgs - P.OB) * NIMG * P.g_img;
   // fused: 2 buffers of the sample operand S, each [hi | lo][128 tile rows x 64 columns], MN-major
   // (the 64 columns of a block are contiguous in a row, so a lane stores 8 columns with one STS.128)
   uint8_t* sbuf = wstage + 2 * (size_t)P.w_stage;
@@ -201,12 +205,12 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
   uint64_t* tempty = bars + 6;   // [2]
   uint64_t* pfull = bars + 8;    // [2]
   uint64_t* pempty = bars + 10;  // [2]
-  uint64_t* gfull = bars + 12;   // [1]
-  uint64_t* gempty = bars + 13;  // [1]
-  uint64_t* sfull = bars + 14;   // [2] sample operand written (fused)
-  uint64_t* sempty = bars + 16;  // [2]
-  uint64_t* dfull = bars + 18;   // [1] weight-gradient accumulators final
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* gfull = bars + 12;   // [2] converted grad_out tile
+  uint64_t* gempty = bars + 14;  // [2]
+  uint64_t* sfull = bars + 16;   // [2] sample operand written (fused)
+  uint64_t* sempty = bars + 18;  // [2]
+  uint64_t* dfull = bars + 20;   // [1] weight-gradient accumulators final
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ncols = P.ncols;
@@ -220,9 +224,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
       mbar_init(&pfull[a], kPlanWarps);
       mbar_init(&pempty[a], kScatWarps);
     }
-    mbar_init(gfull, kConvWarps);
-    mbar_init(gempty, 1);
     for (int a = 0; a < 2; ++a) {
+      mbar_init(&gfull[a], kConvWarps);
+      mbar_init(&gempty[a], 1);
       mbar_init(&sfull[a], kScatWarps);
       mbar_init(&sempty[a], 1);
     }
@@ -415,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, ncols, false, false);
       const uint32_t idesc_w = make_idesc_bf16(128, ncols, true, true);  // A = g^T and B = S, both MN-major
-      int s = 0, acc = 0, sb = 0;
+      int s = 0, acc = 0, sb = 0, gb = 0;
       uint32_t phase = 0, acc_phase = 0, gphase = 0, sphase = 0;
       bool first_tile = true;
       // gW[o, cols of block] += g^T[o, 128 rows] * S[128 rows, cols]; A = the resident grad_out
@@ -423,13 +427,16 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
       auto wgrad_mmas = [&](int cb, bool first) {
         mbar_wait_relaxed(&sfull[sb], sphase, 32);
         tc_fence_after();
-        const uint32_t g_hi = smem_u32(gtile), g_lo = g_hi + P.g_img;
+        // 64-o atoms of the MN-major A operand: this buffer's image, then its second image or — O <= 64 —
+        // the shared zero image
+        const uint32_t g_hi = smem_u32(gtile) + (uint32_t)gb * g_buf, g_lo = g_hi + P.g_img;
+        const uint32_t g_lbo = P.OB >= 2 ? NIMG * P.g_img : g_zero_off - (uint32_t)gb * g_buf;
         const uint32_t sbase = smem_u32(sbuf + (size_t)sb * s_buf);
         const uint32_t d_tmem = d2_base + (uint32_t)((cb - cb0) * ncols);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // 8 steps of 16 tile rows
-          const uint64_t dgh = make_sdesc_sw128(g_hi + ks * 2048, NIMG * P.g_img, 1024);
-          const uint64_t dgl = make_sdesc_sw128(g_lo + ks * 2048, NIMG * P.g_img, 1024);
+          const uint64_t dgh = make_sdesc_sw128(g_hi + ks * 2048, g_lbo, 1024);
+          const uint64_t dgl = make_sdesc_sw128(g_lo + ks * 2048, g_lbo, 1024);
           const uint64_t dsh = make_sdesc_sw128(sbase + ks * 2048, 1024, 1024);
           const uint64_t dsl = make_sdesc_sw128(sbase + s_img + ks * 2048, 1024, 1024);
           umma_bf16(d_tmem, dgh, dsh, idesc_w, (first && ks == 0) ? 0u : 1u);
@@ -443,8 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
         if (sb == 0) sphase ^= 1;
       };
       for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
-        mbar_wait_relaxed(gfull, gphase, 32);
-        gphase ^= 1;
+        mbar_wait_relaxed(&gfull[gb], gphase, 32);
         for (int cb = cb0; cb < cb1; ++cb) {
           mbar_wait_relaxed(&tempty[acc], acc_phase ^ 1, 32);
           tc_fence_after();
@@ -454,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
             tc_fence_after();
             // resident converted grad_out image and streamed Wm^T image; Torch: A = grad_out rows,
             // B = Wm^T columns; Jittor: A = Wm^T lanes, B = grad_out pixels
-            const uint32_t r_hi = smem_u32(gtile + (size_t)ob * NIMG * P.g_img);
+            const uint32_t r_hi = smem_u32(gtile) + (uint32_t)gb * g_buf + (uint32_t)ob * NIMG * P.g_img;
             const uint32_t r_lo = r_hi + P.g_img;
             const uint32_t w_hi = smem_u32(wstage + (size_t)s * P.w_stage);
             const uint32_t w_lo = w_hi + (P.w_stage >> 1);
@@ -485,7 +491,11 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
           if (FUSE && cb > cb0) wgrad_mmas(cb - 1, first_tile);
         }
         if (FUSE) wgrad_mmas(cb1 - 1, first_tile);
-        umma_commit(gempty);  // grad_out tile may be overwritten
+        umma_commit(&gempty[gb]);  // grad_out tile buffer may be overwritten
+        if (++gb == P.g_nbuf) {
+          gb = 0;
+          gphase ^= 1;
+        }
         first_tile = false;
       }
       if (FUSE) umma_commit(dfull);
@@ -512,15 +522,16 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
     // A operand of GEMM-1: g[row m, o] = gout[b, o, r0 + (chunk*Gt + i_lo)*R], K-major, per 64 o's
     const int ct = tid - kFirstConvWarp * 32;  // 0..63
     uint32_t gphase = 0;
+    int gb = 0;
     if (FUSE) {
       // images beyond OB (the o >= 64*OB half of the M = 128 weight-gradient MMA) stay zero
-      for (uint32_t i = (uint32_t)P.OB * NIMG * P.g_img + ct * 16; i < (uint32_t)P.g_imgs * NIMG * P.g_img;
-           i += kConvWarps * 32 * 16)
+      const uint32_t zero_end = g_zero_off + (uint32_t)(P.g_imgs - P.OB) * NIMG * P.g_img;
+      for (uint32_t i = g_zero_off + ct * 16; i < zero_end; i += kConvWarps * 32 * 16)
         *reinterpret_cast<uint4*>(gtile + i) = make_uint4(0, 0, 0, 0);
     }
     for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
-      mbar_wait_relaxed(gempty, gphase ^ 1, 64);
-      gphase ^= 1;
+      mbar_wait_relaxed(&gempty[gb], gphase ^ 1, 64);
+      uint8_t* gdst = gtile + (size_t)gb * g_buf;
       const int groups = P.OB * 8;  // groups of 8 output channels
       const int rows = VARIANT == DCN_VARIANT_TORCH ? 128 : ncols;  // rows of the resident operand
       for (int item = ct; item < rows * groups; item += kConvWarps * 32) {
@@ -549,14 +560,18 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
         split_pair(v[2], v[3], hi.y, lo.y);
         split_pair(v[4], v[5], hi.z, lo.z);
         split_pair(v[6], v[7], hi.w, lo.w);
-        uint8_t* img = gtile + (size_t)(og >> 3) * NIMG * P.g_img;
+        uint8_t* img = gdst + (size_t)(og >> 3) * NIMG * P.g_img;
         const uint32_t so = kmajor_sw128_off(mm, (og & 7) * 8);
         *reinterpret_cast<uint4*>(img + so) = hi;
         if (!BF) *reinterpret_cast<uint4*>(img + P.g_img + so) = lo;
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(gfull);
+      if (lane == 0) mbar_arrive(&gfull[gb]);
+      if (++gb == P.g_nbuf) {
+        gb = 0;
+        gphase ^= 1;
+      }
     }
   } else {
     // ================================================================ plan warps
@@ -630,6 +645,7 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
   const size_t nimg = operand == DCN_OPERAND_BF16 ? 1 : 2;
   if (!make_tiling(g, &P->t)) return false;
   P->fuse_w = 0;
+  P->g_nbuf = 1;
   P->gw = nullptr;
   P->nslices = P->nchunks = 1;
   P->cb_per_slice = 0;
@@ -657,11 +673,12 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
     if (allow_fuse && g.O <= 128) {
       const int ncols = 64;
       const size_t plan = 2 * (size_t)P->Rt * ncols * sizeof(bd::ScatEntry);
-      const size_t smem = 2 * nimg * (size_t)bd::kGImg + 2 * (size_t)(nimg * ncols * 128) +
-                          2 * nimg * (size_t)(128 * 128) + plan + 256 + 1024;
-      if (P->Rt * ncols <= bd::kPlanMax && smem <= 227 * 1024) {
+      const size_t rest = 2 * (size_t)(nimg * ncols * 128) + 2 * nimg * (size_t)(128 * 128) + plan + 256 + 1024;
+      const size_t zero = (size_t)(2 - P->OB) * nimg * bd::kGImg, real = (size_t)P->OB * nimg * bd::kGImg;
+      if (P->Rt * ncols <= bd::kPlanMax && real + zero + rest <= 227 * 1024) {
         P->fuse_w = 1;
         P->g_imgs = 2;
+        P->g_nbuf = (2 * real + zero + rest <= 227 * 1024) ? 2 : 1;
         P->ncols = ncols;
         P->cblocks = (g.K + ncols - 1) / ncols;
         P->plan_cap = P->Rt * ncols;
@@ -679,8 +696,10 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
     // columns per accumulator block: 128 unless the plan ring / operand tiles would not fit
     for (int ncols : {128, 64}) {
       const size_t plan = 2 * (size_t)P->Rt * ncols * sizeof(bd::ScatEntry);
-      const size_t smem = (size_t)P->OB * nimg * bd::kGImg + 2 * (size_t)(nimg * ncols * 128) + plan + 256 + 1024;
-      if (P->Rt * ncols <= bd::kPlanMax && smem <= 227 * 1024) {
+      const size_t real = (size_t)P->OB * nimg * bd::kGImg;
+      const size_t rest = 2 * (size_t)(nimg * ncols * 128) + plan + 256 + 1024;
+      if (P->Rt * ncols <= bd::kPlanMax && real + rest <= 227 * 1024) {
+        P->g_nbuf = (2 * real + rest <= 227 * 1024) ? 2 : 1;
         P->ncols = ncols;
         P->cblocks = (g.K + ncols - 1) / ncols;
         P->plan_cap = P->Rt * ncols;
@@ -698,8 +717,10 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
   const int taps = g.C >= 128 ? 1 : 128 / g.C;
   for (int ncols : {128, 64}) {
     const size_t plan = 2 * (size_t)taps * ncols * sizeof(bd::ScatEntry);
-    const size_t smem = (size_t)P->OB * nimg * (ncols * 128) + 2 * (size_t)(nimg * 128 * 128) + plan + 256 + 1024;
-    if (taps * ncols <= bd::kPlanMax && smem <= 227 * 1024) {
+    const size_t real = (size_t)P->OB * nimg * (ncols * 128);
+    const size_t rest = 2 * (size_t)(nimg * 128 * 128) + plan + 256 + 1024;
+    if (taps * ncols <= bd::kPlanMax && real + rest <= 227 * 1024) {
+      P->g_nbuf = (2 * real + rest <= 227 * 1024) ? 2 : 1;
       P->ncols = ncols;
       P->pix_blocks = (g.HW + ncols - 1) / ncols;
       P->num_tiles = g.B * P->pix_blocks;
@@ -773,7 +794,9 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
   P.wtiles = wtiles;
   P.goff = goff;
   P.gw = gw;
-  const size_t smem = (size_t)P.g_imgs * nimg * P.g_img + 2 * (size_t)P.w_stage +
+  if (const char* e = getenv("DCN_BWD_GBUF"))
+    if (atoi(e) == 1) P.g_nbuf = 1;
+  const size_t smem = ((size_t)P.g_nbuf * P.OB + (P.g_imgs - P.OB)) * nimg * P.g_img + 2 * (size_t)P.w_stage +
                       (P.fuse_w ? 2 * nimg * (size_t)(128 * 128) : 0) +
                       2 * (size_t)P.plan_cap * sizeof(bd::ScatEntry) + 256 + 1024;
   int dev = 0, sms = 148;
