@@ -44,13 +44,16 @@ constexpr int kPlanPerThread = 8;
 constexpr int kPlanMax = kPlanThreads * kPlanPerThread;  // 1024 entries per column block
 constexpr uint32_t kGImg = 128 * 64 * 2;                 // one bf16 image of a grad_out K block
 
-// what the scatter warps need for one (class instance, column): 48 bytes
+// what the scatter warps need for one (class instance, column): 64 bytes
 struct __align__(16) ScatEntry {
-  uint32_t off[4];  // corner BYTE offsets inside image b of the channels-last copies (pad pixel if invalid)
-  float w[4];   // corner weights, 0 for invalid corners
+  uint32_t off[4];   // corner BYTE offsets (float image) for the value loads: the zero pad pixel if invalid
+  uint32_t roff[4];  // corner BYTE offsets for the scatter: an out-of-image corner is redirected to the
+                     // nearest in-image pixel, where it adds 0.0 (weight 0) — unconditional REDs, no
+                     // branches, and no hot spot on a single dummy address
+  float w[4];        // corner weights, 0 for invalid corners
   float fx, fy;
-  int gidx;     // index of grad_offset[b, n, p] (the "x" offset); "y" is N*HW further; -1 = none
-  int pad_;
+  int gidx;          // index of grad_offset[b, n, p] (the "x" offset); "y" is N*HW further; -1 = none
+  int live;          // 0 for padding columns / rows of no instance: nothing to scatter
 };
 
 struct Params {
@@ -81,16 +84,6 @@ struct Params {
   uint32_t w_stage;      // bytes of one Wm^T stage (hi | lo)
   uint32_t tmem_cols;
 };
-
-// red.global.add.f32 [addr], val  executed only where gate != 0 (one predicated instruction)
-__device__ __forceinline__ void red_add_if(char* addr, float val, float gate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.neu.f32 p, %2, 0f00000000;\n\t"
-      "@p red.global.add.f32 [%0], %1;\n\t}" ::"l"(addr),
-      "f"(val), "f"(gate)
-      : "memory");
-}
 
 struct RowInfo {
   int b, r0, chunk, valid;
@@ -154,14 +147,22 @@ __device__ __forceinline__ ScatEntry plan_finish(const Geo& g, const PlanWork& p
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     e.off[k] = pad;
+    e.roff[k] = 4u * (uint32_t)pw.chan_base;  // pixel 0 (adds 0.0)
     e.w[k] = 0.f;
   }
   e.fx = e.fy = 0.f;
   e.gidx = -1;
-  e.pad_ = 0;
+  e.live = 0;
   if (pw.valid) {
     const Tap tp = tap_of(g, pw.h, pw.w, pw.ox, pw.oy);
     const unsigned m = corner_mask(tp, g.H, g.W);
+    e.live = 1;
+    // scatter targets: valid corners at their pixel, invalid ones clamped into the image (add 0.0)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = min(max(tp.y0 + (k >> 1), 0), g.H - 1), xx = min(max(tp.x0 + (k & 1), 0), g.W - 1);
+      e.roff[k] = 4u * (uint32_t)((yy * g.W + xx) * g.C + pw.chan_base);
+    }
     if (m) {
       float cw[4];
       corner_weights(tp, cw);
@@ -315,6 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
             const float gs = __uint_as_float(raw[u]);
             const ScatEntry* e = pl + c0 + u;
             const uint4 off = *reinterpret_cast<const uint4*>(e->off);
+            const uint4 roff = *reinterpret_cast<const uint4*>(e->roff);
             const float4 w = *reinterpret_cast<const float4*>(e->w);
             const float2 f = *reinterpret_cast<const float2*>(&e->fx);
             // entry offsets are bytes of the float grad image; the bf16 x image is half as wide
@@ -323,13 +325,12 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
             const float v1 = (float)__ldg(reinterpret_cast<const XT*>(ximg + (off.y >> XS)));
             const float v2 = (float)__ldg(reinterpret_cast<const XT*>(ximg + (off.z >> XS)));
             const float v3 = (float)__ldg(reinterpret_cast<const XT*>(ximg + (off.w >> XS)));
-            if (gimg) {
-              // zero-weight corners are out of the image (or the whole column is padding):
-              // predicated red.global, no branches
-              red_add_if(gimg + off.x, gs * w.x, w.x);
-              red_add_if(gimg + off.y, gs * w.y, w.y);
-              red_add_if(gimg + off.z, gs * w.z, w.z);
-              red_add_if(gimg + off.w, gs * w.w, w.w);
+            if (gimg && e->live) {
+              // branch-free, coalesced red.global.add.f32 x4 (an out-of-image corner adds 0.0 in-image)
+              atomicAdd(reinterpret_cast<float*>(gimg + roff.x), gs * w.x);
+              atomicAdd(reinterpret_cast<float*>(gimg + roff.y), gs * w.y);
+              atomicAdd(reinterpret_cast<float*>(gimg + roff.z), gs * w.z);
+              atomicAdd(reinterpret_cast<float*>(gimg + roff.w), gs * w.w);
             }
             part_g[u] = gs * ((v1 - v0) * (1.f - f.y) + (v3 - v2) * f.y);
             part_g[8 + u] = gs * ((v2 - v0) * (1.f - f.x) + (v3 - v1) * f.x);
