@@ -63,7 +63,12 @@ enum {
   DCN_VARIANT_JITTOR = 0,
   /* train.py:95-140 — coordinates normalised by (W_in-1,H_in-1) (:111-112), columns are the
    * memory-reinterpreting reshape of the [B,C,Ho,Wo,N] sample tensor (:129-131). */
-  DCN_VARIANT_TORCH = 1
+  DCN_VARIANT_TORCH = 1,
+  /* Not in the reference: standard deformable convolution v1 as in
+   * torchvision.ops.deform_conv2d / mmcv (one offset group, no mask, dilation 1): sampling point
+   * (h*s - p + ki + dy, w*s - p + kj + dx), offsets interleaved (dy, dx) per tap, columns ordered
+   * (c, tap).  Same kernels, different coordinate generator; torchvision is its oracle. */
+  DCN_VARIANT_DCNV1 = 2
 };
 
 /* Storage / arithmetic mode of the dense contraction. */

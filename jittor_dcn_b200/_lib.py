@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(HERE, "libdcn_b200.so")
 
 VARIANT_JITTOR = 0   # deform_conv.py:56-81
 VARIANT_TORCH = 1    # train.py:95-140
+VARIANT_DCNV1 = 2    # standard DCNv1 (torchvision.ops.deform_conv2d semantics), SURVEY 8f.3
 OPERAND_FP32 = 0
 OPERAND_BF16 = 1
 FLAG_ACCUM_GRAD_X = 1 << 0

@@ -23,7 +23,28 @@ struct Geo {
   int variant;  // DCN_VARIANT_*
   float Dx, Dy; // normalisation divisors            (:37-38 / :111-112)
   float sx, sy; // (W-1)/2, (H-1)/2                  (GridSampler.h:27-36)
+  // DCNv1 coordinate mode needs the conv geometry itself
+  int kw, sh, sw, ph, pw;
+  // Offset channel that moves the ROW (iy) / COLUMN (ix) coordinate of tap n: n*mul + add.
+  //   reference: row <- channel n ("x" offset: the sample is transposed), column <- channel N + n
+  //   DCNv1    : row <- channel 2n (dy),                                   column <- channel 2n + 1 (dx)
+  int row_mul, row_add, col_mul, col_add;
 };
+
+__host__ __device__ __forceinline__ int off_row_ch(const Geo& g, int n) { return n * g.row_mul + g.row_add; }
+__host__ __device__ __forceinline__ int off_col_ch(const Geo& g, int n) { return n * g.col_mul + g.col_add; }
+
+// Flat index into weight[O, C, kh, kw] of GEMM column j of output o.  The tile kernels order the
+// columns of every non-Torch layout (tap, channel): j = n*C + c.
+//   Jittor layout (deform_conv.py:72-74): column n*C + c multiplies flat weight element j itself;
+//   DCNv1: column (c, n) of the (c, tap)-ordered weight, i.e. element c*N + n.
+__host__ __device__ __forceinline__ size_t wt_index(const Geo& g, int o, int j) {
+  if (g.variant == DCN_VARIANT_DCNV1) {
+    const int n = j / g.C, c = j - n * g.C;
+    return (size_t)o * g.K + (size_t)c * g.N + n;
+  }
+  return (size_t)o * g.K + j;
+}
 
 // One sampling point: north-west corner + fractions.  16 bytes, the "plan" entry.
 struct __align__(16) Tap {
@@ -37,7 +58,8 @@ __host__ inline int make_geo(const DcnShape* s, Geo* g) {
       s->sh <= 0 || s->sw <= 0 || s->ph < 0 || s->pw < 0)
     return DCN_ERR_BAD_SHAPE;
   if (s->H + 2 * s->ph < s->kh || s->W + 2 * s->pw < s->kw) return DCN_ERR_BAD_SHAPE;
-  if (s->variant != DCN_VARIANT_JITTOR && s->variant != DCN_VARIANT_TORCH) return DCN_ERR_BAD_SHAPE;
+  if (s->variant != DCN_VARIANT_JITTOR && s->variant != DCN_VARIANT_TORCH && s->variant != DCN_VARIANT_DCNV1)
+    return DCN_ERR_BAD_SHAPE;
   g->B = s->B; g->C = s->C; g->O = s->O; g->H = s->H; g->W = s->W;
   g->N = s->kh * s->kw;
   g->Ho = (s->H + 2 * s->ph - s->kh) / s->sh + 1;
@@ -61,6 +83,12 @@ __host__ inline int make_geo(const DcnShape* s, Geo* g) {
   }
   g->sx = (float)(s->W - 1) / 2.0f;
   g->sy = (float)(s->H - 1) / 2.0f;
+  g->kw = s->kw; g->sh = s->sh; g->sw = s->sw; g->ph = s->ph; g->pw = s->pw;
+  if (s->variant == DCN_VARIANT_DCNV1) {
+    g->row_mul = 2; g->row_add = 0; g->col_mul = 2; g->col_add = 1;
+  } else {
+    g->row_mul = 1; g->row_add = 0; g->col_mul = 1; g->col_add = g->N;
+  }
   return DCN_OK;
 }
 
@@ -74,7 +102,21 @@ __device__ __forceinline__ int sat_int(float v) {
 // The reference's float32 op chain, one IEEE rounding per op, no FMA contraction
 // (the _rn intrinsics are never fused by nvcc).  Bit-exact with the CPU reference:
 // torch CPU evaluates `tensor / python_int` as a true IEEE divide.
-__device__ __forceinline__ Tap tap_of(const Geo& g, int h, int w, float off_x, float off_y) {
+// off_x = the offset that ends up moving the ROW (channel off_row_ch(n)), off_y the COLUMN one.
+__device__ __forceinline__ Tap tap_of(const Geo& g, int h, int w, int n, float off_x, float off_y) {
+  if (g.variant == DCN_VARIANT_DCNV1) {
+    // torchvision deform_conv2d: y = (h*sh - ph + ki) + dy ; x = (w*sw - pw + kj) + dx, no round trip
+    const int ki = n / g.kw, kj = n - ki * g.kw;
+    const float iy = __fadd_rn((float)(h * g.sh - g.ph + ki), off_x);
+    const float ix = __fadd_rn((float)(w * g.sw - g.pw + kj), off_y);
+    const float xf = floorf(ix), yf = floorf(iy);
+    Tap t;
+    t.fx = __fsub_rn(ix, xf);
+    t.fy = __fsub_rn(iy, yf);
+    t.x0 = sat_int(xf);
+    t.y0 = sat_int(yf);
+    return t;
+  }
   float loc_x = __fadd_rn((float)w, off_x);
   float loc_y = __fadd_rn((float)h, off_y);
   float nx = __fsub_rn(__fmul_rn(__fdiv_rn(loc_x, g.Dx), 2.0f), 1.0f);

@@ -33,10 +33,10 @@ __global__ void __launch_bounds__(256) plan_kernel(Geo g, const float* __restric
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int n = i / g.HW, p = i - n * g.HW;
     const float* ob = off + (size_t)b * 2 * g.N * g.HW;
-    const float ox = __ldg(ob + (size_t)n * g.HW + p);
-    const float oy = __ldg(ob + (size_t)(g.N + n) * g.HW + p);
+    const float ox = __ldg(ob + (size_t)off_row_ch(g, n) * g.HW + p);
+    const float oy = __ldg(ob + (size_t)off_col_ch(g, n) * g.HW + p);
     const int h = p / g.Wo, w = p - h * g.Wo;
-    plan[plan_index<VARIANT>(g, b, n, p)] = tap_of(g, h, w, ox, oy);
+    plan[plan_index<VARIANT>(g, b, n, p)] = tap_of(g, h, w, n, ox, oy);
   }
 }
 
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) corners_kernel(Geo g, const float* __rest
     const int n = i / g.HW, p = i - n * g.HW;
     const float* ob = off + (size_t)b * 2 * g.N * g.HW;
     const int h = p / g.Wo, w = p - h * g.Wo;
-    Tap t = tap_of(g, h, w, ob[(size_t)n * g.HW + p], ob[(size_t)(g.N + n) * g.HW + p]);
+    Tap t = tap_of(g, h, w, n, ob[(size_t)off_row_ch(g, n) * g.HW + p], ob[(size_t)off_col_ch(g, n) * g.HW + p]);
     float cw[4];
     corner_weights(t, cw);
     const size_t o = (size_t)b * total + i;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) fwd_kernel(Geo g, const float* __restrict
     for (int i = 0; i < 4; ++i) {
       const int kk = tid & 15, oo = (tid >> 4) + 16 * i;
       float v = 0.f;
-      if (o0 + oo < g.O && k0 + kk < g.K) v = __ldg(wt + (size_t)(o0 + oo) * g.K + k0 + kk);
+      if (o0 + oo < g.O && k0 + kk < g.K) v = __ldg(wt + wt_index(g, o0 + oo, k0 + kk));
       Bs[kk][oo] = v;
     }
     __syncthreads();
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) bwd_data_kernel(Geo g, int want_gx,
     for (int i = 0; i < 4; ++i) {
       const int jj = tid & 63, oo = (tid >> 6) + 4 * i;
       float v = 0.f;
-      if (j0 + jj < g.K && o0 + oo < g.O) v = __ldg(wt + (size_t)(o0 + oo) * g.K + j0 + jj);
+      if (j0 + jj < g.K && o0 + oo < g.O) v = __ldg(wt + wt_index(g, o0 + oo, j0 + jj));
       Ws[oo][jj] = v;
     }
     __syncthreads();
@@ -264,8 +264,8 @@ __global__ void __launch_bounds__(256) bwd_data_kernel(Geo g, int want_gx,
   auto flush = [&]() {
     if (q_prev >= 0 && (six != 0.f || siy != 0.f)) {
       const int p = q_prev / g.N, n = q_prev - p * g.N;
-      atomicAdd(goffb + (size_t)n * g.HW + p, siy);
-      atomicAdd(goffb + (size_t)(g.N + n) * g.HW + p, six);
+      atomicAdd(goffb + (size_t)off_row_ch(g, n) * g.HW + p, siy);
+      atomicAdd(goffb + (size_t)off_col_ch(g, n) * g.HW + p, six);
     }
     six = siy = 0.f;
   };
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(256) bwd_weight_kernel(Geo g, int chunks_per_s
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
       const int j = j0 + tx * 4 + jj;
-      if (j < g.K) atomicAdd(gw + (size_t)o * g.K + j, acc[i][jj]);
+      if (j < g.K) atomicAdd(gw + wt_index(g, o, j), acc[i][jj]);
     }
   }
 }
@@ -446,6 +446,7 @@ int launch_bias_grad(const Geo& g, const void* gout, int operand, float* gb, cud
 }
 
 int launch_offset_scale(const Geo& g, float* goff, cudaStream_t st) {
+  if (g.variant == DCN_VARIANT_DCNV1) return DCN_OK;  // coordinates are pixels already: factor 1
   const size_t total = (size_t)g.B * 2 * g.N * g.HW;
   KernelScope scope("offset_scale_kernel", st);
   offset_scale_kernel<<<(unsigned)min((total + 255) / 256, (size_t)8192), 256, 0, st>>>(g, goff);
@@ -473,9 +474,8 @@ int simt_backward(const Geo& g, int flags, const float* x, const Tap* plan, cons
         bwd_data_kernel<DCN_VARIANT_JITTOR><<<grid, 256, 0, st>>>(g, want_gx, x, plan, wt, gout, gx, goff);
     }
     DCN_KERNEL_CHECK("bwd_data_kernel");
-    const size_t total = (size_t)g.B * 2 * g.N * g.HW;
-    offset_scale_kernel<<<(unsigned)min((total + 255) / 256, (size_t)8192), 256, 0, st>>>(g, goff);
-    DCN_KERNEL_CHECK("offset_scale_kernel");
+    int rc = launch_offset_scale(g, goff, st);
+    if (rc) return rc;
   }
   if (parts & SIMT_BWD_WEIGHT) {
     const int tiles = ((g.O + TM - 1) / TM) * ((g.K + TN - 1) / TN);

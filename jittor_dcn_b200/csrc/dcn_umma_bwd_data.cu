@@ -52,7 +52,8 @@ struct __align__(16) ScatEntry {
                      // branches, and no hot spot on a single dummy address
   float w[4];        // corner weights, 0 for invalid corners
   float fx, fy;
-  int gidx;          // index of grad_offset[b, n, p] (the "x" offset); "y" is N*HW further; -1 = none
+  int gidx;          // index of the grad_offset element that receives g_iy (the channel moving the row);
+                     // g_ix goes ix_delta further (Params); -1 = none
   int live;          // 0 for padding columns / rows of no instance: nothing to scatter
 };
 
@@ -68,6 +69,7 @@ struct Params {
   int Gt, Rt, chunks, num_inst, num_tiles;  // backward tiling (rows = (instance, channel))
   FastDiv divR, divChunks;
   int pix_blocks;        // Jittor: ceil(HW / ncols) pixel blocks per image
+  int ix_delta;          // distance, in floats, from a tap's g_iy slot in grad_offset to its g_ix slot
   int ncols;             // TMEM columns per accumulator block: 128 or 64 (Torch: j's; Jittor: pixels)
   int cblocks;           // blocks per tile: Torch ceil(K / ncols) column blocks, Jittor ceil(K / 128) lane blocks
   int OB;                // ceil(O / 64) K blocks of the GEMM
@@ -102,7 +104,7 @@ __device__ __forceinline__ RowInfo decode(const Params& P, int inst) {
 
 struct PlanWork {
   float ox, oy;
-  int h, w, chan_base, gidx, valid;
+  int h, w, n, chan_base, gidx, valid;
 };
 
 template <int VARIANT>
@@ -110,7 +112,7 @@ __device__ __forceinline__ void plan_prepare(const Params& P, int tile, int cb, 
   const Geo& g = P.g;
   pw.valid = 0;
   pw.ox = pw.oy = 0.f;
-  pw.h = pw.w = pw.chan_base = 0;
+  pw.h = pw.w = pw.n = pw.chan_base = 0;
   pw.gidx = -1;
   uint32_t p, n, h, w;
   int b;
@@ -134,10 +136,11 @@ __device__ __forceinline__ void plan_prepare(const Params& P, int tile, int cb, 
   P.t.divWo.divmod(p, h, w);
   pw.h = (int)h;
   pw.w = (int)w;
-  pw.gidx = (b * 2 * g.N + (int)n) * g.HW + (int)p;
+  pw.n = (int)n;
+  pw.gidx = (b * 2 * g.N + off_row_ch(g, (int)n)) * g.HW + (int)p;  // target of g_iy
   const float* ob = P.off + (size_t)b * 2 * g.N * g.HW;
-  pw.ox = __ldg(ob + (size_t)n * g.HW + p);
-  pw.oy = __ldg(ob + (size_t)(g.N + n) * g.HW + p);
+  pw.ox = __ldg(ob + (size_t)off_row_ch(g, (int)n) * g.HW + p);
+  pw.oy = __ldg(ob + (size_t)off_col_ch(g, (int)n) * g.HW + p);
   pw.valid = 1;
 }
 
@@ -154,7 +157,7 @@ __device__ __forceinline__ ScatEntry plan_finish(const Geo& g, const PlanWork& p
   e.gidx = -1;
   e.live = 0;
   if (pw.valid) {
-    const Tap tp = tap_of(g, pw.h, pw.w, pw.ox, pw.oy);
+    const Tap tp = tap_of(g, pw.h, pw.w, pw.n, pw.ox, pw.oy);
     const unsigned m = corner_mask(tp, g.H, g.W);
     e.live = 1;
     // scatter targets: valid corners at their pixel, invalid ones clamped into the image (add 0.0)
@@ -367,9 +370,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
           if (gl < 16 && (RW == 16 || lane < 16)) {
             const int vi = gl & 15, col = vi & 7;
             const int gidx = pl[c0 + col].gidx;
-            // value 0..7: g_ix -> "y" offset channel (N + n); 8..15: g_iy -> "x" offset channel n
+            // value 0..7: g_ix -> the column-moving offset channel; 8..15: g_iy -> the row-moving one
             if (gidx >= 0 && part_g[0] != 0.f)
-              atomicAdd(P.goff + (size_t)gidx + (vi < 8 ? (size_t)g.N * g.HW : 0), part_g[0]);
+              atomicAdd(P.goff + (size_t)gidx + (vi < 8 ? (size_t)P.ix_delta : 0), part_g[0]);
           }
         }
         tc_fence_before();
@@ -630,7 +633,7 @@ __global__ void __launch_bounds__(256) weight_tiles_bwd_kernel(Geo g, int ncols,
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int o = i % (OB * 64), jj = i / (OB * 64);  // lanes along o: Wm[o, j] strided reads, small
     const int cb = jj / ncols, jl = jj - cb * ncols, ob = o >> 6, ol = o & 63;
-    const float v = (o < g.O && jj < g.K) ? (float)wt[(size_t)o * g.K + jj] : 0.f;
+    const float v = (o < g.O && jj < g.K) ? (float)wt[wt_index(g, o, jj)] : 0.f;
     __nv_bfloat16 hi, lo;
     ptx::split_bf16(v, hi, lo);
     uint8_t* base = tiles + (size_t)(cb * OB + ob) * NIMG * img + ptx::kmajor_sw128_off(jl, ol);
@@ -795,6 +798,7 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
   P.wtiles = wtiles;
   P.goff = goff;
   P.gw = gw;
+  P.ix_delta = (off_col_ch(g, 0) - off_row_ch(g, 0)) * g.HW;
   if (const char* e = getenv("DCN_BWD_GBUF"))
     if (atoi(e) == 1) P.g_nbuf = 1;
   const size_t smem = ((size_t)P.g_nbuf * P.OB + (P.g_imgs - P.OB)) * nimg * P.g_img + 2 * (size_t)P.w_stage +

@@ -70,7 +70,7 @@ struct FwdParams {
 // flight (issued one K block ahead so that their latency hides behind the gather phase).
 struct PlanWork {
   float ox, oy;
-  int h, w, chan_base, valid;
+  int h, w, n, chan_base, valid;
 };
 
 template <int VARIANT>
@@ -78,7 +78,7 @@ __device__ __forceinline__ void plan_prepare(const Geo& g, const Tiling& t, cons
                                              int tile, int kb, int e, PlanWork& pw) {
   pw.valid = 0;
   pw.ox = pw.oy = 0.f;
-  pw.h = pw.w = pw.chan_base = 0;
+  pw.h = pw.w = pw.n = pw.chan_base = 0;
   int b, p, n;
   if (VARIANT == DCN_VARIANT_TORCH) {
     const int il = e >> 6, kk = e & 63, j = kb * 64 + kk;
@@ -102,9 +102,10 @@ __device__ __forceinline__ void plan_prepare(const Geo& g, const Tiling& t, cons
   t.divWo.divmod((uint32_t)p, h, w);
   pw.h = (int)h;
   pw.w = (int)w;
+  pw.n = n;
   const float* ob = off + (size_t)b * 2 * g.N * g.HW;
-  pw.ox = __ldg(ob + (size_t)n * g.HW + p);
-  pw.oy = __ldg(ob + (size_t)(g.N + n) * g.HW + p);
+  pw.ox = __ldg(ob + (size_t)off_row_ch(g, n) * g.HW + p);
+  pw.oy = __ldg(ob + (size_t)off_col_ch(g, n) * g.HW + p);
   pw.valid = 1;
 }
 
@@ -118,7 +119,7 @@ __device__ __forceinline__ PlanEntry plan_finish(const Geo& g, const PlanWork& p
     e.w[k] = 0.f;
   }
   if (pw.valid) {
-    const Tap tp = tap_of(g, pw.h, pw.w, pw.ox, pw.oy);
+    const Tap tp = tap_of(g, pw.h, pw.w, pw.n, pw.ox, pw.oy);
     const unsigned m = corner_mask(tp, g.H, g.W);
     if (m) {
       float cw[4];
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int j = kb0 * 64 + c0 + i;
-            if (j < g.K) atomicAdd(P.gw + (size_t)o * g.K + j, v[i]);
+            if (j < g.K) atomicAdd(P.gw + wt_index(g, o, j), v[i]);
           }
         }
       }
@@ -696,7 +697,7 @@ static int num_sms() {
 static bool tiling_ok(const Geo& g, Tiling* t) {
   if (!make_tiling(g, t)) return false;
   if (g.variant == DCN_VARIANT_TORCH && t->Rt * 64 > kPlanMax) return false;
-  if (g.variant == DCN_VARIANT_JITTOR && 128 * t->taps_per_kb > kPlanMax) return false;
+  if (g.variant != DCN_VARIANT_TORCH && 128 * t->taps_per_kb > kPlanMax) return false;
   static_assert(kPlanMax == kPlanPerThread * kPlanThreads, "plan slots");
   return true;
 }

@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 from ._lib import (FLAG_ACCUM_GRAD_X, FLAG_FORCE_SIMT, FLAG_NO_GRAD_X, OPERAND_BF16, OPERAND_FP32,
-                   PHASE_BACKWARD, PHASE_FORWARD, VARIANT_JITTOR, VARIANT_TORCH)
+                   PHASE_BACKWARD, PHASE_FORWARD, VARIANT_DCNV1, VARIANT_JITTOR, VARIANT_TORCH)
 
 _workspaces = {}
 
@@ -184,3 +184,12 @@ def deform_conv2d(x, offset, weight, bias=None, kernel_size=3, stride=1, padding
     """Differentiable DeformConv2d core: everything after the offset conv."""
     cfg = (_lib._pair(kernel_size), _lib._pair(stride), _lib._pair(padding), variant, operand, flags)
     return DeformConvFunction.apply(x, offset, weight, bias, cfg)
+
+
+def deform_conv2d_v1(input, offset, weight, bias=None, stride=1, padding=0):
+    """Standard deformable convolution v1 with the call signature (and semantics) of
+    ``torchvision.ops.deform_conv2d(input, offset, weight, bias, stride, padding)`` for one offset
+    group, no mask, dilation 1 — the same kernels as the reference's operators with the textbook
+    coordinate generator.  Differentiable in input, offset, weight and bias."""
+    kernel_size = (int(weight.shape[2]), int(weight.shape[3]))
+    return deform_conv2d(input, offset, weight, bias, kernel_size, stride, padding, variant=VARIANT_DCNV1)

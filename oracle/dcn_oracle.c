@@ -31,6 +31,11 @@
  *                        documented formula (same as torch's).  Checked only against a
  *                        torch transliteration of deform_conv.py:30-81.
  *
+ *   DCN_VARIANT_DCNV1  — (not a reference operator) torchvision.ops.deform_conv2d
+ *                        semantics restated from its published CPU kernel (deform_conv2d_kernel.cpp:
+ *                        bilinear_interpolate, deformable_im2col, one offset group, no mask).
+ *                        PINNED to tests/golden/dcnv1_*.npz produced by torchvision 0.26 itself.
+ *
  * Build: see oracle/Makefile  (gcc -O2 -ffp-contract=off: no FMA contraction, so every
  * float op below rounds exactly once, like the reference's op-by-op tensor chain).
  */
@@ -50,7 +55,12 @@ typedef struct Geo {
   float Dx, Dy;                       /* normalisation divisors */
   float sx, sy;                       /* (W-1)/2, (H-1)/2 */
   int variant;
+  int kw, sh, sw, ph, pw;
 } Geo;
+
+/* offset channel that moves the ROW / COLUMN coordinate of tap n (see dcn_b200.h variants) */
+static inline int off_row_ch(const Geo* g, int n) { return g->variant == DCN_VARIANT_DCNV1 ? 2 * n : n; }
+static inline int off_col_ch(const Geo* g, int n) { return g->variant == DCN_VARIANT_DCNV1 ? 2 * n + 1 : g->N + n; }
 
 static int make_geo(const DcnShape* s, Geo* g) {
   if (!s || s->B <= 0 || s->C <= 0 || s->O <= 0 || s->H <= 0 || s->W <= 0 || s->kh <= 0 ||
@@ -73,6 +83,7 @@ static int make_geo(const DcnShape* s, Geo* g) {
   }
   g->sx = (float)(s->W - 1) / 2.0f;
   g->sy = (float)(s->H - 1) / 2.0f;
+  g->kw = s->kw; g->sh = s->sh; g->sw = s->sw; g->ph = s->ph; g->pw = s->pw;
   return 0;
 }
 
@@ -89,8 +100,28 @@ typedef struct Corner {
   float w[4];   /* nw, ne, sw, se */
 } Corner;
 
-/* One sampling point.  off_x / off_y are offset channels n and N+n at (h,w). */
-static inline void corner_of(const Geo* g, int h, int w, float off_x, float off_y, Corner* c) {
+/* One sampling point.  off_x / off_y are the offsets of channels off_row_ch(n) / off_col_ch(n) at
+ * (h,w): the reference's "x" offset (channel n) ends up moving the ROW because its grid is
+ * [norm_y, norm_x]; DCNv1's dy (channel 2n) moves the row directly. */
+static inline void corner_of(const Geo* g, int h, int w, int n, float off_x, float off_y, Corner* c) {
+  if (g->variant == DCN_VARIANT_DCNV1) {
+    /* torchvision deform_conv2d_kernel.cpp deformable_im2col:
+     *   y = (out_y*stride_h - pad_h) + i*dil_h + offset_h ; x likewise; bilinear_interpolate */
+    const int ki = n / g->kw, kj = n % g->kw;
+    volatile float iy = (float)(h * g->sh - g->ph + ki) + off_x;
+    volatile float ix = (float)(w * g->sw - g->pw + kj) + off_y;
+    float xf = floorf(ix), yf = floorf(iy);
+    c->fx = ix - xf;
+    c->fy = iy - yf;
+    c->x0 = sat_int(xf);
+    c->y0 = sat_int(yf);
+    volatile float e = 1.0f - c->fx, s = 1.0f - c->fy;
+    c->w[0] = s * e;
+    c->w[1] = s * c->fx;
+    c->w[2] = c->fy * e;
+    c->w[3] = c->fy * c->fx;
+    return;
+  }
   /* sampling_locs = grid + offset            deform_conv.py:68  train.py:109 */
   volatile float loc_x = (float)w + off_x;
   volatile float loc_y = (float)h + off_y;
@@ -152,6 +183,10 @@ static inline void col_map(const Geo* g, int r, int j, int* c, int* p, int* n) {
     int q = (int)(f % g->P);
     *p = q / g->N;
     *n = q % g->N;
+  } else if (g->variant == DCN_VARIANT_DCNV1) {
+    *c = j / g->N; /* torchvision columns: (c, tap) */
+    *n = j % g->N;
+    *p = r;
   } else {
     *n = j / g->C;
     *c = j % g->C;
@@ -171,8 +206,8 @@ int dcn_oracle_corners(const DcnShape* s, const float* off, int32_t* y0, int32_t
       for (int p = 0; p < HW; ++p) {
         Corner c;
         const float* ob = off + (size_t)b * 2 * g.N * HW;
-        corner_of(&g, p / g.Wo, p % g.Wo, ob[(size_t)n * HW + p], ob[(size_t)(g.N + n) * HW + p],
-                  &c);
+        corner_of(&g, p / g.Wo, p % g.Wo, n, ob[(size_t)off_row_ch(&g, n) * HW + p],
+                  ob[(size_t)off_col_ch(&g, n) * HW + p], &c);
         size_t i = ((size_t)b * g.N + n) * HW + p;
         y0[i] = c.y0;
         x0[i] = c.x0;
@@ -196,8 +231,8 @@ int dcn_oracle_sample(const DcnShape* s, const float* x, const float* off, float
     for (int p = 0; p < HW; ++p)
       for (int n = 0; n < g.N; ++n) {
         Corner c;
-        corner_of(&g, p / g.Wo, p % g.Wo, ob[(size_t)n * HW + p], ob[(size_t)(g.N + n) * HW + p],
-                  &c);
+        corner_of(&g, p / g.Wo, p % g.Wo, n, ob[(size_t)off_row_ch(&g, n) * HW + p],
+                  ob[(size_t)off_col_ch(&g, n) * HW + p], &c);
         for (int ch = 0; ch < g.C; ++ch) {
           const float* xp = x + ((size_t)b * g.C + ch) * g.H * g.W;
           S[(((size_t)b * g.C + ch) * HW + p) * g.N + n] = sample_plane(xp, g.H, g.W, &c);
@@ -212,6 +247,11 @@ static void build_columns(const Geo* g, const float* S_b /* [C,HW,N] */, float* 
   const int HW = g->Ho * g->Wo;
   if (g->variant == DCN_VARIANT_TORCH) {
     memcpy(A, S_b, sizeof(float) * (size_t)HW * g->K); /* raw reshape */
+  } else if (g->variant == DCN_VARIANT_DCNV1) {
+    for (int p = 0; p < HW; ++p)
+      for (int c = 0; c < g->C; ++c)
+        for (int n = 0; n < g->N; ++n)
+          A[(size_t)p * g->K + c * g->N + n] = S_b[((size_t)c * HW + p) * g->N + n];
   } else {
     for (int p = 0; p < HW; ++p)
       for (int n = 0; n < g->N; ++n)
@@ -266,8 +306,9 @@ int dcn_oracle_backward(const DcnShape* s, const float* x, const float* off, con
   if ((gx && !gxd) || !gwd || !gbd || !S) return -2;
   dcn_oracle_sample(s, x, off, S);
   /* d(ix)/d(off_y) = 2/Dy * sx ; d(iy)/d(off_x) = 2/Dx * sy   (chain through :37-39) */
-  const double mul_offx = 2.0 / (double)g.Dx * (double)g.sy; /* "x" offset moves the ROW */
-  const double mul_offy = 2.0 / (double)g.Dy * (double)g.sx;
+  const int v1 = g.variant == DCN_VARIANT_DCNV1; /* pixel coordinates: no chain-rule factor */
+  const double mul_offx = v1 ? 1.0 : 2.0 / (double)g.Dx * (double)g.sy; /* row-moving offset */
+  const double mul_offy = v1 ? 1.0 : 2.0 / (double)g.Dy * (double)g.sx; /* column-moving offset */
 
   float* A = (float*)malloc(sizeof(float) * (size_t)HW * K);
   double* gA = (double*)malloc(sizeof(double) * (size_t)HW * K);
@@ -301,8 +342,8 @@ int dcn_oracle_backward(const DcnShape* s, const float* x, const float* off, con
         int c, p, n;
         col_map(&g, r, j, &c, &p, &n);
         Corner cr;
-        corner_of(&g, p / g.Wo, p % g.Wo, ob[(size_t)n * HW + p], ob[(size_t)(N + n) * HW + p],
-                  &cr);
+        corner_of(&g, p / g.Wo, p % g.Wo, n, ob[(size_t)off_row_ch(&g, n) * HW + p],
+                  ob[(size_t)off_col_ch(&g, n) * HW + p], &cr);
         const double gs = gA[(size_t)r * K + j];
         const float* xp = x + ((size_t)b * C + c) * H * W;
         double* gxp = gxd ? gxd + ((size_t)b * C + c) * H * W : NULL;
@@ -324,8 +365,8 @@ int dcn_oracle_backward(const DcnShape* s, const float* x, const float* off, con
         for (int p = 0; p < HW; ++p) {
           double a = giy[(size_t)n * HW + p], c2 = gix[(size_t)n * HW + p];
           /* a non-finite coordinate samples nothing and has zero gradient */
-          gob2[(size_t)n * HW + p] = (float)(a * mul_offx);
-          gob2[(size_t)(N + n) * HW + p] = (float)(c2 * mul_offy);
+          gob2[(size_t)off_row_ch(&g, n) * HW + p] = (float)(a * mul_offx);
+          gob2[(size_t)off_col_ch(&g, n) * HW + p] = (float)(c2 * mul_offy);
         }
     }
   }

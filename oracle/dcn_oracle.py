@@ -14,6 +14,7 @@ _SO = os.path.join(_HERE, "_build", "libdcn_oracle.so")
 
 VARIANT_JITTOR = 0  # deform_conv.py:56-81
 VARIANT_TORCH = 1   # train.py:95-140
+VARIANT_DCNV1 = 2   # torchvision.ops.deform_conv2d semantics
 
 
 class DcnShape(ctypes.Structure):

@@ -16,6 +16,8 @@ Fixture kinds
                 for S in {128,64,56,32,28,14}, again through one-hot
                channels, bit-exact.
   layer_*    : forward + the four autograd gradients on small random problems.
+  dcnv1_*    : DCN_VARIANT_DCNV1 (standard DCNv1, not a reference operator): outputs of
+               torchvision.ops.deform_conv2d itself, incl. bit-exact stencil probes.
   jittor_*   : same problems through the torch transliteration of deform_conv.py
                (oracle/torch_chain.py, variant="jittor") — NOT a run of the reference
                (jittor is not installable here); pins the C oracle's Jittor variant to the
@@ -185,6 +187,54 @@ def make_detector_golden():
     _save("detector_eval", x=x.numpy(), cls=cls_logits.numpy(), bbox=bbox.numpy(), **arrays)
 
 
+DCNV1 = {
+    #  name             B  C   O   H   W   k       s  p       sigma
+    "dcnv1_a_s1":      (2, 4,  6,  9,  11, 3,      1, 1,      1.5),
+    "dcnv1_b_s2":      (2, 16, 32, 16, 16, 3,      2, 1,      2.0),   # tiles onto the tensor path
+    "dcnv1_c_far":     (1, 3,  4,  8,  8,  3,      1, 1,      6.0),
+    "dcnv1_d_k1x3":    (1, 4,  5,  7,  10, (1, 3), 1, (0, 1), 1.0),
+    "dcnv1_e_64":      (1, 64, 64, 12, 12, 3,      1, 1,      1.0),   # tensor path, one tap per K block
+}
+
+
+def make_dcnv1(rng):
+    """Standard DCNv1 (DCN_VARIANT_DCNV1): outputs of torchvision.ops.deform_conv2d itself (CPU)."""
+    from torchvision.ops import deform_conv2d
+    for name, (B, C, O, H, W, k, s, p, sigma) in DCNV1.items():
+        kh, kw = torch_chain._pair(k)
+        sh, sw = torch_chain._pair(s)
+        ph, pw = torch_chain._pair(p)
+        N = kh * kw
+        Ho, Wo = torch_chain.out_hw(H, W, k, s, p)
+        x = torch.as_tensor(rng.standard_normal((B, C, H, W)).astype(np.float32)).requires_grad_(True)
+        off = torch.as_tensor((rng.standard_normal((B, 2 * N, Ho, Wo)) * sigma).astype(np.float32)).requires_grad_(True)
+        wt = torch.as_tensor((rng.standard_normal((O, C, kh, kw)) * np.sqrt(2.0 / (C * N))).astype(np.float32)).requires_grad_(True)
+        bias = torch.as_tensor(rng.standard_normal((O,)).astype(np.float32)).requires_grad_(True)
+        gout = torch.as_tensor(rng.standard_normal((B, O, Ho, Wo)).astype(np.float32))
+        out = deform_conv2d(x, off, wt, bias, stride=(sh, sw), padding=(ph, pw))
+        gx, goff, gw, gb = torch.autograd.grad(out, [x, off, wt, bias], gout)
+        _save(name, cfg=_cfg(B=B, C=C, O=O, H=H, W=W, kh=kh, kw=kw, sh=sh, sw=sw, ph=ph, pw=pw),
+              x=x.detach().numpy(), off=off.detach().numpy(), weight=wt.detach().numpy(), bias=bias.detach().numpy(),
+              gout=gout.numpy(), out=out.detach().numpy(), gx=gx.numpy(), goff=goff.numpy(), gw=gw.numpy(),
+              gb=gb.numpy())
+    # sampling geometry, bit-exact: one-hot channels and identity weights, so out IS the column matrix
+    for name, (H, W, k, s, p, sigma) in {"dcnv1_stencil_s1": (6, 7, 3, 1, 1, 1.5),
+                                         "dcnv1_stencil_s2": (9, 8, 3, 2, 1, 2.5)}.items():
+        N, C, B = 9, H * W, 2
+        Ho, Wo = torch_chain.out_hw(H, W, k, s, p)
+        x = torch.zeros(B, C, H, W)
+        for c in range(C):
+            x[:, c, c // W, c % W] = 1.0
+        off = torch.as_tensor((rng.standard_normal((B, 2 * N, Ho, Wo)) * sigma).astype(np.float32))
+        off[0, :, 0, :] = 0.0
+        off[1, :, -1, :] = torch.round(off[1, :, -1, :])
+        wt = torch.eye(C * N).reshape(C * N, C, 3, 3)        # out[b, c*N + n, p] = column (c, n) of pixel p
+        out = deform_conv2d(x, off, wt, None, stride=s, padding=p)
+        S = out.reshape(B, C, N, Ho, Wo).permute(0, 1, 3, 4, 2).contiguous()   # [B, C, Ho, Wo, N]
+        _save(name, cfg=_cfg(B=B, C=C, O=C * N, H=H, W=W, kh=3, kw=3, sh=s, sw=s, ph=p, pw=p),
+              off=off.numpy(), S=S.numpy())
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference (build container only)"
     os.makedirs(OUT, exist_ok=True)
@@ -195,6 +245,7 @@ def main():
     make_module_golden()
     make_detector_golden()
     make_wobble()
+    make_dcnv1(np.random.default_rng(4242))
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as fh:
         fh.write("made by: python -m oracle.make_golden\n"
                  f"torch {torch.__version__}, numpy {np.__version__}\n"
@@ -203,7 +254,8 @@ def main():
                  "stencil_*, wobble_*, layer_*, module_*, detector_*: outputs of the unmodified "
                  "reference\n"
                  "jittor_*: torch transliteration of deform_conv.py:30-81 "
-                 "(oracle/torch_chain.py) - parity unpinned\n")
+                 "(oracle/torch_chain.py) - parity unpinned\n"
+                 "dcnv1_*: outputs of torchvision.ops.deform_conv2d (CPU) for DCN_VARIANT_DCNV1\n")
 
 
 if __name__ == "__main__":

@@ -299,3 +299,48 @@ def test_bf16_module_autograd():
     m32.load_state_dict(m.state_dict())
     out32 = m32(x.detach())
     assert rel_err(out.detach().cpu().numpy(), out32.detach().cpu().numpy()) < 2e-2
+
+
+# ---- DCN_VARIANT_DCNV1 (standard DCNv1; oracle = torchvision.ops.deform_conv2d goldens) ---------
+@pytest.mark.parametrize("name", golden_names("dcnv1_stencil_"))
+def test_dcnv1_corners_bit_exact(name):
+    g = golden(name)
+    s = shape_from_cfg(g["cfg"], orc.VARIANT_DCNV1)
+    k, st, p = _ksp(g["cfg"])
+    y0, x0, w4, _ = orc.corners(s, g["off"])
+    gy0, gx0, gw4 = dcn.dcn_corners(_cuda(g["off"]), (s.H, s.W), k, st, p, dcn.VARIANT_DCNV1)
+    assert np.array_equal(gy0.cpu().numpy(), y0) and np.array_equal(gx0.cpu().numpy(), x0)
+    assert np.array_equal(gw4.cpu().numpy().view(np.uint32), w4.view(np.uint32))
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS)
+@pytest.mark.parametrize("name", [n for n in golden_names("dcnv1_") if "stencil" not in n])
+def test_dcnv1_against_torchvision_golden(name, flags):
+    g = golden(name)
+    out, gx, goff, gw, gb = _engine(g, dcn.VARIANT_DCNV1, flags)
+    assert rel_err(out.cpu().numpy(), g["out"]) < FWD_TOL
+    assert rel_err(gx.cpu().numpy(), g["gx"]) < GRAD_TOL
+    assert rel_err(goff.cpu().numpy(), g["goff"]) < GRAD_TOL
+    assert rel_err(gw.cpu().numpy(), g["gw"]) < GRAD_TOL
+    assert rel_err(gb.cpu().numpy(), g["gb"]) < GRAD_TOL
+
+
+def test_dcnv1_functional_matches_torchvision_live():
+    """deform_conv2d_v1 has torchvision's call signature; compare on the GPU at a tensor-path size."""
+    tv = pytest.importorskip("torchvision.ops")
+    torch.manual_seed(5)
+    x = torch.randn(4, 64, 32, 32, device="cuda", requires_grad=True)
+    off = (torch.randn(4, 18, 32, 32, device="cuda") * 2).requires_grad_(True)
+    wt = (torch.randn(64, 64, 3, 3, device="cuda") * 0.06).requires_grad_(True)
+    bias = torch.randn(64, device="cuda", requires_grad=True)
+    gout = torch.randn(4, 64, 32, 32, device="cuda")
+    try:
+        ref = tv.deform_conv2d(x, off, wt, bias, stride=1, padding=1)
+    except (RuntimeError, NotImplementedError):
+        pytest.skip("torchvision has no CUDA deform_conv2d kernel in this build")
+    rg = torch.autograd.grad(ref, [x, off, wt, bias], gout)
+    out = dcn.deform_conv2d_v1(x, off, wt, bias, stride=1, padding=1)
+    og = torch.autograd.grad(out, [x, off, wt, bias], gout)
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < FWD_TOL
+    for a, b, nm in zip(og, rg, ("gx", "goff", "gw", "gb")):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < GRAD_TOL, nm

@@ -102,3 +102,27 @@ def test_sample_tensor_layout():
         x[:, c, c // s.W, c % s.W] = 1.0
     S = orc.sample(s, x, g["off"])
     assert np.array_equal(S, g["S"])
+
+
+# ---- DCN_VARIANT_DCNV1: the oracle against torchvision.ops.deform_conv2d's own outputs ----------
+@pytest.mark.parametrize("name", golden_names("dcnv1_stencil_"))
+def test_dcnv1_corners_bit_exact_vs_torchvision(name):
+    g = golden(name)
+    s = shape_from_cfg(g["cfg"], orc.VARIANT_DCNV1)
+    y0, x0, w4, _ = orc.corners(s, g["off"])
+    st = stencil_from_corners(y0, x0, w4, s.H, s.W)
+    ref = g["S"].transpose(0, 4, 2, 3, 1)
+    assert np.array_equal(st.view(np.uint32) & 0x7FFFFFFF, ref.view(np.uint32) & 0x7FFFFFFF)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("dcnv1_") if "stencil" not in n])
+def test_dcnv1_oracle_matches_torchvision(name):
+    g = golden(name)
+    s = shape_from_cfg(g["cfg"], orc.VARIANT_DCNV1)
+    out = orc.forward(s, g["x"], g["off"], g["weight"], g["bias"])
+    assert rel_err(out, g["out"]) < 2e-6
+    gx, goff, gw, gb = orc.backward(s, g["x"], g["off"], g["weight"], g["gout"])
+    assert rel_err(gx, g["gx"]) < 5e-6
+    assert rel_err(goff, g["goff"]) < 5e-6
+    assert rel_err(gw, g["gw"]) < 5e-6
+    assert rel_err(gb, g["gb"]) < 5e-6
