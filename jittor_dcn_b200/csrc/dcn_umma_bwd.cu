@@ -25,7 +25,9 @@ bool umma_bwd_data_supported(const Geo& g, int operand);
 size_t umma_bwd_data_wtile_bytes(const Geo& g, int operand);
 bool umma_bwd_data_fuses_wgrad(const Geo& g, int operand);
 int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, const float* off, const void* wt,
-                      const void* gout, float* goff, float* gw, uint8_t* wtiles, cudaStream_t st);
+                      const void* gout, float* goff, float* gw, uint8_t* wtiles, uint8_t* gtiles,
+                      cudaStream_t st);
+size_t umma_bwd_data_gtile_bytes(const Geo& g, int operand);
 
 static size_t plan_bytes(const Geo& g) { return align_up(sizeof(Tap) * (size_t)g.B * g.P, 1024); }
 
@@ -42,8 +44,9 @@ bool umma_bwd_supported(const Geo& g, int operand) {
 }
 
 size_t umma_bwd_workspace(const Geo& g, int operand) {
-  // [xt] then either [gxt | Wm^T tiles] (tensor-path data gradient) or [sampling plan] (generic)
-  const size_t a = umma_xt_bytes(g, DCN_OPERAND_FP32) + umma_bwd_data_wtile_bytes(g, operand);
+  // [xt] then either [gxt | Wm^T tiles | grad_out tiles] (tensor-path data gradient) or [sampling plan] (generic)
+  const size_t a = umma_xt_bytes(g, DCN_OPERAND_FP32) + umma_bwd_data_wtile_bytes(g, operand) +
+                   umma_bwd_data_gtile_bytes(g, operand);
   const size_t b = operand == DCN_OPERAND_FP32 ? plan_bytes(g) : 0;
   return umma_xt_bytes(g, operand) + (a > b ? a : b);
 }
@@ -67,11 +70,12 @@ int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, cons
   if (operand != DCN_OPERAND_FP32 || use_umma_data(g, operand)) {
     float* gxt = (float*)rest;
     uint8_t* wtiles = rest + umma_xt_bytes(g, DCN_OPERAND_FP32);
+    uint8_t* gtiles = wtiles + umma_bwd_data_wtile_bytes(g, operand);
     if (want_gx) DCN_CUDA_TRY(cudaMemsetAsync(gxt, 0, sizeof(float) * (size_t)g.B * xt_image_stride(g), st));
     DCN_CUDA_TRY(cudaMemsetAsync(goff, 0, sizeof(float) * (size_t)g.B * 2 * g.N * g.HW, st));
     const bool fused = umma_bwd_data_fuses_wgrad(g, operand);  // one pass over the samples yields gW as well
     if (fused) DCN_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.O * g.K, st));
-    if ((rc = umma_bwd_data_any(g, operand, xt, want_gx ? gxt : nullptr, off, wt, gout, goff, gw, wtiles, st)))
+    if ((rc = umma_bwd_data_any(g, operand, xt, want_gx ? gxt : nullptr, off, wt, gout, goff, gw, wtiles, gtiles, st)))
       return rc;
     if ((rc = launch_offset_scale(g, goff, st))) return rc;
     if (want_gx && (rc = launch_nhwc_to_nchw_add(g, t, gxt, gx, (flags & DCN_FLAG_ACCUM_GRAD_X) ? 1 : 0, st)))

@@ -21,7 +21,10 @@
 // Warp roles (768 threads, 1 CTA / SM, persistent over row tiles):
 //   warps  0-15  scatter / coord-grad epilogue (quarter = w % 4 of the TMEM lanes, w / 4 = column part)
 //   warp   16    MMA issuer          warp 17  Wm^T tile loader (cp.async.bulk)
-//   warps 18-19  grad_out converter (fp32 -> bf16 hi/lo, K-major A operand, once per tile)
+//   warps 18-19  grad_out operand: Jittor layout converts fp32 -> bf16 hi/lo in place (coalesced along
+//                the pixels); Torch layout rows are R floats apart, so a staging kernel
+//                (gout_tiles_torch_kernel) pre-builds every tile's UMMA images and one thread
+//                fetches them with cp.async.bulk
 //   warps 20-23  plan: offsets -> bit-exact coordinate chain -> scatter entries (2-deep ring)
 #include <cstdlib>
 #include <type_traits>
@@ -65,6 +68,7 @@ struct Params {
   const float* off;
   const void* gout;      // float or bfloat16
   const uint8_t* wtiles; // [cblocks][OB][hi|lo][ncols x 64] K-major SW128 images of Wm^T
+  const uint8_t* gtiles; // Torch layout: [tile][OB][hi|lo][128 rows x 64 o] K-major SW128 images of grad_out
   float* goff;           // raw g_iy / g_ix accumulators (zeroed); scaled afterwards
   int Gt, Rt, chunks, num_inst, num_tiles;  // backward tiling (rows = (instance, channel))
   FastDiv divR, divChunks;
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
       mbar_init(&pempty[a], kScatWarps);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&gfull[a], kConvWarps);
+      mbar_init(&gfull[a], VARIANT == DCN_VARIANT_TORCH ? 1 : kConvWarps);
       mbar_init(&gempty[a], 1);
       mbar_init(&sfull[a], kScatWarps);
       mbar_init(&sempty[a], 1);
@@ -243,6 +247,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
                  "r"(P.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (FUSE) {
+    // images beyond OB (the o >= 64*OB half of the M = 128 weight-gradient MMA) stay zero
+    const uint32_t zero_end = g_zero_off + (uint32_t)(P.g_imgs - P.OB) * NIMG * P.g_img;
+    for (uint32_t i = g_zero_off + tid * 16; i < zero_end; i += kThreads * 16)
+      *reinterpret_cast<uint4*>(gtile + i) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -527,54 +538,55 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
     const int ct = tid - kFirstConvWarp * 32;  // 0..63
     uint32_t gphase = 0;
     int gb = 0;
-    if (FUSE) {
-      // images beyond OB (the o >= 64*OB half of the M = 128 weight-gradient MMA) stay zero
-      const uint32_t zero_end = g_zero_off + (uint32_t)(P.g_imgs - P.OB) * NIMG * P.g_img;
-      for (uint32_t i = g_zero_off + ct * 16; i < zero_end; i += kConvWarps * 32 * 16)
-        *reinterpret_cast<uint4*>(gtile + i) = make_uint4(0, 0, 0, 0);
-    }
-    for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
-      mbar_wait_relaxed(&gempty[gb], gphase ^ 1, 64);
-      uint8_t* gdst = gtile + (size_t)gb * g_buf;
-      const int groups = P.OB * 8;  // groups of 8 output channels
-      const int rows = VARIANT == DCN_VARIANT_TORCH ? 128 : ncols;  // rows of the resident operand
-      for (int item = ct; item < rows * groups; item += kConvWarps * 32) {
-        const int mm = item % rows, og = item / rows;  // lanes run along the rows
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = 0.f;
-        const XT* src = nullptr;
-        const XT* gsrc = reinterpret_cast<const XT*>(P.gout);
-        if (VARIANT == DCN_VARIANT_TORCH) {
-          const int il2 = mm / P.Gt, i2 = mm - il2 * P.Gt;
-          const RowInfo ri = decode(P, tile * P.Rt + il2);
-          if (ri.valid)
-            src = gsrc + ((size_t)ri.b * g.O + og * 8) * g.HW + ri.r0 + (size_t)(ri.chunk * P.Gt + i2) * P.t.R;
-        } else {
-          const int b = tile / P.pix_blocks, p = (tile - b * P.pix_blocks) * ncols + mm;
-          if (p < g.HW) src = gsrc + ((size_t)b * g.O + og * 8) * g.HW + p;
+    if (VARIANT == DCN_VARIANT_TORCH) {
+      // the tile's images were staged by gout_tiles_torch_kernel: one bulk copy per tile
+      if (ct == 0) {
+        for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
+          mbar_wait_relaxed(&gempty[gb], gphase ^ 1, 64);
+          mbar_arrive_expect_tx(&gfull[gb], g_buf);
+          bulk_g2s(gtile + (size_t)gb * g_buf, P.gtiles + (size_t)tile * g_buf, g_buf, &gfull[gb]);
+          if (++gb == P.g_nbuf) {
+            gb = 0;
+            gphase ^= 1;
+          }
         }
-        if (src) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (og * 8 + k < g.O) v[k] = (float)__ldg(src + (size_t)k * g.HW);
-        }
-        uint4 hi, lo;
-        split_pair(v[0], v[1], hi.x, lo.x);
-        split_pair(v[2], v[3], hi.y, lo.y);
-        split_pair(v[4], v[5], hi.z, lo.z);
-        split_pair(v[6], v[7], hi.w, lo.w);
-        uint8_t* img = gdst + (size_t)(og >> 3) * NIMG * P.g_img;
-        const uint32_t so = kmajor_sw128_off(mm, (og & 7) * 8);
-        *reinterpret_cast<uint4*>(img + so) = hi;
-        if (!BF) *reinterpret_cast<uint4*>(img + P.g_img + so) = lo;
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&gfull[gb]);
-      if (++gb == P.g_nbuf) {
-        gb = 0;
-        gphase ^= 1;
+    } else {
+      for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
+        mbar_wait_relaxed(&gempty[gb], gphase ^ 1, 64);
+        uint8_t* gdst = gtile + (size_t)gb * g_buf;
+        const int groups = P.OB * 8;  // groups of 8 output channels
+        const int rows = ncols;       // rows of the resident operand: the tile's pixels
+        for (int item = ct; item < rows * groups; item += kConvWarps * 32) {
+          const int mm = item % rows, og = item / rows;  // lanes run along the pixels
+          float v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = 0.f;
+          const XT* gsrc = reinterpret_cast<const XT*>(P.gout);
+          const int b = tile / P.pix_blocks, p = (tile - b * P.pix_blocks) * ncols + mm;
+          if (p < g.HW) {
+            const XT* src = gsrc + ((size_t)b * g.O + og * 8) * g.HW + p;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (og * 8 + k < g.O) v[k] = (float)__ldg(src + (size_t)k * g.HW);
+          }
+          uint4 hi, lo;
+          split_pair(v[0], v[1], hi.x, lo.x);
+          split_pair(v[2], v[3], hi.y, lo.y);
+          split_pair(v[4], v[5], hi.z, lo.z);
+          split_pair(v[6], v[7], hi.w, lo.w);
+          uint8_t* img = gdst + (size_t)(og >> 3) * NIMG * P.g_img;
+          const uint32_t so = kmajor_sw128_off(mm, (og & 7) * 8);
+          *reinterpret_cast<uint4*>(img + so) = hi;
+          if (!BF) *reinterpret_cast<uint4*>(img + P.g_img + so) = lo;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gfull[gb]);
+        if (++gb == P.g_nbuf) {
+          gb = 0;
+          gphase ^= 1;
+        }
       }
     }
   } else {
@@ -619,6 +631,72 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols)
                  : "memory");
+  }
+}
+
+// grad_out rows of a Torch-layout tile are R floats apart (row (instance, i) = pixel r0 + i*R of
+// channel plane o), so gathering them inside the main kernel costs one L1 wavefront per float.
+// This staging pass reads 16 consecutive instances at a time (64-byte runs), transposes through
+// shared memory and writes every tile's operand exactly as the MMAs read it:
+//   gtiles[tile][ob][hi | lo][row m = il*Gt + i][64 o]  bf16, K-major, 128-byte swizzle.
+// Block = (16 instances) x (16 of the Gt channels) x (32 output channels) = 32 KB of floats.
+constexpr int kGtInst = 16, kGtCh = 16, kGtOsub = 32;
+constexpr int kGtRow = kGtOsub + 1;        // floats per (instance, channel) row, odd
+constexpr int kGtIS = kGtCh * kGtRow + 2;  // floats per instance: == 2 mod 32 -> (16 inst x 2 ch) lanes hit 32 banks
+
+template <typename T>
+__global__ void __launch_bounds__(256) gout_tiles_torch_kernel(const __grid_constant__ Params P,
+                                                               uint8_t* __restrict__ gtiles) {
+  constexpr int NIMG = sizeof(T) == 2 ? 1 : 2;
+  __shared__ float gt_buf[kGtInst * kGtIS];
+  const Geo& g = P.g;
+  const int Gt = P.Gt, tid = threadIdx.x;
+  const int ch_blocks = Gt / kGtCh;
+  const int o0 = (blockIdx.y / ch_blocks) * kGtOsub, i0 = (blockIdx.y % ch_blocks) * kGtCh;
+  {
+    // lanes: 16 instances (one 64-byte run) x 2 channels; the instance of a thread is fixed
+    const int r = tid & 15;
+    const RowInfo ri = decode(P, blockIdx.x * kGtInst + r);
+    const T* src = reinterpret_cast<const T*>(P.gout) + ((size_t)ri.b * g.O + o0) * g.HW + ri.r0 +
+                   ((size_t)ri.chunk * Gt + i0) * P.t.R;
+    float* dst = gt_buf + r * kGtIS;
+    const int p0 = tid >> 4;  // 0..15: (ol, i2) pairs, i2 fastest
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int it = p0 + 16 * k, ol = it / kGtCh, i2 = it % kGtCh;
+      v[k] = 0.f;
+      if (ri.valid && o0 + ol < g.O) v[k] = (float)__ldg(src + (size_t)ol * g.HW + (size_t)i2 * P.t.R);
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int it = p0 + 16 * k, ol = it / kGtCh, i2 = it % kGtCh;
+      dst[i2 * kGtRow + ol] = v[k];
+    }
+  }
+  __syncthreads();
+  // 16-byte chunks (8 o) of the images: lanes = 4 chunks x 8 consecutive rows of one instance
+  const uint32_t img_bytes = 128u * 128u;
+  const int ob = o0 >> 6, c_base = (o0 & 63) >> 3;
+#pragma unroll
+  for (int k = 0; k < kGtInst * kGtCh * (kGtOsub / 8) / 256; ++k) {
+    const int it = tid + 256 * k;
+    const int ck = it & 3, row = it >> 2, r = row / kGtCh, i2 = row % kGtCh;
+    const int inst = blockIdx.x * kGtInst + r, tile = inst / P.Rt, il = inst - tile * P.Rt;
+    if (tile >= P.num_tiles) continue;
+    const float* srow = gt_buf + r * kGtIS + i2 * kGtRow + ck * 8;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = srow[q];
+    uint4 hi, lo;
+    split_pair(v[0], v[1], hi.x, lo.x);
+    split_pair(v[2], v[3], hi.y, lo.y);
+    split_pair(v[4], v[5], hi.z, lo.z);
+    split_pair(v[6], v[7], hi.w, lo.w);
+    const int m = il * Gt + i0 + i2;
+    uint8_t* img = gtiles + ((size_t)tile * P.OB + ob) * NIMG * img_bytes + kmajor_sw128_off(m, (c_base + ck) * 8);
+    *reinterpret_cast<uint4*>(img) = hi;
+    if (NIMG == 2) *reinterpret_cast<uint4*>(img + img_bytes) = lo;
   }
 }
 
@@ -766,10 +844,19 @@ size_t umma_bwd_data_wtile_bytes(const Geo& g, int operand) {
   return align_up((size_t)P.cblocks * P.OB * P.w_stage, 1024);
 }
 
+// staged grad_out operand images (Torch layout only)
+size_t umma_bwd_data_gtile_bytes(const Geo& g, int operand) {
+  bd::Params P;
+  P.g = g;
+  if (g.variant != DCN_VARIANT_TORCH || !bwd_data_tiling(g, operand, &P, fuse_allowed())) return 0;
+  return align_up((size_t)P.num_tiles * P.OB * (operand == DCN_OPERAND_BF16 ? 1 : 2) * bd::kGImg, 1024);
+}
+
 // gxt (channels-last grad_x, may be null), goff and — when the shape fuses the weight gradient
 // (umma_bwd_data_fuses_wgrad) — gw must be zero on entry.
 int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, const float* off, const void* wt,
-                      const void* gout, float* goff, float* gw, uint8_t* wtiles, cudaStream_t st) {
+                      const void* gout, float* goff, float* gw, uint8_t* wtiles, uint8_t* gtiles,
+                      cudaStream_t st) {
   bd::Params P;
   P.g = g;
   const bool bf = operand == DCN_OPERAND_BF16;
@@ -796,6 +883,17 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
   P.off = off;
   P.gout = gout;
   P.wtiles = wtiles;
+  P.gtiles = gtiles;
+  if (g.variant == DCN_VARIANT_TORCH) {
+    const dim3 grid((unsigned)(((size_t)P.num_tiles * P.Rt + bd::kGtInst - 1) / bd::kGtInst),
+                    (unsigned)((P.OB * 64 / bd::kGtOsub) * (P.Gt / bd::kGtCh)));
+    KernelScope scope("gout_tiles_kernel", st);
+    if (bf)
+      bd::gout_tiles_torch_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(P, gtiles);
+    else
+      bd::gout_tiles_torch_kernel<float><<<grid, 256, 0, st>>>(P, gtiles);
+    DCN_KERNEL_CHECK("gout_tiles_kernel");
+  }
   P.goff = goff;
   P.gw = gw;
   P.ix_delta = (off_col_ch(g, 0) - off_row_ch(g, 0)) * g.HW;
