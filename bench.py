@@ -392,9 +392,15 @@ def main():
     import ctypes
     stream = torch.cuda.current_stream(dev)
 
+    # one scratch buffer for both phases of the step: the backward pass reuses the staged
+    # channels-last copy of x that the forward pass left at its head (DCN_FLAG_XT_STAGED)
+    from jittor_dcn_b200.functional import staged_workspace
+    ws = staged_workspace(x, wt, k, s, p, variant, operand, flags)
+
     def step():
-        out = dcn.dcn_forward(x, off, wt, bias, k, s, p, variant, operand=operand, flags=flags)
-        gx, goff, gw, gb = dcn.dcn_backward(x, off, wt, gout, True, k, s, p, variant, operand=operand, flags=flags)
+        out = dcn.dcn_forward(x, off, wt, bias, k, s, p, variant, operand=operand, flags=flags, ws=ws)
+        gx, goff, gw, gb = dcn.dcn_backward(x, off, wt, gout, True, k, s, p, variant, operand=operand, flags=flags,
+                                            ws=ws, xt_staged=ws is not None)
         if comm is not None:
             bucket[:n_w].copy_(gw.view(-1))
             bucket[n_w:n_w + n_b].copy_(gb)
@@ -499,6 +505,7 @@ def main():
         layer = cls(C, O, k, s, p).to(dev)
         layer.engine_flags = flags
         layer.operand = operand
+        layer.keep_staged_input = True
         with torch.no_grad():
             layer.offset_conv.weight.normal_(0, 0.01)
             layer.offset_conv.bias.normal_(0, 1.0)

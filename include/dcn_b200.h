@@ -86,7 +86,13 @@ enum {
   DCN_FLAG_FORCE_SIMT = 1 << 1,    /* use the generic CUDA-core kernels even when the
                                       tcgen05 path supports the shape (A/B testing) */
   DCN_FLAG_NO_GRAD_X = 1 << 2,     /* dcn_backward: skip grad_x (first layer of a net) */
-  DCN_FLAG_RELU_OUT = 1 << 3       /* reserved for the fused epilogue */
+  DCN_FLAG_RELU_OUT = 1 << 3,      /* reserved for the fused epilogue */
+  DCN_FLAG_XT_STAGED = 1 << 4      /* dcn_backward: the workspace is the very buffer the preceding
+                                      dcn_forward of the same shape / operand was given (sized for the
+                                      backward phase) and nothing has written to it since, so its head
+                                      still holds the staged copy of x: skip re-staging.  Only
+                                      meaningful when both phases run on the tensor path
+                                      (dcn_path_name == "umma"); ignored otherwise */
 };
 
 /* Problem description.  Constructor arguments of the reference modules

@@ -16,6 +16,7 @@ OPERAND_BF16 = 1
 FLAG_ACCUM_GRAD_X = 1 << 0
 FLAG_FORCE_SIMT = 1 << 1
 FLAG_NO_GRAD_X = 1 << 2
+FLAG_XT_STAGED = 1 << 4
 PHASE_FORWARD, PHASE_BACKWARD, PHASE_CORNERS = 0, 1, 2
 
 # every symbol include/dcn_b200.h declares (tests/test_abi.py checks the two lists agree)
@@ -107,6 +108,11 @@ def make_shape(B, C, O, H, W, kernel_size=3, stride=1, padding=1, variant=VARIAN
                operand=OPERAND_FP32, flags=0):
     (kh, kw), (sh, sw), (ph, pw) = _pair(kernel_size), _pair(stride), _pair(padding)
     return DcnShape(B, C, O, H, W, kh, kw, sh, sw, ph, pw, variant, operand, flags)
+
+
+def path_name(shape, phase):
+    """Which kernel family runs: "umma" (tcgen05 kernels) or "simt" (generic CUDA-core kernels) for this problem / phase."""
+    return load().dcn_path_name(ctypes.byref(shape), phase).decode()
 
 
 def output_hw(shape):

@@ -65,7 +65,9 @@ int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, cons
     return DCN_ERR_UNSUPPORTED;
   }
   int rc;
-  if ((rc = launch_nchw_to_nhwc(g, t, x, xt, operand, st))) return rc;
+  // DCN_FLAG_XT_STAGED: the head of the workspace still holds the staged copy of x that dcn_forward
+  // wrote for this very shape / operand (same layout in both phases) — skip the transpose
+  if (!(flags & DCN_FLAG_XT_STAGED) && (rc = launch_nchw_to_nhwc(g, t, x, xt, operand, st))) return rc;
   const bool want_gx = !(flags & DCN_FLAG_NO_GRAD_X) && gx != nullptr;
   if (operand != DCN_OPERAND_FP32 || use_umma_data(g, operand)) {
     float* gxt = (float*)rest;
@@ -77,7 +79,6 @@ int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, cons
     if (fused) DCN_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.O * g.K, st));
     if ((rc = umma_bwd_data_any(g, operand, xt, want_gx ? gxt : nullptr, off, wt, gout, goff, gw, wtiles, gtiles, st)))
       return rc;
-    if ((rc = launch_offset_scale(g, goff, st))) return rc;
     if (want_gx && (rc = launch_nhwc_to_nchw_add(g, t, gxt, gx, (flags & DCN_FLAG_ACCUM_GRAD_X) ? 1 : 0, st)))
       return rc;
     if ((rc = launch_bias_grad(g, gout, operand, gb, st))) return rc;

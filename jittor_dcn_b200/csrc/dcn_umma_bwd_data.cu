@@ -47,17 +47,16 @@ constexpr int kPlanPerThread = 8;
 constexpr int kPlanMax = kPlanThreads * kPlanPerThread;  // 1024 entries per column block
 constexpr uint32_t kGImg = 128 * 64 * 2;                 // one bf16 image of a grad_out K block
 
-// what the scatter warps need for one (class instance, column): 64 bytes
+// what the scatter warps need for one (class instance, column): 16 bytes = ONE shared-memory load.
+// The framed staging layout (dcn_umma_common.cuh) makes the four corners base + {0, C, pitch,
+// pitch + C} for the value loads AND the scatter alike, with no validity mask; the corner weights
+// are re-formed from (fx, fy) in registers exactly as the forward pass forms them.
 struct __align__(16) ScatEntry {
-  uint32_t off[4];   // corner BYTE offsets (float image) for the value loads: the zero pad pixel if invalid
-  uint32_t roff[4];  // corner BYTE offsets for the scatter: an out-of-image corner is redirected to the
-                     // nearest in-image pixel, where it adds 0.0 (weight 0) — unconditional REDs, no
-                     // branches, and no hot spot on a single dummy address
-  float w[4];        // corner weights, 0 for invalid corners
+  uint32_t base;  // BYTE offset (float image) of the top-left corner inside the framed image
   float fx, fy;
-  int gidx;          // index of the grad_offset element that receives g_iy (the channel moving the row);
-                     // g_ix goes ix_delta further (Params); -1 = none
-  int live;          // 0 for padding columns / rows of no instance: nothing to scatter
+  int gidx;       // index of the grad_offset element that receives g_iy (the channel moving the row);
+                  // g_ix goes ix_delta further (Params).  < 0: dead entry (padding column / row of
+                  // no instance / no corner inside the image): nothing to scatter, sample 0
 };
 
 struct Params {
@@ -69,7 +68,8 @@ struct Params {
   const void* gout;      // float or bfloat16
   const uint8_t* wtiles; // [cblocks][OB][hi|lo][ncols x 64] K-major SW128 images of Wm^T
   const uint8_t* gtiles; // Torch layout: [tile][OB][hi|lo][128 rows x 64 o] K-major SW128 images of grad_out
-  float* goff;           // raw g_iy / g_ix accumulators (zeroed); scaled afterwards
+  float* goff;           // grad_offset accumulators (zeroed)
+  float scale_iy, scale_ix;  // chain-rule factors of the coordinate normalisation (1 for DCNv1)
   int Gt, Rt, chunks, num_inst, num_tiles;  // backward tiling (rows = (instance, channel))
   FastDiv divR, divChunks;
   int pix_blocks;        // Jittor: ceil(HW / ncols) pixel blocks per image
@@ -150,39 +150,20 @@ __device__ __forceinline__ void plan_prepare(const Params& P, int tile, int cb, 
 
 __device__ __forceinline__ ScatEntry plan_finish(const Geo& g, const PlanWork& pw) {
   ScatEntry e;
-  const uint32_t pad = 4u * (uint32_t)(g.H * g.W * g.C + pw.chan_base);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    e.off[k] = pad;
-    e.roff[k] = 4u * (uint32_t)pw.chan_base;  // pixel 0 (adds 0.0)
-    e.w[k] = 0.f;
-  }
+  int base = xt_null_base(g);
   e.fx = e.fy = 0.f;
   e.gidx = -1;
-  e.live = 0;
   if (pw.valid) {
     const Tap tp = tap_of(g, pw.h, pw.w, pw.n, pw.ox, pw.oy);
-    const unsigned m = corner_mask(tp, g.H, g.W);
-    e.live = 1;
-    // scatter targets: valid corners at their pixel, invalid ones clamped into the image (add 0.0)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int yy = min(max(tp.y0 + (k >> 1), 0), g.H - 1), xx = min(max(tp.x0 + (k & 1), 0), g.W - 1);
-      e.roff[k] = 4u * (uint32_t)((yy * g.W + xx) * g.C + pw.chan_base);
-    }
-    if (m) {
-      float cw[4];
-      corner_weights(tp, cw);
-      const int base = (tp.y0 * g.W + tp.x0) * g.C + pw.chan_base;  // may be < 0 only for masked corners
-      if (m & 1u) { e.off[0] = 4u * (uint32_t)base;                     e.w[0] = cw[0]; }
-      if (m & 2u) { e.off[1] = 4u * (uint32_t)(base + g.C);             e.w[1] = cw[1]; }
-      if (m & 4u) { e.off[2] = 4u * (uint32_t)(base + g.W * g.C);       e.w[2] = cw[2]; }
-      if (m & 8u) { e.off[3] = 4u * (uint32_t)(base + g.W * g.C + g.C); e.w[3] = cw[3]; }
+    bool inside;
+    base = xt_corner_base(g, tp.y0, tp.x0, inside);
+    if (inside) {
       e.fx = tp.fx;
       e.fy = tp.fy;
-      e.gidx = pw.gidx;  // a point with no valid corner has zero coordinate gradient
+      e.gidx = pw.gidx;
     }
   }
+  e.base = 4u * (uint32_t)(base + pw.chan_base);
   return e;
 }
 
@@ -286,6 +267,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
     const int gl = lane & (RW - 1);             // lane inside its reduction group
     int acc = 0, pb = 0, sb = 0;
     uint32_t acc_phase = 0, pphase = 0, sphase = 0;
+    // byte distances to the east / south corner in the framed images (x: float or bfloat16; grad: float)
+    const int dg1 = 4 * g.C, dg2 = 4 * xt_row_pitch(g);
+    const int dx1 = (int)sizeof(XT) * g.C, dx2 = (int)sizeof(XT) * xt_row_pitch(g);
     for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
       // Torch: lane = (class instance il, channel i_lo) for the whole tile
       int slot = 0, chan = 0, bimg = 0;
@@ -328,28 +312,31 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const float gs = __uint_as_float(raw[u]);
-            const ScatEntry* e = pl + c0 + u;
-            const uint4 off = *reinterpret_cast<const uint4*>(e->off);
-            const uint4 roff = *reinterpret_cast<const uint4*>(e->roff);
-            const float4 w = *reinterpret_cast<const float4*>(e->w);
-            const float2 f = *reinterpret_cast<const float2*>(&e->fx);
+            const uint4 e4 = *reinterpret_cast<const uint4*>(pl + c0 + u);  // {base, fx, fy, gidx}
+            const float fx = __uint_as_float(e4.y), fy = __uint_as_float(e4.z);
             // entry offsets are bytes of the float grad image; the bf16 x image is half as wide
             constexpr int XS = BF ? 1 : 0;
-            const float v0 = (float)__ldg(reinterpret_cast<const XT*>(ximg + (off.x >> XS)));
-            const float v1 = (float)__ldg(reinterpret_cast<const XT*>(ximg + (off.y >> XS)));
-            const float v2 = (float)__ldg(reinterpret_cast<const XT*>(ximg + (off.z >> XS)));
-            const float v3 = (float)__ldg(reinterpret_cast<const XT*>(ximg + (off.w >> XS)));
-            if (gimg && e->live) {
-              // branch-free, coalesced red.global.add.f32 x4 (an out-of-image corner adds 0.0 in-image)
-              atomicAdd(reinterpret_cast<float*>(gimg + roff.x), gs * w.x);
-              atomicAdd(reinterpret_cast<float*>(gimg + roff.y), gs * w.y);
-              atomicAdd(reinterpret_cast<float*>(gimg + roff.z), gs * w.z);
-              atomicAdd(reinterpret_cast<float*>(gimg + roff.w), gs * w.w);
+            const char* xp = ximg + (e4.x >> XS);
+            const float v0 = (float)__ldg(reinterpret_cast<const XT*>(xp));
+            const float v1 = (float)__ldg(reinterpret_cast<const XT*>(xp + dx1));
+            const float v2 = (float)__ldg(reinterpret_cast<const XT*>(xp + dx2));
+            const float v3 = (float)__ldg(reinterpret_cast<const XT*>(xp + dx2 + dx1));
+            // corner weights as the forward pass forms them (dcn_common.cuh:corner_weights)
+            const float ex = __fsub_rn(1.0f, fx), sy = __fsub_rn(1.0f, fy);
+            const float w0 = __fmul_rn(sy, ex), w1 = __fmul_rn(sy, fx), w2 = __fmul_rn(fy, ex),
+                        w3 = __fmul_rn(fy, fx);
+            if (gimg && (int)e4.w >= 0) {
+              // coalesced red.global.add.f32 x4; a corner outside the image lands on the frame
+              char* gp = gimg + e4.x;
+              atomicAdd(reinterpret_cast<float*>(gp), gs * w0);
+              atomicAdd(reinterpret_cast<float*>(gp + dg1), gs * w1);
+              atomicAdd(reinterpret_cast<float*>(gp + dg2), gs * w2);
+              atomicAdd(reinterpret_cast<float*>(gp + dg2 + dg1), gs * w3);
             }
-            part_g[u] = gs * ((v1 - v0) * (1.f - f.y) + (v3 - v2) * f.y);
-            part_g[8 + u] = gs * ((v2 - v0) * (1.f - f.x) + (v3 - v1) * f.x);
+            part_g[u] = gs * ((v1 - v0) * sy + (v3 - v2) * fy);
+            part_g[8 + u] = gs * ((v2 - v0) * ex + (v3 - v1) * fx);
             // the sample itself (same blend order as the forward pass)
-            if (FUSE) smp8[u] = fmaf(v3, w.w, fmaf(v2, w.z, fmaf(v1, w.y, v0 * w.x)));
+            if (FUSE) smp8[u] = fmaf(v3, w3, fmaf(v2, w2, fmaf(v1, w1, v0 * w0)));
           }
           if (FUSE) {
             // columns c0..c0+7 of row m: one 16-byte chunk of the MN-major operand, swizzled by m % 8
@@ -383,7 +370,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
             const int gidx = pl[c0 + col].gidx;
             // value 0..7: g_ix -> the column-moving offset channel; 8..15: g_iy -> the row-moving one
             if (gidx >= 0 && part_g[0] != 0.f)
-              atomicAdd(P.goff + (size_t)gidx + (vi < 8 ? (size_t)P.ix_delta : 0), part_g[0]);
+              atomicAdd(P.goff + (size_t)gidx + (vi < 8 ? (size_t)P.ix_delta : 0),
+                        part_g[0] * (vi < 8 ? P.scale_ix : P.scale_iy));
           }
         }
         tc_fence_before();
@@ -732,7 +720,7 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
   P->nslices = P->nchunks = 1;
   P->cb_per_slice = 0;
   if ((long long)g.B * 2 * g.N * g.HW > 0x7fffffffLL) return false;
-  if ((long long)(g.H * g.W + 1) * g.C >= (1LL << 30)) return false;  // 32-bit byte offsets inside an image
+  if ((long long)xt_image_stride(g) >= (1LL << 30)) return false;  // 32-bit byte offsets inside an image
   P->OB = (g.O + 63) / 64;
   if (P->OB > 4) return false;
   P->Gt = P->Rt = P->chunks = P->num_inst = 1;
@@ -897,6 +885,10 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
   P.goff = goff;
   P.gw = gw;
   P.ix_delta = (off_col_ch(g, 0) - off_row_ch(g, 0)) * g.HW;
+  // grad_offset[row-moving channel] = g_iy * sy * 2 / Dx ; [column-moving channel] = g_ix * sx * 2 / Dy
+  // (autograd of train.py:111-113 -> GridSampler.h:27-36; dcn_simt.cu:offset_scale_kernel)
+  P.scale_iy = g.variant == DCN_VARIANT_DCNV1 ? 1.f : g.sy * 2.0f / g.Dx;
+  P.scale_ix = g.variant == DCN_VARIANT_DCNV1 ? 1.f : g.sx * 2.0f / g.Dy;
   if (const char* e = getenv("DCN_BWD_GBUF"))
     if (atoi(e) == 1) P.g_nbuf = 1;
   const size_t smem = ((size_t)P.g_nbuf * P.OB + (P.g_imgs - P.OB)) * nimg * P.g_img + 2 * (size_t)P.w_stage +

@@ -122,20 +122,32 @@ __host__ __device__ inline int perm_channel(int c, int variant, int G, int Cs) {
   return variant == DCN_VARIANT_TORCH ? (c % Cs) * G + c / Cs : c;
 }
 
-// Plan entry as the gather warps consume it (32 bytes in shared memory): the four corners'
-// float offsets inside image b of the channels-last copy and their weights.  An out-of-image
-// corner (zero padding) points at the all-zero pad pixel that closes every image and carries
-// weight 0, so the gather needs no branches and never multiplies a foreign (possibly
-// non-finite) value.
+// Channels-last staging copy with an all-zero frame: [B][(H + 3) x (W + 2)][C].  Image pixel (y, x)
+// lives at frame position (y + 1, x + 1); frame rows 0, H + 1, H + 2 and frame columns 0, W + 1
+// are zero.  Every sample with at least one corner inside the image has its top-left corner
+// (y0, x0) in [-1, H-1] x [-1, W-1], so its four corners are base + {0, C, pitch, pitch + C} with
+// NO validity test: zero padding is reading the frame, and gradient scattered into the frame is
+// discarded.  The 2 x 2 block at frame position (H + 1, 0) is frame only: it stands in for samples
+// with no corner inside the image (and for padding rows / columns of a tile), so a foreign,
+// possibly non-finite value is never multiplied by a zero weight.
+__host__ __device__ inline int xt_row_pitch(const Geo& g) { return (g.W + 2) * g.C; }  // elements
+__host__ __device__ inline size_t xt_image_stride(const Geo& g) { return (size_t)(g.H + 3) * (g.W + 2) * g.C; }
+__host__ __device__ inline int xt_null_base(const Geo& g) { return (g.H + 1) * (g.W + 2) * g.C; }
+// element offset (channel 0) of the top-left corner of a sample; inside = some corner is in the image
+__device__ __forceinline__ int xt_corner_base(const Geo& g, int y0, int x0, bool& inside) {
+  inside = (unsigned)(y0 + 1) <= (unsigned)g.H && (unsigned)(x0 + 1) <= (unsigned)g.W;
+  return inside ? ((y0 + 1) * (g.W + 2) + (x0 + 1)) * g.C : xt_null_base(g);
+}
+
+// Plan entry as the forward gather warps consume it (32 bytes in shared memory): the four
+// corners' element offsets inside image b of the framed copy and their weights.
 struct __align__(16) PlanEntry {
   int off[4];   // nw, ne, sw, se
   float w[4];
 };
 
-// channels-last staging copy: [B][H*W + 1][C]; pixel H*W of every image is zero
-__host__ __device__ inline size_t xt_image_stride(const Geo& g) { return (size_t)(g.H * g.W + 1) * g.C; }
-
 // x / xt: float (DCN_OPERAND_FP32) or bfloat16 (DCN_OPERAND_BF16)
+// (the frame is re-zeroed on every call: the workspace belongs to the caller)
 int launch_nchw_to_nhwc(const Geo& g, const Tiling& t, const void* x, void* xt, int operand, cudaStream_t st);
 int launch_nhwc_to_nchw_add(const Geo& g, const Tiling& t, const float* gxt, float* gx, int accumulate,
                             cudaStream_t st);

@@ -109,28 +109,26 @@ __device__ __forceinline__ void plan_prepare(const Geo& g, const Tiling& t, cons
   pw.valid = 1;
 }
 
-// coordinate chain (bit-exact, dcn_common.cuh:tap_of) -> branch-free gather entry
+// coordinate chain (bit-exact, dcn_common.cuh:tap_of) -> branch-free gather entry: corners
+// outside the image fall on the zero frame of the staging copy, samples with no corner inside
+// (and padding rows / columns) on the frame-only block with zero weights
 __device__ __forceinline__ PlanEntry plan_finish(const Geo& g, const PlanWork& pw) {
   PlanEntry e;
-  const int pad = g.H * g.W * g.C + pw.chan_base;  // the zero pixel
+  int base = xt_null_base(g);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    e.off[k] = pad;
-    e.w[k] = 0.f;
-  }
+  for (int k = 0; k < 4; ++k) e.w[k] = 0.f;
   if (pw.valid) {
     const Tap tp = tap_of(g, pw.h, pw.w, pw.n, pw.ox, pw.oy);
-    const unsigned m = corner_mask(tp, g.H, g.W);
-    if (m) {
-      float cw[4];
-      corner_weights(tp, cw);
-      const int base = (tp.y0 * g.W + tp.x0) * g.C + pw.chan_base;  // only used for valid corners
-      if (m & 1u) { e.off[0] = base;                     e.w[0] = cw[0]; }
-      if (m & 2u) { e.off[1] = base + g.C;               e.w[1] = cw[1]; }
-      if (m & 4u) { e.off[2] = base + g.W * g.C;         e.w[2] = cw[2]; }
-      if (m & 8u) { e.off[3] = base + g.W * g.C + g.C;   e.w[3] = cw[3]; }
-    }
+    bool inside;
+    base = xt_corner_base(g, tp.y0, tp.x0, inside);
+    if (inside) corner_weights(tp, e.w);
   }
+  base += pw.chan_base;
+  const int pitch = xt_row_pitch(g);
+  e.off[0] = base;
+  e.off[1] = base + g.C;
+  e.off[2] = base + pitch;
+  e.off[3] = base + pitch + g.C;
   return e;
 }
 
@@ -533,9 +531,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     for (int it = 0; it < kIt; ++it) {
       const int pair = slot + it * pairs_per_pass;
       if (VARIANT == DCN_VARIANT_TORCH) {
-        const int il = pair >> 6, kk = pair & 63;
+        // class instance fastest: the lanes of a warp then fill BOTH 8-byte halves of the 16-byte
+        // chunks they touch, i.e. all 32 banks (instance-major order left half the banks idle and
+        // made every A-image store a 4-way conflict)
+        const int il = pair % t.Rt, kk = pair / t.Rt;
         item_il[it] = il;
-        ent_idx[it] = pair;  // = il * 64 + kk
+        ent_idx[it] = il * 64 + kk;
         st_off[it] = mnmajor_sw128_off(grp * (V * t.Rt) + il * V, kk, kAMnLbo, kAMnSbo);
       } else {
         item_il[it] = 0;

@@ -8,7 +8,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (FLAG_ACCUM_GRAD_X, FLAG_FORCE_SIMT, FLAG_NO_GRAD_X, OPERAND_BF16, OPERAND_FP32,
+from ._lib import (FLAG_ACCUM_GRAD_X, FLAG_FORCE_SIMT, FLAG_NO_GRAD_X, FLAG_XT_STAGED, OPERAND_BF16, OPERAND_FP32,
                    PHASE_BACKWARD, PHASE_FORWARD, VARIANT_DCNV1, VARIANT_JITTOR, VARIANT_TORCH)
 
 _workspaces = {}
@@ -69,8 +69,22 @@ def _shape_of(x, weight, kernel_size, stride, padding, variant, operand, flags):
     return _lib.make_shape(B, C, O, H, W, kernel_size, stride, padding, variant, operand, flags)
 
 
+def staged_workspace(x, weight, kernel_size=3, stride=1, padding=1, variant=VARIANT_TORCH,
+                     operand=OPERAND_FP32, flags=0):
+    """A private scratch buffer big enough for BOTH phases of one layer call, or None when either
+    phase would not run on the tensor path.  Passing it to dcn_forward and then to dcn_backward
+    (xt_staged=True) lets the backward pass reuse the staged copy of x (DCN_FLAG_XT_STAGED)."""
+    lib = _lib.load()
+    shp = _shape_of(x, weight, kernel_size, stride, padding, variant, operand, flags)
+    if any(_lib.path_name(shp, ph) != "umma" for ph in (PHASE_FORWARD, PHASE_BACKWARD)):
+        return None
+    need = max(lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_FORWARD),
+               lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_BACKWARD))
+    return torch.empty(need, dtype=torch.uint8, device=x.device)
+
+
 def dcn_forward(x, offset, weight, bias, kernel_size=3, stride=1, padding=1, variant=VARIANT_TORCH,
-                operand=OPERAND_FP32, flags=0):
+                operand=OPERAND_FP32, flags=0, ws=None):
     """out[B,O,Ho,Wo] = engine forward on CUDA tensors (no autograd)."""
     lib = _lib.load()
     shp = _shape_of(x, weight, kernel_size, stride, padding, variant, operand, flags)
@@ -87,7 +101,8 @@ def dcn_forward(x, offset, weight, bias, kernel_size=3, stride=1, padding=1, var
     with torch.cuda.device(x.device):
         stream = torch.cuda.current_stream(x.device)
         need = lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_FORWARD)
-        ws = _workspace(x.device, stream.cuda_stream, need)
+        if ws is None:
+            ws = _workspace(x.device, stream.cuda_stream, need)
         rc = lib.dcn_forward(ctypes.byref(shp), _ptr(x), _ptr(offset), _ptr(weight), _ptr(bias),
                              _ptr(out), _ptr(ws), ws.numel(), ctypes.c_void_p(stream.cuda_stream))
     _lib.check(rc, "dcn_forward")
@@ -95,11 +110,15 @@ def dcn_forward(x, offset, weight, bias, kernel_size=3, stride=1, padding=1, var
 
 
 def dcn_backward(x, offset, weight, grad_out, has_bias, kernel_size=3, stride=1, padding=1,
-                 variant=VARIANT_TORCH, operand=OPERAND_FP32, flags=0, need_grad_x=True):
-    """-> grad_x (or None), grad_offset, grad_weight, grad_bias (or None); all float32."""
+                 variant=VARIANT_TORCH, operand=OPERAND_FP32, flags=0, need_grad_x=True, ws=None,
+                 xt_staged=False):
+    """-> grad_x (or None), grad_offset, grad_weight, grad_bias (or None); all float32.
+    ws / xt_staged: the buffer from staged_workspace() that the matching dcn_forward used."""
     lib = _lib.load()
     if not need_grad_x:
         flags |= FLAG_NO_GRAD_X
+    if xt_staged and ws is not None:
+        flags |= FLAG_XT_STAGED
     shp = _shape_of(x, weight, kernel_size, stride, padding, variant, operand, flags)
     Ho, Wo = _lib.output_hw(shp)
     N = shp.kh * shp.kw
@@ -114,7 +133,8 @@ def dcn_backward(x, offset, weight, grad_out, has_bias, kernel_size=3, stride=1,
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev)
         need = lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_BACKWARD)
-        ws = _workspace(dev, stream.cuda_stream, need)
+        if ws is None:
+            ws = _workspace(dev, stream.cuda_stream, need)
         rc = lib.dcn_backward(ctypes.byref(shp), _ptr(x), _ptr(offset), _ptr(weight), _ptr(grad_out),
                               _ptr(gx), _ptr(goff), _ptr(gw), _ptr(gb), _ptr(ws), ws.numel(),
                               ctypes.c_void_p(stream.cuda_stream))
@@ -148,12 +168,18 @@ class DeformConvFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, offset, weight, bias, cfg):
-        kernel_size, stride, padding, variant, operand, flags = cfg
+        kernel_size, stride, padding, variant, operand, flags = cfg[:6]
+        keep_staged = len(cfg) > 6 and cfg[6]
         home = x.device
         dev = _compute_device(x)
         xd, od, wd = _to_device(x, dev), _to_device(offset, dev), _to_device(weight, dev)
         bd = _to_device(bias, dev)
-        out = dcn_forward(xd, od, wd, bd, kernel_size, stride, padding, variant, operand, flags)
+        act = torch.bfloat16 if operand == OPERAND_BF16 else torch.float32
+        ctx.ws = None
+        if keep_staged and xd.dtype == act and xd.is_contiguous():
+            # private scratch that lives until backward: its head keeps the staged copy of x
+            ctx.ws = staged_workspace(xd, wd, kernel_size, stride, padding, variant, operand, flags)
+        out = dcn_forward(xd, od, wd, bd, kernel_size, stride, padding, variant, operand, flags, ws=ctx.ws)
         ctx.save_for_backward(xd, od, wd)
         ctx.cfg, ctx.home, ctx.has_bias = cfg, home, bias is not None
         ctx.dtypes = (x.dtype, offset.dtype, weight.dtype)
@@ -162,11 +188,13 @@ class DeformConvFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         xd, od, wd = ctx.saved_tensors
-        kernel_size, stride, padding, variant, operand, flags = ctx.cfg
+        kernel_size, stride, padding, variant, operand, flags = ctx.cfg[:6]
         dev = xd.device
         gx, goff, gw, gb = dcn_backward(xd, od, wd, _to_device(grad_out, dev), ctx.has_bias,
                                         kernel_size, stride, padding, variant, operand, flags,
-                                        need_grad_x=ctx.needs_input_grad[0])
+                                        need_grad_x=ctx.needs_input_grad[0], ws=ctx.ws,
+                                        xt_staged=ctx.ws is not None)
+        ctx.ws = None
         home = ctx.home
 
         def back(t, dtype):
@@ -180,9 +208,12 @@ class DeformConvFunction(torch.autograd.Function):
 
 
 def deform_conv2d(x, offset, weight, bias=None, kernel_size=3, stride=1, padding=1,
-                  variant=VARIANT_TORCH, operand=OPERAND_FP32, flags=0):
-    """Differentiable DeformConv2d core: everything after the offset conv."""
-    cfg = (_lib._pair(kernel_size), _lib._pair(stride), _lib._pair(padding), variant, operand, flags)
+                  variant=VARIANT_TORCH, operand=OPERAND_FP32, flags=0, keep_staged=False):
+    """Differentiable DeformConv2d core: everything after the offset conv.
+    keep_staged: hold a private scratch buffer (backward-phase size) from forward to backward so
+    that the backward pass reuses the staged copy of x instead of transposing it again."""
+    cfg = (_lib._pair(kernel_size), _lib._pair(stride), _lib._pair(padding), variant, operand, flags,
+           bool(keep_staged))
     return DeformConvFunction.apply(x, offset, weight, bias, cfg)
 
 

@@ -28,6 +28,10 @@ class TorchDeformConv2d(nn.Module):
         self.N = self.kernel_size[0] * self.kernel_size[1]
         self.operand = _lib.OPERAND_FP32
         self.engine_flags = 0
+        # True: a private scratch buffer of backward-phase size lives from forward to backward so
+        # that the backward pass reuses the staged channels-last copy of x (no second transpose);
+        # costs device memory between the two passes, saves one full pass over x
+        self.keep_staged_input = False
 
         # companion offset conv: C -> 2N, same k/s/p (train.py:80-85)
         self.offset_conv = nn.Conv2d(in_channels, 2 * self.N, kernel_size=self.kernel_size,
@@ -44,7 +48,8 @@ class TorchDeformConv2d(nn.Module):
     def forward(self, x):
         offset = self.offset_conv(x)
         return deform_conv2d(x, offset, self.weight, self.bias, self.kernel_size, self.stride,
-                             self.padding, self.variant, self.operand, self.engine_flags)
+                             self.padding, self.variant, self.operand, self.engine_flags,
+                             keep_staged=self.keep_staged_input and torch.is_grad_enabled())
 
     def extra_repr(self):
         return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, "

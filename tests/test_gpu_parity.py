@@ -191,6 +191,45 @@ def test_flags_accumulate_and_skip_grad_x():
     assert rel_err(gw2.cpu().numpy(), gw.cpu().numpy()) < 1e-5
 
 
+def test_backward_reuses_the_forward_staging():
+    """DCN_FLAG_XT_STAGED: backward on the forward's own scratch buffer == backward that re-stages x."""
+    from jittor_dcn_b200.functional import staged_workspace
+    torch.manual_seed(5)
+    B, C, O, H, W = 3, 32, 32, 24, 40
+    x = torch.randn(B, C, H, W, device="cuda")
+    off = torch.randn(B, 18, H, W, device="cuda") * 2
+    w = torch.randn(O, C, 3, 3, device="cuda") * 0.1
+    gout = torch.randn(B, O, H, W, device="cuda")
+    for variant in (dcn.VARIANT_TORCH, dcn.VARIANT_JITTOR, dcn.VARIANT_DCNV1):
+        ws = staged_workspace(x, w, 3, 1, 1, variant)
+        assert ws is not None
+        ref = dcn.dcn_backward(x, off, w, gout, True, 3, 1, 1, variant)
+        ws.fill_(0xff)  # garbage everywhere: only a real forward pass makes the staging valid
+        out = dcn.dcn_forward(x, off, w, None, 3, 1, 1, variant, ws=ws)
+        got = dcn.dcn_backward(x, off, w, gout, True, 3, 1, 1, variant, ws=ws, xt_staged=True)
+        assert rel_err(out.cpu().numpy(), dcn.dcn_forward(x, off, w, None, 3, 1, 1, variant).cpu().numpy()) < 1e-6
+        for a, b in zip(got, ref):
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-5
+
+
+def test_module_keep_staged_input_matches_default():
+    torch.manual_seed(6)
+    m = dcn.TorchDeformConv2d(32, 32, 3, 1, 1).cuda()
+    with torch.no_grad():
+        m.offset_conv.weight.normal_(0, 0.05)
+        m.offset_conv.bias.normal_(0, 1.0)
+    x = torch.randn(2, 32, 20, 24, device="cuda")
+    grads = []
+    for keep in (False, True):
+        m.keep_staged_input = keep
+        xi = x.clone().requires_grad_(True)
+        m.zero_grad()
+        m(xi).square().sum().backward()
+        grads.append([xi.grad.clone()] + [q.grad.clone() for q in m.parameters()])
+    for a, b in zip(*grads):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-5
+
+
 def test_error_path_reports_small_workspace():
     import ctypes
     lib = dcn.load()
