@@ -81,7 +81,10 @@ __device__ __forceinline__ void plan_prepare(const Geo& g, const Tiling& t, cons
   pw.h = pw.w = pw.n = pw.chan_base = 0;
   int b, p, n;
   if (VARIANT == DCN_VARIANT_TORCH) {
-    const int il = e >> 6, kk = e & 63, j = kb * 64 + kk;
+    // Rt <= 4: entries are instance-interleaved (e = kk * Rt + il) so that the entries a warp reads
+    // together sit next to each other in shared memory, i.e. in different banks; Rt = 8 keeps the
+    // instance-major order (e = il * 64 + kk), which measured faster there
+    const int kk = t.Rt <= 4 ? e / t.Rt : (e & 63), il = t.Rt <= 4 ? e - kk * t.Rt : (e >> 6), j = kb * 64 + kk;
     const TileRowInfo ri = decode_inst(t, tile * t.Rt + il);
     if (!ri.valid || j >= g.K) return;
     uint32_t cb, q, pp, nn;
@@ -523,20 +526,29 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     // `groups` lanes share one sampling point; a "pair" is one (class instance, column) of the
     // Torch tile or one row of the Jittor tile
     const int groups = VARIANT == DCN_VARIANT_TORCH ? (t.Gt / V) : (64 / V);
-    const int grp = pt % groups, slot = pt / groups;
+    int grp = pt % groups, slot = pt / groups;
     const int pairs_per_pass = kProdThreads / groups;
+    // fp32, Gt = 64 (two class instances of 16 groups): a 64-bit shared store is served per half-warp,
+    // and the 8-byte pieces of a half-warp must fall into 32 different banks.  Lanes are therefore
+    // laid out (group low 3 bits, instance, group high bit): each quarter-warp still gathers one
+    // contiguous 128-byte run of ONE entry, while a half-warp stores both 8-byte halves (instance 0 / 1)
+    // of 8 different 16-byte chunks — conflict-free, where the plain order was a 2-way conflict.
+    const bool paired = VARIANT == DCN_VARIANT_TORCH && !BF && t.Rt == 2;
+    if (paired) grp = (lane & 7) | ((lane >> 4) << 3);
     int ent_idx[kIt], item_il[kIt];
     uint32_t st_off[kIt];
 #pragma unroll
     for (int it = 0; it < kIt; ++it) {
       const int pair = slot + it * pairs_per_pass;
       if (VARIANT == DCN_VARIANT_TORCH) {
-        // class instance fastest: the lanes of a warp then fill BOTH 8-byte halves of the 16-byte
-        // chunks they touch, i.e. all 32 banks (instance-major order left half the banks idle and
-        // made every A-image store a 4-way conflict)
-        const int il = pair % t.Rt, kk = pair / t.Rt;
+        // consecutive slots read consecutive plan entries (see plan_prepare)
+        int il = t.Rt <= 4 ? pair % t.Rt : (pair >> 6), kk = t.Rt <= 4 ? pair / t.Rt : (pair & 63);
+        if (paired) {
+          il = (lane >> 3) & 1;
+          kk = (warp - kFirstProdWarp) + kProdWarps * it;
+        }
         item_il[it] = il;
-        ent_idx[it] = il * 64 + kk;
+        ent_idx[it] = t.Rt <= 4 ? kk * t.Rt + il : il * 64 + kk;
         st_off[it] = mnmajor_sw128_off(grp * (V * t.Rt) + il * V, kk, kAMnLbo, kAMnSbo);
       } else {
         item_il[it] = 0;
