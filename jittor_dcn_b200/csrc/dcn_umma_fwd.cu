@@ -21,7 +21,10 @@
 //
 // fp32 parity: every fp32 operand v is split as hi = bf16(v), lo = bf16(v - hi) and the product
 // is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation (relative error ~5e-6, measured).
+#include <cuda.h>
+
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "dcn_umma.h"
@@ -64,6 +67,11 @@ struct FwdParams {
   uint32_t b_tile;     // bytes of one bf16 B image = O*128
   uint32_t stage_bytes;
   uint32_t tmem_cols;  // 2*O rounded to a power of two >= 32
+  // Torch layout, forward: out[b, o, r0 + i*R] of a tile is Gt x O runs of only Rt floats, R floats
+  // apart.  With tma_out the epilogue stages `tpg` consecutive tiles (box_r = tpg*Rt >= 4 adjacent
+  // instances) in shared memory as [o][i][r] and ONE tensor-map store writes the 16-byte runs.
+  int tma_out, tpg, box_r, n_ost;  // n_ost = 1 or 2 staging buffers
+  uint32_t stage_out_bytes;         // of ONE staging buffer
 };
 
 // One plan entry in the making: the index math is done and the two offset loads are in
@@ -154,7 +162,8 @@ __device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
 // operand is ONE bf16 image and every K step ONE MMA; otherwise fp32 with the hi/lo split (two
 // images, three MMAs).  A gather item is one 16-byte load per corner: V = 4 fp32 or 8 bf16 channels.
 template <int VARIANT, int MODE, bool BF>
-__global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_constant__ FwdParams P) {
+__global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_constant__ FwdParams P,
+                                                                   const __grid_constant__ CUtensorMap tmap_out) {
   constexpr int V = BF ? 8 : 4;
   constexpr int NIMG = BF ? 1 : 2;
   constexpr int kIt = 128 * 64 / V / kProdThreads;  // gather items per thread and K block: 4 or 2
@@ -169,7 +178,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
   uint8_t* stage_base = smem;
   uint8_t* gbuf_base = smem + (size_t)P.stages * P.stage_bytes;
   const uint32_t gbuf_bytes = MODE == MODE_WGRAD ? 2u * NIMG * P.g_img : 0u;  // 2 row halves x (hi | lo)
-  PlanEntry* plan = reinterpret_cast<PlanEntry*>(gbuf_base + (size_t)(MODE == MODE_WGRAD ? P.n_gbuf : 0) * gbuf_bytes);
+  float* ostage = reinterpret_cast<float*>(gbuf_base);  // forward + tma_out: [O][Gt][box_r] floats
+  PlanEntry* plan = reinterpret_cast<PlanEntry*>(gbuf_base + (size_t)(MODE == MODE_WGRAD ? P.n_gbuf : 0) * gbuf_bytes +
+                                                 (MODE == MODE_FWD ? P.n_ost * P.stage_out_bytes : 0u));
   uint64_t* bars = reinterpret_cast<uint64_t*>(plan + 2 * P.plan_cap);
   uint64_t* full = bars;                   // [stages]
   uint64_t* empty = bars + kMaxStages;     // [stages]
@@ -191,6 +202,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     tile_step = gridDim.x;
     kb0 = 0;
     kb1 = t.KB;
+    if (P.tpg == 2) tile0 = 2 * blockIdx.x;  // CTAs walk PAIRS of tiles: 2c, 2c+1, 2(c+grid), ...
   } else {
     const int slice = blockIdx.x % P.nslices;
     tile0 = blockIdx.x / P.nslices;
@@ -198,6 +210,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     kb0 = slice * P.kb_per_slice;
     kb1 = min(t.KB, kb0 + P.kb_per_slice);
   }
+  const bool pairs = MODE == MODE_FWD && P.tpg == 2;
+  auto next_tile = [&](int tile) {
+    return pairs ? ((tile & 1) ? tile + 2 * (int)gridDim.x - 1 : tile + 1) : tile + tile_step;
+  };
 
   if (tid == 0) {
     for (int s = 0; s < P.stages; ++s) {
@@ -230,18 +246,23 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     if constexpr (MODE == MODE_FWD) {
     // ================================================================ epilogue (forward)
     uint32_t acc_phase = 0;
-    int acc = 0;
-    for (int tile = tile0; tile < t.num_tiles; tile += tile_step) {
-      const int m = warp * 32 + lane;  // TMEM lane == tile row
+    int acc = 0, ost = 0;
+    const int m = warp * 32 + lane;  // TMEM lane == tile row
+    for (int tile = tile0; tile < t.num_tiles; tile = next_tile(tile)) {
       size_t out_off = 0;
       bool valid;
+      int il = 0, ich = 0;           // Torch: class instance inside the tile, channel inside the Gt chunk
+      TileRowInfo ri0 = {0, 0, 0, 0};
       if (VARIANT == DCN_VARIANT_TORCH) {
         // tile row m = grp*(V*Rt) + il*V + ch: V channels of class instance il are V consecutive rows
-        const int grp = m / (V * t.Rt), il = (m / V) % t.Rt, ch = m % V;
+        const int grp = m / (V * t.Rt), ch = m % V;
+        il = (m / V) % t.Rt;
+        ich = V * grp + ch;
         const TileRowInfo ri = decode_inst(t, tile * t.Rt + il);
         valid = ri.valid;
-        const int i = ri.chunk * t.Gt + V * grp + ch;
+        const int i = ri.chunk * t.Gt + ich;
         out_off = (size_t)ri.b * O * g.HW + (size_t)(ri.r0 + i * t.R);
+        if (P.tma_out) ri0 = decode_inst(t, (tile - (tile % P.tpg)) * t.Rt);  // first instance of the group
       } else {
         const int b = tile / t.pix_blocks, p = (tile - b * t.pix_blocks) * 128 + m;
         valid = p < g.HW;
@@ -250,23 +271,67 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       mbar_wait_relaxed(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * O);
-      for (int c0 = 0; c0 < O; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-        if (valid) {
+      if (VARIANT == DCN_VARIANT_TORCH && P.tma_out) {
+        const int sub = tile % P.tpg;  // position of this tile inside its staging group
+        if (sub == 0) {
+          // the store that last used this staging buffer must have finished reading it
+          if (tid == 0) {
+            if (P.n_ost == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        float* obuf = ostage + (size_t)ost * (P.stage_out_bytes >> 2);
+        float* dst = obuf + (size_t)ich * P.box_r + sub * t.Rt + il;
+        const int o_stride = t.Gt * P.box_r;
+        for (int c0 = 0; c0 < O; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float bv = P.bias ? __ldg(P.bias + c0 + i) : 0.f;
-            P.out[out_off + (size_t)(c0 + i) * g.HW] = v[i] + bv;
+            dst[(size_t)(c0 + i) * o_stride] = v[i] + bv;
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (sub == P.tpg - 1) {
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy engine
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (tid == 0) {
+            // box {box_r, Gt, O, 1} at (r0, chunk*Gt, 0, b) of out viewed as [B][O][G][R]
+            asm volatile(
+                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                    reinterpret_cast<uint64_t>(&tmap_out)),
+                "r"(smem_u32(obuf)), "r"(ri0.r0), "r"(ri0.chunk * t.Gt), "r"(0), "r"(ri0.b)
+                : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          if (P.n_ost == 2) ost ^= 1;
+        }
+      } else {
+        for (int c0 = 0; c0 < O; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float bv = P.bias ? __ldg(P.bias + c0 + i) : 0.f;
+              P.out[out_off + (size_t)(c0 + i) * g.HW] = v[i] + bv;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    // the last tensor store must have left shared memory before the CTA exits
+    if (VARIANT == DCN_VARIANT_TORCH && P.tma_out && tid == 0)
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
     // ================================================================ grad_out converter, then the
     // one-shot epilogue (weight gradient).  Per row tile: g[row m, o] = gout[b(m), o, r(m)] is
@@ -275,7 +340,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     const int O_pad = P.o_blocks * 128;
     int ab = 0;
     uint32_t aphase = 0;
-    for (int tile = tile0; tile < t.num_tiles; tile += tile_step) {
+    for (int tile = tile0; tile < t.num_tiles; tile = next_tile(tile)) {
       mbar_wait_relaxed(&aempty[ab], aphase ^ 1);
       uint8_t* gb = gbuf_base + (size_t)ab * gbuf_bytes;
       // items: (o, group of 4 consecutive tile rows); lanes run along the row groups
@@ -355,7 +420,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       const uint32_t idesc = make_idesc_bf16(128, O, VARIANT == DCN_VARIANT_TORCH, false);
       int s = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = tile0; tile < t.num_tiles; tile += tile_step) {
+      for (int tile = tile0; tile < t.num_tiles; tile = next_tile(tile)) {
         mbar_wait_relaxed(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * O);
@@ -408,7 +473,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       int s = 0, ab = 0;
       uint32_t phase = 0, aphase = 0;
       bool first_tile = true;
-      for (int tile = tile0; tile < t.num_tiles; tile += tile_step) {
+      for (int tile = tile0; tile < t.num_tiles; tile = next_tile(tile)) {
         mbar_wait_relaxed(&afull[ab], aphase, 64);
         const uint32_t gb = smem_u32(gbuf_base + (size_t)ab * gbuf_bytes);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -463,7 +528,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     if (MODE == MODE_FWD && lane == 0) {
       int s = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < t.num_tiles; tile += tile_step) {
+      for (int tile = tile0; tile < t.num_tiles; tile = next_tile(tile)) {
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_relaxed(&empty[s], phase ^ 1);
           uint8_t* dst = stage_base + (size_t)s * P.stage_bytes + NIMG * kATile;
@@ -489,7 +554,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         if (pt + u * kPlanThreads < n_ent)
           plan_prepare<VARIANT>(g, t, P.off, tile0, kb0, pt + u * kPlanThreads, pw[u]);
     }
-    for (int tile = tile0; tile < t.num_tiles; tile += tile_step) {
+    for (int tile = tile0; tile < t.num_tiles; tile = next_tile(tile)) {
       for (int kb = kb0; kb < kb1; ++kb) {
         PlanEntry* pl = plan + pbuf * P.plan_cap;
         mbar_wait_relaxed(&pempty[pbuf], pphase ^ 1, 64);
@@ -503,7 +568,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         int ntile = tile, nkb = kb + 1;
         if (nkb == kb1) {
           nkb = kb0;
-          ntile = tile + tile_step;
+          ntile = next_tile(tile);
         }
         if (ntile < t.num_tiles) {
 #pragma unroll
@@ -564,7 +629,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     auto advance = [&](Pos& q) {
       if (++q.kb == kb1) {
         q.kb = kb0;
-        q.tile += tile_step;
+        q.tile = next_tile(q.tile);
       }
       if (++q.s == P.stages) {
         q.s = 0;
@@ -744,6 +809,36 @@ size_t umma_fwd_workspace(const Geo& g, int operand) {
   return umma_xt_bytes(g, operand) + align_up((size_t)t.KB * nimg * g.O * 128, 1024);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// out[B, O, Ho*Wo] of the Torch layout viewed as a 4-D tensor [B][O][G][R] (pixel = i*R + r), box
+// {box_r, Gt, O, 1}: what one staged tile group covers.  false if the driver call is unavailable.
+static bool make_out_tensor_map(const Geo& g, const Tiling& t, int box_r, float* out, CUtensorMap* map) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)t.R, (cuuint64_t)t.G, (cuuint64_t)g.O, (cuuint64_t)g.B};
+  const cuuint64_t strides[3] = {(cuuint64_t)t.R * 4, (cuuint64_t)g.HW * 4, (cuuint64_t)g.O * g.HW * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)box_r, (cuuint32_t)t.Gt, (cuuint32_t)g.O, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static void common_params(const Geo& g, FwdParams& P) {
   const int n_ent = g.variant == DCN_VARIANT_TORCH ? P.t.Rt * 64 : 128 * P.t.taps_per_kb;
   P.plan_cap = (n_ent + 255) / 256 * 256;
@@ -753,15 +848,21 @@ static void common_params(const Geo& g, FwdParams& P) {
   P.o_blocks = 1;
   P.n_gbuf = 0;
   P.g_img = 0;
+  P.tma_out = 0;
+  P.tpg = 1;
+  P.n_ost = 1;
+  P.box_r = 0;
+  P.stage_out_bytes = 0;
 }
 
 template <int MODE>
-static int launch_gemm(const Geo& g, int operand, const FwdParams& P, int grid, size_t smem, cudaStream_t st) {
+static int launch_gemm(const Geo& g, int operand, const FwdParams& P, const CUtensorMap& tmap, int grid,
+                       size_t smem, cudaStream_t st) {
 #define DCN_GEMM_CASE(V, BFV)                                                                              \
   do {                                                                                                     \
     DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<V, MODE, BFV>,                                      \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-    umma_gemm_kernel<V, MODE, BFV><<<grid, kFwdThreads, smem, st>>>(P);                                    \
+    umma_gemm_kernel<V, MODE, BFV><<<grid, kFwdThreads, smem, st>>>(P, tmap);                              \
   } while (0)
   const bool bf = operand == DCN_OPERAND_BF16;
   if (g.variant == DCN_VARIANT_TORCH) {
@@ -797,7 +898,27 @@ int umma_forward_any(const Geo& g, int operand, const void* x, const float* off,
   P.out = out;
   P.b_tile = (uint32_t)g.O * 128;
   P.stage_bytes = nimg * (kATile + P.b_tile);
-  const size_t fixed = 2 * (size_t)P.plan_cap * sizeof(PlanEntry) + 256 + 1024;  // plan ring, barriers, align slack
+  size_t fixed = 2 * (size_t)P.plan_cap * sizeof(PlanEntry) + 256 + 1024;  // plan ring, barriers, align slack
+  // Torch layout: stage the output of box_r >= 4 adjacent class instances and write it with one
+  // tensor-map store (16-byte runs) instead of 4-byte stores R floats apart
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  // (Rt = 2 only: with Rt >= 4 the direct stores already write 16-byte runs, and the staged path
+  // measured slower there)
+  if (g.variant == DCN_VARIANT_TORCH && P.t.Rt == 2 && !getenv("DCN_FWD_NO_TMA_OUT")) {
+    const int box_r = P.t.Rt < 4 ? 4 : P.t.Rt;
+    const size_t bytes = sizeof(float) * (size_t)g.O * P.t.Gt * box_r;
+    if (P.t.R % box_r == 0 && bytes <= 64 * 1024 && g.O <= 256 &&
+        (size_t)2 * P.stage_bytes + bytes + fixed <= 227 * 1024 && make_out_tensor_map(g, P.t, box_r, out, &tmap)) {
+      P.tma_out = 1;
+      P.box_r = box_r;
+      P.tpg = box_r / P.t.Rt;
+      P.stage_out_bytes = (uint32_t)align_up(bytes, 1024);
+      // two staging buffers when three pipeline stages still fit next to them
+      P.n_ost = (size_t)3 * P.stage_bytes + 2 * P.stage_out_bytes + fixed <= 227 * 1024 ? 2 : 1;
+      fixed += (size_t)P.n_ost * P.stage_out_bytes;
+    }
+  }
   int stages = (int)((227 * 1024 - fixed) / P.stage_bytes);
   // A few stages are enough to overlap the (fast) MMAs with the (slow) gather; every KB of
   // shared memory not taken stays L1 for the gather's footprint (L1 + smem share 256 KB).
@@ -813,9 +934,10 @@ int umma_forward_any(const Geo& g, int operand, const void* x, const float* off,
   P.tmem_cols = pow2_cols(2 * g.O);
   const size_t smem = (size_t)P.stages * P.stage_bytes + fixed;
   const int sms = num_sms();
-  const int grid = P.t.num_tiles < sms ? P.t.num_tiles : sms;
+  const int groups = (P.t.num_tiles + P.tpg - 1) / P.tpg;  // CTAs walk groups of tpg tiles
+  const int grid = groups < sms ? groups : sms;
   KernelScope scope("umma_fwd_kernel", st);
-  if ((rc = launch_gemm<MODE_FWD>(g, operand, P, grid, smem, st))) return rc;
+  if ((rc = launch_gemm<MODE_FWD>(g, operand, P, tmap, grid, smem, st))) return rc;
   DCN_KERNEL_CHECK("umma_fwd_kernel");
   return DCN_OK;
 }
@@ -865,7 +987,9 @@ int umma_wgrad_any(const Geo& g, int operand, const void* xt, const float* off, 
   const int grid = P.nslices * P.nchunks;
   KernelScope scope("umma_bwd_weight_kernel", st);
   int rc;
-  if ((rc = launch_gemm<MODE_WGRAD>(g, operand, P, grid, smem, st))) return rc;
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if ((rc = launch_gemm<MODE_WGRAD>(g, operand, P, tmap, grid, smem, st))) return rc;
   DCN_KERNEL_CHECK("umma_bwd_weight_kernel");
   return DCN_OK;
 }
