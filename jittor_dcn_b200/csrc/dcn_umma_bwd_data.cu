@@ -18,14 +18,15 @@
 //                 TMEM columns are 128 consecutive output pixels.  Streamed operand A = Wm^T,
 //                 resident operand B = converted grad_out pixels.
 //
-// Warp roles (768 threads, 1 CTA / SM, persistent over row tiles):
+// Warp roles (704 threads Torch layout / 768 Jittor layout, 1 CTA / SM, persistent over row tiles):
 //   warps  0-15  scatter / coord-grad epilogue (quarter = w % 4 of the TMEM lanes, w / 4 = column part)
-//   warp   16    MMA issuer          warp 17  Wm^T tile loader (cp.async.bulk)
-//   warps 18-19  grad_out operand: Jittor layout converts fp32 -> bf16 hi/lo in place (coalesced along
-//                the pixels); Torch layout rows are R floats apart, so a staging kernel
-//                (gout_tiles_torch_kernel) pre-builds every tile's UMMA images and one thread
-//                fetches them with cp.async.bulk
-//   warps 20-23  plan: offsets -> bit-exact coordinate chain -> scatter entries (2-deep ring)
+//   warp   16    MMA issuer          warp 17  loader: lane 0 streams the Wm^T tiles, lane 1 (Torch
+//                layout) the staged grad_out tiles (cp.async.bulk)
+//   warps 18-21  plan: offsets -> bit-exact coordinate chain -> scatter entries (2-deep ring)
+//   warps 22-23  (Jittor layout only) grad_out converter fp32 -> bf16 hi/lo, coalesced along the
+//                pixels.  Torch-layout rows are R floats apart, so a staging kernel
+//                (gout_tiles_torch_kernel) pre-builds every tile's UMMA images instead; without the
+//                two converter warps the scatter warps get 88 registers.
 #include <cstdlib>
 #include <type_traits>
 
@@ -38,13 +39,20 @@ using namespace ptx;
 
 namespace bd {
 
-constexpr int kScatWarps = 16, kConvWarps = 2, kPlanWarps = 4;
+constexpr int kScatWarps = 16, kConvWarps = 2;
 constexpr int kMmaWarp = kScatWarps, kLoadWarp = kScatWarps + 1;
-constexpr int kFirstConvWarp = kScatWarps + 2, kFirstPlanWarp = kFirstConvWarp + kConvWarps;
-constexpr int kThreads = (kFirstPlanWarp + kPlanWarps) * 32;  // 768
-constexpr int kPlanThreads = kPlanWarps * 32;
+constexpr int kFirstPlanWarp = kScatWarps + 2;
+// Role layout by the number of plan warps PW:
+//   Torch layout, Gt = 64 (Rt = 2, <= 256 entries per block): PW = 2 and no converter warps = 20 warps, i.e.
+//                 5 per SM sub-partition and 96 registers per thread for the scatter loop;
+//   Torch layout, Rt >= 4 (more sampling points per block): PW = 4, 22 warps, 80 registers;
+//   Jittor layout: PW = 4 plus the 2 converter warps, 24 warps, 80 registers.
+__host__ __device__ constexpr int first_conv_warp_of(int pw) { return kFirstPlanWarp + pw; }
+__host__ __device__ constexpr int threads_of(int variant, int pw) {
+  return (first_conv_warp_of(pw) + (variant == DCN_VARIANT_TORCH ? 0 : kConvWarps)) * 32;
+}
 constexpr int kPlanPerThread = 8;
-constexpr int kPlanMax = kPlanThreads * kPlanPerThread;  // 1024 entries per column block
+__host__ __device__ constexpr int plan_max_of(int pw) { return pw * 32 * kPlanPerThread; }
 constexpr uint32_t kGImg = 128 * 64 * 2;                 // one bf16 image of a grad_out K block
 
 // what the scatter warps need for one (class instance, column): 16 bytes = ONE shared-memory load.
@@ -169,8 +177,8 @@ __device__ __forceinline__ ScatEntry plan_finish(const Geo& g, const PlanWork& p
 
 // RW = lanes that share one sampling point (32, or 16 when only 16 channels do)
 // BF  = bf16 operand mode: x / weight / grad_out are bfloat16, one image per operand, one MMA per K step
-template <int VARIANT, int RW, bool FUSE, bool BF>
-__global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_constant__ Params P) {
+template <int VARIANT, int RW, bool FUSE, bool BF, int PW>
+__global__ void __launch_bounds__(threads_of(VARIANT, PW), 1) bwd_data_kernel(const __grid_constant__ Params P) {
   constexpr int NIMG = BF ? 1 : 2;
   typedef typename std::conditional<BF, __nv_bfloat16, float>::type XT;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
       mbar_init(&wempty[a], 1);
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], kScatWarps);
-      mbar_init(&pfull[a], kPlanWarps);
+      mbar_init(&pfull[a], PW);
       mbar_init(&pempty[a], kScatWarps);
     }
     for (int a = 0; a < 2; ++a) {
@@ -232,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
   if (FUSE) {
     // images beyond OB (the o >= 64*OB half of the M = 128 weight-gradient MMA) stay zero
     const uint32_t zero_end = g_zero_off + (uint32_t)(P.g_imgs - P.OB) * NIMG * P.g_img;
-    for (uint32_t i = g_zero_off + tid * 16; i < zero_end; i += kThreads * 16)
+    for (uint32_t i = g_zero_off + tid * 16; i < zero_end; i += threads_of(VARIANT, PW) * 16)
       *reinterpret_cast<uint4*>(gtile + i) = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
@@ -299,7 +307,16 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
         uint8_t* s_row = sbuf + (size_t)sb * s_buf + (size_t)(m >> 3) * 1024 + (m & 7) * 128;
         const ScatEntry* pl = plan + pb * P.plan_cap + slot * ncols;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ncols);
-        for (int c0 = part * cols_per_part; c0 < (part + 1) * cols_per_part; c0 += 8) {
+        // WIDE would reduce the coordinate gradient in batches of 16 columns (32 values over 32 lanes cost
+        // the same 31 shuffles as 16 values do).  Measured SLOWER on B200 (cfg2: 13.2 vs 11.7 ms): one
+        // long pass per block exposes more latency than the saved shuffles buy.  Kept for reference.
+        constexpr bool WIDE = false;
+        constexpr int NB = WIDE ? 2 : 1;  // 8-column sub-batches per reduction
+        for (int cc = part * cols_per_part; cc < (part + 1) * cols_per_part; cc += 8 * NB) {
+          float part_g[16 * NB];  // [0 .. 8*NB) g_ix of the batch's columns, [8*NB .. 16*NB) g_iy
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+          const int c0 = cc + 8 * nb;
           uint32_t raw[8];
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                        : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]), "=r"(raw[4]), "=r"(raw[5]),
@@ -307,7 +324,6 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
                        : "r"(taddr + c0)
                        : "memory");
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          float part_g[16];  // [0..7] g_ix of the 8 columns, [8..15] g_iy
           float smp8[8];     // fused: the 8 samples of this row
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
@@ -333,8 +349,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
               atomicAdd(reinterpret_cast<float*>(gp + dg2), gs * w2);
               atomicAdd(reinterpret_cast<float*>(gp + dg2 + dg1), gs * w3);
             }
-            part_g[u] = gs * ((v1 - v0) * sy + (v3 - v2) * fy);
-            part_g[8 + u] = gs * ((v2 - v0) * ex + (v3 - v1) * fx);
+            part_g[8 * nb + u] = gs * ((v1 - v0) * sy + (v3 - v2) * fy);
+            part_g[8 * NB + 8 * nb + u] = gs * ((v2 - v0) * ex + (v3 - v1) * fx);
             // the sample itself (same blend order as the forward pass)
             if (FUSE) smp8[u] = fmaf(v3, w3, fmaf(v2, w2, fmaf(v1, w1, v0 * w0)));
           }
@@ -349,14 +365,15 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
             *reinterpret_cast<uint4*>(s_row + so) = hi;
             if (!BF) *reinterpret_cast<uint4*>(s_row + s_img + so) = lo;
           }
+          }  // sub-batch
           // butterfly reduce-scatter over the RW lanes that share the sampling points:
-          // afterwards lane gl (< 16) holds the total of value index gl
-          if (RW == 32) {
+          // afterwards lane gl (< 16*NB) holds the total of value index gl
+          if (!WIDE && RW == 32) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) part_g[k] += __shfl_xor_sync(0xffffffffu, part_g[k], 16);
           }
 #pragma unroll
-          for (int s = 8, n = 8; s >= 1; s >>= 1, n >>= 1) {
+          for (int s = 8 * NB, n = 8 * NB; s >= 1; s >>= 1, n >>= 1) {
             const bool up = (lane & s) != 0;
 #pragma unroll
             for (int k = 0; k < n; ++k) {
@@ -365,13 +382,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
               part_g[k] = keep + __shfl_xor_sync(grp_mask, send, s);
             }
           }
-          if (gl < 16 && (RW == 16 || lane < 16)) {
-            const int vi = gl & 15, col = vi & 7;
-            const int gidx = pl[c0 + col].gidx;
-            // value 0..7: g_ix -> the column-moving offset channel; 8..15: g_iy -> the row-moving one
+          if (WIDE || (gl < 16 && (RW == 16 || lane < 16))) {
+            const int vi = WIDE ? lane : (gl & 15), col = vi & (8 * NB - 1);
+            const int gidx = pl[cc + col].gidx;
+            // lower half of the values: g_ix -> the column-moving offset channel; upper half: g_iy -> the row-moving one
             if (gidx >= 0 && part_g[0] != 0.f)
-              atomicAdd(P.goff + (size_t)gidx + (vi < 8 ? (size_t)P.ix_delta : 0),
-                        part_g[0] * (vi < 8 ? P.scale_ix : P.scale_iy));
+              atomicAdd(P.goff + (size_t)gidx + (vi < 8 * NB ? (size_t)P.ix_delta : 0),
+                        part_g[0] * (vi < 8 * NB ? P.scale_ix : P.scale_iy));
           }
         }
         tc_fence_before();
@@ -519,27 +536,27 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
             if (s == 0) phase ^= 1;
           }
       }
-    }
-  } else if (warp < kFirstPlanWarp) {
-    // ================================================================ grad_out converter
-    // A operand of GEMM-1: g[row m, o] = gout[b, o, r0 + (chunk*Gt + i_lo)*R], K-major, per 64 o's
-    const int ct = tid - kFirstConvWarp * 32;  // 0..63
-    uint32_t gphase = 0;
-    int gb = 0;
-    if (VARIANT == DCN_VARIANT_TORCH) {
-      // the tile's images were staged by gout_tiles_torch_kernel: one bulk copy per tile
-      if (ct == 0) {
-        for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
-          mbar_wait_relaxed(&gempty[gb], gphase ^ 1, 64);
-          mbar_arrive_expect_tx(&gfull[gb], g_buf);
-          bulk_g2s(gtile + (size_t)gb * g_buf, P.gtiles + (size_t)tile * g_buf, g_buf, &gfull[gb]);
-          if (++gb == P.g_nbuf) {
-            gb = 0;
-            gphase ^= 1;
-          }
+    } else if (VARIANT == DCN_VARIANT_TORCH && lane == 1) {
+      // the tile's grad_out images were staged by gout_tiles_torch_kernel: one bulk copy per tile
+      uint32_t gphase = 0;
+      int gb = 0;
+      for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
+        mbar_wait_relaxed(&gempty[gb], gphase ^ 1, 64);
+        mbar_arrive_expect_tx(&gfull[gb], g_buf);
+        bulk_g2s(gtile + (size_t)gb * g_buf, P.gtiles + (size_t)tile * g_buf, g_buf, &gfull[gb]);
+        if (++gb == P.g_nbuf) {
+          gb = 0;
+          gphase ^= 1;
         }
       }
-    } else {
+    }
+  } else if (warp >= first_conv_warp_of(PW)) {
+    // ================================================================ grad_out converter (Jittor layout only)
+    // A operand of GEMM-1: g[row m, o] = gout[b, o, r0 + (chunk*Gt + i_lo)*R], K-major, per 64 o's
+    const int ct = tid - first_conv_warp_of(PW) * 32;  // 0..63
+    uint32_t gphase = 0;
+    int gb = 0;
+    {
       for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
         mbar_wait_relaxed(&gempty[gb], gphase ^ 1, 64);
         uint8_t* gdst = gtile + (size_t)gb * g_buf;
@@ -579,7 +596,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_data_kernel(const __grid_cons
     }
   } else {
     // ================================================================ plan warps
-    const int pt = tid - kFirstPlanWarp * 32;  // 0..127
+    const int pt = tid - kFirstPlanWarp * 32;  // 0..63 / 0..127
+    constexpr int kPlanThreads = PW * 32;
     const int n_ent = P.plan_cap;
     int pb = 0;
     uint32_t pphase = 0;
@@ -745,7 +763,7 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
       const size_t plan = 2 * (size_t)P->Rt * ncols * sizeof(bd::ScatEntry);
       const size_t rest = 2 * (size_t)(nimg * ncols * 128) + 2 * nimg * (size_t)(128 * 128) + plan + 256 + 1024;
       const size_t zero = (size_t)(2 - P->OB) * nimg * bd::kGImg, real = (size_t)P->OB * nimg * bd::kGImg;
-      if (P->Rt * ncols <= bd::kPlanMax && real + zero + rest <= 227 * 1024) {
+      if (P->Rt * ncols <= bd::plan_max_of(4) && real + zero + rest <= 227 * 1024) {
         P->fuse_w = 1;
         P->g_imgs = 2;
         P->g_nbuf = (2 * real + zero + rest <= 227 * 1024) ? 2 : 1;
@@ -768,7 +786,7 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
       const size_t plan = 2 * (size_t)P->Rt * ncols * sizeof(bd::ScatEntry);
       const size_t real = (size_t)P->OB * nimg * bd::kGImg;
       const size_t rest = 2 * (size_t)(nimg * ncols * 128) + plan + 256 + 1024;
-      if (P->Rt * ncols <= bd::kPlanMax && real + rest <= 227 * 1024) {
+      if (P->Rt * ncols <= bd::plan_max_of(4) && real + rest <= 227 * 1024) {
         P->g_nbuf = (2 * real + rest <= 227 * 1024) ? 2 : 1;
         P->ncols = ncols;
         P->cblocks = (g.K + ncols - 1) / ncols;
@@ -789,7 +807,7 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
     const size_t plan = 2 * (size_t)taps * ncols * sizeof(bd::ScatEntry);
     const size_t real = (size_t)P->OB * nimg * (ncols * 128);
     const size_t rest = 2 * (size_t)(nimg * 128 * 128) + plan + 256 + 1024;
-    if (taps * ncols <= bd::kPlanMax && real + rest <= 227 * 1024) {
+    if (taps * ncols <= bd::plan_max_of(4) && real + rest <= 227 * 1024) {
       P->g_nbuf = (2 * real + rest <= 227 * 1024) ? 2 : 1;
       P->ncols = ncols;
       P->pix_blocks = (g.HW + ncols - 1) / ncols;
@@ -906,29 +924,32 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
   }
   const bool narrow = g.variant == DCN_VARIANT_TORCH ? P.Gt == 16 : g.C == 16;  // 16 channels per sampling point
   KernelScope scope("umma_bwd_data_kernel", st);
-#define DCN_LAUNCH_BD(V, RW, F)                                                                          \
-  do {                                                                                                   \
-    if (bf) {                                                                                            \
-      DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<V, RW, F, true>,                             \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-      bd::bwd_data_kernel<V, RW, F, true><<<grid, bd::kThreads, smem, st>>>(P);                          \
-    } else {                                                                                             \
-      DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<V, RW, F, false>,                            \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-      bd::bwd_data_kernel<V, RW, F, false><<<grid, bd::kThreads, smem, st>>>(P);                         \
-    }                                                                                                    \
+#define DCN_LAUNCH_BD(V, RW, F, PW)                                                                       \
+  do {                                                                                                    \
+    if (bf) {                                                                                             \
+      DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<V, RW, F, true, PW>,                          \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+      bd::bwd_data_kernel<V, RW, F, true, PW><<<grid, bd::threads_of(V, PW), smem, st>>>(P);              \
+    } else {                                                                                              \
+      DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<V, RW, F, false, PW>,                         \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+      bd::bwd_data_kernel<V, RW, F, false, PW><<<grid, bd::threads_of(V, PW), smem, st>>>(P);             \
+    }                                                                                                     \
   } while (0)
   if (g.variant == DCN_VARIANT_TORCH) {
+    const bool slim = P.Rt == 2 && P.plan_cap <= bd::plan_max_of(2);  // Gt = 64: 2 plan warps are enough
     if (P.fuse_w) {
-      if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 16, true);
-      else DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32, true);
+      if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 16, true, 4);
+      else if (slim) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32, true, 2);
+      else DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32, true, 4);
     } else {
-      if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 16, false);
-      else DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32, false);
+      if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 16, false, 4);
+      else if (slim) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32, false, 2);
+      else DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32, false, 4);
     }
   } else {
-    if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 16, false);
-    else DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 32, false);
+    if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 16, false, 4);
+    else DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 32, false, 4);
   }
 #undef DCN_LAUNCH_BD
   DCN_KERNEL_CHECK("umma_bwd_data_kernel");
