@@ -20,7 +20,8 @@ namespace dcn {
 bool umma_wgrad_supported(const Geo& g, int operand);
 size_t umma_xt_bytes(const Geo& g, int operand);
 int umma_wgrad_any(const Geo& g, int operand, const void* xt, const float* off, const void* gout, float* gw,
-                   cudaStream_t st);
+                   uint8_t* gtiles, cudaStream_t st);
+size_t umma_wgrad_gtile_bytes(const Geo& g, int operand);
 bool umma_bwd_data_supported(const Geo& g, int operand);
 size_t umma_bwd_data_wtile_bytes(const Geo& g, int operand);
 bool umma_bwd_data_fuses_wgrad(const Geo& g, int operand);
@@ -44,11 +45,15 @@ bool umma_bwd_supported(const Geo& g, int operand) {
 }
 
 size_t umma_bwd_workspace(const Geo& g, int operand) {
-  // [xt] then either [gxt | Wm^T tiles | grad_out tiles] (tensor-path data gradient) or [sampling plan] (generic)
+  // [xt] then either [gxt | Wm^T tiles | grad_out tiles] (tensor-path data gradient) or [sampling plan]
+  // (generic); the unfused weight-gradient pass runs last and re-uses that region for its own staged
+  // grad_out tiles
   const size_t a = umma_xt_bytes(g, DCN_OPERAND_FP32) + umma_bwd_data_wtile_bytes(g, operand) +
                    umma_bwd_data_gtile_bytes(g, operand);
   const size_t b = operand == DCN_OPERAND_FP32 ? plan_bytes(g) : 0;
-  return umma_xt_bytes(g, operand) + (a > b ? a : b);
+  const size_t c = umma_wgrad_gtile_bytes(g, operand);
+  const size_t m = a > b ? a : b;
+  return umma_xt_bytes(g, operand) + (m > c ? m : c);
 }
 
 int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, const float* off, const void* wtv,
@@ -90,7 +95,8 @@ int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, cons
                             gb, st, SIMT_BWD_DATA | SIMT_BWD_BIAS)))
       return rc;
   }
-  return umma_wgrad_any(g, operand, xt, off, gout, gw, st);
+  // everything that lived in `rest` (gxt, tiles, plan) is dead by now
+  return umma_wgrad_any(g, operand, xt, off, gout, gw, rest, st);
 }
 
 }  // namespace dcn

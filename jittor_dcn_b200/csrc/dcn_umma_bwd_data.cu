@@ -28,6 +28,7 @@
 //                (gout_tiles_torch_kernel) pre-builds every tile's UMMA images instead; without the
 //                two converter warps the scatter warps get 88 registers.
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "dcn_umma.h"
@@ -76,6 +77,8 @@ struct Params {
   const void* gout;      // float or bfloat16
   const uint8_t* wtiles; // [cblocks][OB][hi|lo][ncols x 64] K-major SW128 images of Wm^T
   const uint8_t* gtiles; // Torch layout: [tile][OB][hi|lo][128 rows x 64 o] K-major SW128 images of grad_out
+  int row_v;             // staging kernel only: 0 = rows ordered (instance, channel) as this kernel wants them;
+                         // V = 4 / 8: the forward-kernel order (channel / V, instance, channel % V) for MODE_WGRAD
   float* goff;           // grad_offset accumulators (zeroed)
   float scale_iy, scale_ix;  // chain-rule factors of the coordinate normalisation (1 for DCNv1)
   int Gt, Rt, chunks, num_inst, num_tiles;  // backward tiling (rows = (instance, channel))
@@ -699,7 +702,8 @@ __global__ void __launch_bounds__(256) gout_tiles_torch_kernel(const __grid_cons
     split_pair(v[2], v[3], hi.y, lo.y);
     split_pair(v[4], v[5], hi.z, lo.z);
     split_pair(v[6], v[7], hi.w, lo.w);
-    const int m = il * Gt + i0 + i2;
+    const int ic = i0 + i2;
+    const int m = P.row_v ? (ic / P.row_v) * (P.row_v * P.Rt) + il * P.row_v + ic % P.row_v : il * Gt + ic;
     uint8_t* img = gtiles + ((size_t)tile * P.OB + ob) * NIMG * img_bytes + kmajor_sw128_off(m, (c_base + ck) * 8);
     *reinterpret_cast<uint4*>(img) = hi;
     if (NIMG == 2) *reinterpret_cast<uint4*>(img + img_bytes) = lo;
@@ -850,6 +854,45 @@ size_t umma_bwd_data_wtile_bytes(const Geo& g, int operand) {
   return align_up((size_t)P.cblocks * P.OB * P.w_stage, 1024);
 }
 
+// the staging pass of the grad_out operand (Torch layout); P needs g, t, Gt, Rt, OB, num_inst, num_tiles,
+// divR, divChunks, gout, row_v
+static int launch_gout_tiles(const bd::Params& P, bool bf, uint8_t* gtiles, cudaStream_t st) {
+  const dim3 grid((unsigned)(((size_t)P.num_tiles * P.Rt + bd::kGtInst - 1) / bd::kGtInst),
+                  (unsigned)((P.OB * 64 / bd::kGtOsub) * (P.Gt / bd::kGtCh)));
+  KernelScope scope("gout_tiles_kernel", st);
+  if (bf)
+    bd::gout_tiles_torch_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(P, gtiles);
+  else
+    bd::gout_tiles_torch_kernel<float><<<grid, 256, 0, st>>>(P, gtiles);
+  DCN_KERNEL_CHECK("gout_tiles_kernel");
+  return DCN_OK;
+}
+
+// grad_out tile images in the FORWARD kernel's row order, for its weight-gradient mode (MODE_WGRAD):
+// [tile][OB = ceil(O / 64)][hi | lo][128 rows x 64 o].  V = channels per gather item (4 fp32 / 8 bf16).
+size_t umma_wgrad_gtile_bytes(const Geo& g, int operand) {
+  Tiling t;
+  if (g.variant != DCN_VARIANT_TORCH || !make_tiling(g, &t)) return 0;
+  return align_up((size_t)t.num_tiles * ((g.O + 63) / 64) * (operand == DCN_OPERAND_BF16 ? 1 : 2) * bd::kGImg, 1024);
+}
+int launch_gout_tiles_fwd_order(const Geo& g, int operand, const void* gout, uint8_t* gtiles, cudaStream_t st) {
+  bd::Params P;
+  memset(&P, 0, sizeof(P));
+  P.g = g;
+  if (!make_tiling(g, &P.t)) return DCN_ERR_UNSUPPORTED;
+  P.Gt = P.t.Gt;
+  P.Rt = P.t.Rt;
+  P.chunks = P.t.chunks;
+  P.num_inst = P.t.num_inst;
+  P.num_tiles = P.t.num_tiles;
+  P.divR = P.t.divR;
+  P.divChunks = P.t.divChunks;
+  P.OB = (g.O + 63) / 64;
+  P.gout = gout;
+  P.row_v = operand == DCN_OPERAND_BF16 ? 8 : 4;
+  return launch_gout_tiles(P, operand == DCN_OPERAND_BF16, gtiles, st);
+}
+
 // staged grad_out operand images (Torch layout only)
 size_t umma_bwd_data_gtile_bytes(const Geo& g, int operand) {
   bd::Params P;
@@ -890,15 +933,10 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
   P.gout = gout;
   P.wtiles = wtiles;
   P.gtiles = gtiles;
+  P.row_v = 0;
   if (g.variant == DCN_VARIANT_TORCH) {
-    const dim3 grid((unsigned)(((size_t)P.num_tiles * P.Rt + bd::kGtInst - 1) / bd::kGtInst),
-                    (unsigned)((P.OB * 64 / bd::kGtOsub) * (P.Gt / bd::kGtCh)));
-    KernelScope scope("gout_tiles_kernel", st);
-    if (bf)
-      bd::gout_tiles_torch_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(P, gtiles);
-    else
-      bd::gout_tiles_torch_kernel<float><<<grid, 256, 0, st>>>(P, gtiles);
-    DCN_KERNEL_CHECK("gout_tiles_kernel");
+    int rc = launch_gout_tiles(P, bf, gtiles, st);
+    if (rc) return rc;
   }
   P.goff = goff;
   P.gw = gw;

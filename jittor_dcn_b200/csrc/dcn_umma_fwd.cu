@@ -57,6 +57,8 @@ struct FwdParams {
   float* out;
   // weight-gradient mode (MODE_WGRAD): gW[o, j] += sum_rows gout[row, o] * S[row, j]
   const void* gout;    // float or bfloat16
+  const uint8_t* gtiles;  // Torch layout: staged grad_out tile images [tile][OB][hi|lo][128 rows x 64 o] (rows in this kernel's order)
+  int g_OB;               // ceil(O / 64) images per tile
   float* gw;
   int nslices, nchunks, kb_per_slice;  // CTA = (K slice, chunk of row tiles)
   int o_blocks;                        // ceil(O / 128) accumulators
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       mbar_init(&tempty[a], kEpiWarps);
       mbar_init(&pfull[a], kPlanWarps);
       mbar_init(&pempty[a], kProdWarps);
-      mbar_init(&afull[a], kEpiWarps);
+      mbar_init(&afull[a], (MODE == MODE_WGRAD && VARIANT == DCN_VARIANT_TORCH) ? 1 : kEpiWarps);
       mbar_init(&aempty[a], 1);
     }
     fence_barrier_init();
@@ -236,6 +238,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
                  "r"(P.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (MODE == MODE_WGRAD && VARIANT == DCN_VARIANT_TORCH && (P.g_OB & 1)) {
+    // O is not a multiple of 128: the upper 64-o half of the last M = 128 operand stays zero
+    for (int ab = 0; ab < P.n_gbuf; ++ab) {
+      uint8_t* z = gbuf_base + (size_t)ab * gbuf_bytes + (size_t)P.g_OB * NIMG * kATile;
+      for (uint32_t i = tid * 16; i < NIMG * kATile; i += kFwdThreads * 16)
+        *reinterpret_cast<uint4*>(z + i) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -341,6 +352,23 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     int ab = 0;
     uint32_t aphase = 0;
     for (int tile = tile0; tile < t.num_tiles; tile = next_tile(tile)) {
+      if (VARIANT == DCN_VARIANT_TORCH) {
+        // Torch-layout rows are R floats apart in gout: the tile's images were staged by
+        // gout_tiles_torch_kernel (in this kernel's row order); one bulk copy fetches them
+        if (tid == 0) {
+          const uint32_t bytes = (uint32_t)P.g_OB * NIMG * kATile;
+          mbar_wait_relaxed(&aempty[ab], aphase ^ 1);
+          mbar_arrive_expect_tx(&afull[ab], bytes);
+          bulk_g2s(gbuf_base + (size_t)ab * gbuf_bytes, P.gtiles + (size_t)tile * bytes, bytes, &afull[ab]);
+        }
+        if (P.n_gbuf == 2) {
+          ab ^= 1;
+          if (ab == 0) aphase ^= 1;
+        } else {
+          aphase ^= 1;
+        }
+        continue;
+      }
       mbar_wait_relaxed(&aempty[ab], aphase ^ 1);
       uint8_t* gb = gbuf_base + (size_t)ab * gbuf_bytes;
       // items: (o, group of 4 consecutive tile rows); lanes run along the row groups
@@ -348,19 +376,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         const int o = item >> 5, mq = item & 31, m = mq * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (o < O) {
-          if (VARIANT == DCN_VARIANT_TORCH) {
-            // rows m..m+3 = 4 consecutive channels of class instance il (dcn_umma_common.cuh:Tiling)
-            const int grp = m / (V * t.Rt), il = (m / V) % t.Rt, ch0 = m % V;
-            const TileRowInfo ri = decode_inst(t, tile * t.Rt + il);
-            if (ri.valid) {
-              const XT* src = reinterpret_cast<const XT*>(P.gout) + ((size_t)ri.b * O + o) * g.HW + ri.r0 +
-                              (size_t)(ri.chunk * t.Gt + V * grp + ch0) * t.R;
-              v.x = (float)__ldg(src);
-              v.y = (float)__ldg(src + t.R);
-              v.z = (float)__ldg(src + 2 * (size_t)t.R);
-              v.w = (float)__ldg(src + 3 * (size_t)t.R);
-            }
-          } else {
+          {
             const int b = tile / t.pix_blocks, p = (tile - b * t.pix_blocks) * 128 + m;
             const XT* src = reinterpret_cast<const XT*>(P.gout) + ((size_t)b * O + o) * g.HW + p;
             if (!BF && p + 3 < g.HW && (g.HW & 3) == 0) {
@@ -468,7 +484,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     //          row half h at +1024;
     //   Jittor image (columns contiguous per row) = MN-major B, 8-row groups 1024 B apart.
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, 64, false, VARIANT != DCN_VARIANT_TORCH);
+      // Torch: A = staged grad_out images [row][64 o] read MN-major (o contiguous, 64-o atoms = consecutive
+      // images), B = sample image K-major; Jittor: A = converted [o][64 rows] K-major, B MN-major
+      const uint32_t idesc = make_idesc_bf16(128, 64, VARIANT == DCN_VARIANT_TORCH, VARIANT != DCN_VARIANT_TORCH);
       const int ncols = (kb1 - kb0) * 64;
       int s = 0, ab = 0;
       uint32_t phase = 0, aphase = 0;
@@ -493,10 +511,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
               dsl = make_sdesc_sw128(s_lo + ks * 2048, 1024, 1024);
             }
             for (int ob = 0; ob < P.o_blocks; ++ob) {
-              const uint32_t g_hi = gb + h * NIMG * P.g_img + ob * (128 * 128) + k4 * 32;
-              const uint32_t g_lo = g_hi + P.g_img;
-              const uint64_t dgh = make_sdesc_sw128(g_hi, 16, 1024);
-              const uint64_t dgl = make_sdesc_sw128(g_lo, 16, 1024);
+              uint64_t dgh, dgl;
+              if (VARIANT == DCN_VARIANT_TORCH) {
+                const uint32_t g_hi = gb + (uint32_t)(2 * ob) * NIMG * kATile + ks * 2048;
+                dgh = make_sdesc_sw128(g_hi, NIMG * kATile, 1024);
+                dgl = make_sdesc_sw128(g_hi + kATile, NIMG * kATile, 1024);
+              } else {
+                const uint32_t g_hi = gb + h * NIMG * P.g_img + ob * (128 * 128) + k4 * 32;
+                dgh = make_sdesc_sw128(g_hi, 16, 1024);
+                dgl = make_sdesc_sw128(g_hi + P.g_img, 16, 1024);
+              }
               const uint32_t d_tmem = tmem_base + (uint32_t)(ob * ncols + (kb - kb0) * 64);
               umma_bf16(d_tmem, dgh, dsh, idesc, (first_tile && ks == 0) ? 0u : 1u);
               if (!BF) {
@@ -844,6 +868,8 @@ static void common_params(const Geo& g, FwdParams& P) {
   P.plan_cap = (n_ent + 255) / 256 * 256;
   P.gout = nullptr;
   P.gw = nullptr;
+  P.gtiles = nullptr;
+  P.g_OB = 0;
   P.nslices = P.nchunks = P.kb_per_slice = 1;
   P.o_blocks = 1;
   P.n_gbuf = 0;
@@ -944,8 +970,12 @@ int umma_forward_any(const Geo& g, int operand, const void* x, const float* off,
 
 // grad_weight[O, K] (zeroed here) = sum over all rows of gout^T * S, S re-sampled by the same
 // plan / gather warps as the forward pass.  xt = channels-last staging copy (already built).
+size_t umma_wgrad_gtile_bytes(const Geo& g, int operand);
+int launch_gout_tiles_fwd_order(const Geo& g, int operand, const void* gout, uint8_t* gtiles, cudaStream_t st);
+
+// gtiles: scratch of umma_wgrad_gtile_bytes() for the staged grad_out tile images (Torch layout; unused otherwise)
 int umma_wgrad_any(const Geo& g, int operand, const void* xt, const float* off, const void* gout, float* gw,
-                   cudaStream_t st) {
+                   uint8_t* gtiles, cudaStream_t st) {
   FwdParams P;
   P.g = g;
   if (!make_tiling(g, &P.t)) {
@@ -962,6 +992,12 @@ int umma_wgrad_any(const Geo& g, int operand, const void* xt, const float* off, 
   P.out = nullptr;
   P.gout = gout;
   P.gw = gw;
+  P.gtiles = gtiles;
+  P.g_OB = (g.O + 63) / 64;
+  if (g.variant == DCN_VARIANT_TORCH) {
+    int rc = launch_gout_tiles_fwd_order(g, operand, gout, gtiles, st);
+    if (rc) return rc;
+  }
   P.o_blocks = (g.O + 127) / 128;
   P.g_img = (uint32_t)P.o_blocks * 128 * 128;
   const int kb_max = 8 / P.o_blocks;  // 512 TMEM columns
