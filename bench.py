@@ -473,6 +473,16 @@ def main():
     roofline, kernels = None, {}
     for name, (cnt, tot_ms) in prof.items():
         kernels[name] = {"launches": cnt, "avg_ms": tot_ms / max(cnt, 1), "share": tot_ms / max(elapsed_ms, 1e-9)}
+    # the layout-staging passes are pure data movement: report them against the HBM copy peak too
+    eb = x.element_size()
+    stage_bytes = {"nchw_to_nhwc_kernel": 2 * x.numel() * eb,                    # read x, write the framed copy
+                   "nhwc_to_nchw_kernel": 2 * x.numel() * 4,                     # read grad copy, write grad_x
+                   "gout_tiles_kernel": gout.numel() * eb + gout.numel() * (4 if eb == 4 else 2),
+                   "bias_grad_kernel": gout.numel() * eb}
+    for name, nbytes in stage_bytes.items():
+        if name in kernels and kernels[name]["avg_ms"] > 0:
+            gbs = nbytes / (kernels[name]["avg_ms"] * 1e-3) / 1e9
+            kernels[name].update({"bytes": nbytes, "GB/s": gbs, "hbm_frac": gbs / pk["hbm"]})
     ranked = sorted((n for n in prof if n in KERNEL_ROLE), key=lambda n: -prof[n][1])
     if ranked:
         top = ranked[0]
@@ -592,6 +602,8 @@ def main():
                        "l2": ("L2 flushed (512 MB write) between timed iterations" if needs_flush else
                               "inputs (x %.0f MB + gout %.0f MB) exceed the 126 MB L2; no flush needed"
                               % (x.numel() * x.element_size() / 1e6, gout.numel() * gout.element_size() / 1e6)),
+                       "staging": ("backward reuses the forward pass's staged copy of x (DCN_FLAG_XT_STAGED, one "
+                                   "scratch buffer for both phases)" if ws is not None else "re-staged per phase"),
                        "allreduce": allreduce_kind, "parallelism": f"dp{world}"},
             "roofline": roofline, "kernels": kernels, "fwd_only": fwd_only, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
