@@ -93,6 +93,7 @@ struct Params {
   // sample S = sum_k w_k v_k they already hold the corners of, store it as a bf16 hi/lo B
   // operand, and a second accumulator set collects gW[o, j] += g^T S over all tiles of the CTA
   int fuse_w;            // 0 / 1
+  int o_cols;            // Jittor layout, fused: TMEM columns of one gW accumulator block = O rounded up to 16
   float* gw;             // [O, K], zeroed
   int nslices, nchunks, cb_per_slice;  // CTA = (slice of column blocks, chunk of tiles)
   int g_imgs;            // grad_out images the MMAs address per tile: OB, or 2 when fused (M = 128 of the o axis)
@@ -428,22 +429,44 @@ __global__ void __launch_bounds__(threads_of(VARIANT, PW), 1) bwd_data_kernel(co
       // ---- one-shot epilogue of the weight gradient: accumulators -> gW (red.global.add)
       mbar_wait_relaxed(dfull, 0);
       tc_fence_after();
-      const int o = quarter * 32 + lane;
-      const int wcols = (cb1 - cb0) * ncols, per_part = (wcols + 3) >> 2;
-      const uint32_t taddr = d2_base + ((uint32_t)(quarter * 32) << 16);
-      for (int c0 = part * per_part; c0 < min(wcols, (part + 1) * per_part); c0 += 8) {
-        uint32_t raw[8];
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]), "=r"(raw[4]), "=r"(raw[5]),
-                       "=r"(raw[6]), "=r"(raw[7])
-                     : "r"(taddr + c0)
-                     : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (o < g.O) {
+      if (VARIANT == DCN_VARIANT_TORCH) {
+        const int o = quarter * 32 + lane;
+        const int wcols = (cb1 - cb0) * ncols, per_part = (wcols + 3) >> 2;
+        const uint32_t taddr = d2_base + ((uint32_t)(quarter * 32) << 16);
+        for (int c0 = part * per_part; c0 < min(wcols, (part + 1) * per_part); c0 += 8) {
+          uint32_t raw[8];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]), "=r"(raw[4]), "=r"(raw[5]),
+                         "=r"(raw[6]), "=r"(raw[7])
+                       : "r"(taddr + c0)
+                       : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (o < g.O) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int j = cb0 * ncols + c0 + u;
-            if (j < g.K) atomicAdd(P.gw + (size_t)o * g.K + j, __uint_as_float(raw[u]));
+            for (int u = 0; u < 8; ++u) {
+              const int j = cb0 * ncols + c0 + u;
+              if (j < g.K) atomicAdd(P.gw + (size_t)o * g.K + j, __uint_as_float(raw[u]));
+            }
+          }
+        }
+      } else {
+        // Jittor layout: lane = column j of a lane block, TMEM columns = output channels
+        for (int cb = cb0; cb < cb1; ++cb) {
+          const int j = cb * 128 + m;
+          const uint32_t taddr = d2_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((cb - cb0) * P.o_cols);
+          for (int c0 = part * 8; c0 < P.o_cols; c0 += 32) {
+            uint32_t raw[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]), "=r"(raw[4]), "=r"(raw[5]),
+                           "=r"(raw[6]), "=r"(raw[7])
+                         : "r"(taddr + c0)
+                         : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (j < g.K) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (c0 + u < g.O) atomicAdd(P.gw + wt_index(g, c0 + u, j), __uint_as_float(raw[u]));
+            }
           }
         }
       }
@@ -459,25 +482,47 @@ __global__ void __launch_bounds__(threads_of(VARIANT, PW), 1) bwd_data_kernel(co
       bool first_tile = true;
       // gW[o, cols of block] += g^T[o, 128 rows] * S[128 rows, cols]; A = the resident grad_out
       // images read MN-major (o contiguous, 64-o atoms = consecutive images), B = sample operand
+      const uint32_t idesc_wj = make_idesc_bf16(128, P.o_cols > 0 ? P.o_cols : 16, false, true);
       auto wgrad_mmas = [&](int cb, bool first) {
         mbar_wait_relaxed(&sfull[sb], sphase, 32);
         tc_fence_after();
-        // 64-o atoms of the MN-major A operand: this buffer's image, then its second image or — O <= 64 —
-        // the shared zero image
         const uint32_t g_hi = smem_u32(gtile) + (uint32_t)gb * g_buf, g_lo = g_hi + P.g_img;
-        const uint32_t g_lbo = P.OB >= 2 ? NIMG * P.g_img : g_zero_off - (uint32_t)gb * g_buf;
         const uint32_t sbase = smem_u32(sbuf + (size_t)sb * s_buf);
-        const uint32_t d_tmem = d2_base + (uint32_t)((cb - cb0) * ncols);
+        if (VARIANT == DCN_VARIANT_TORCH) {
+          // gW[o, cols of block] += g^T[o, 128 rows] * S[128 rows, cols]: A = the resident grad_out images read
+          // MN-major (o contiguous; 64-o atoms = this buffer's image, then its second image or — O <= 64 — the
+          // shared zero image), B = sample operand read MN-major
+          const uint32_t g_lbo = P.OB >= 2 ? NIMG * P.g_img : g_zero_off - (uint32_t)gb * g_buf;
+          const uint32_t d_tmem = d2_base + (uint32_t)((cb - cb0) * ncols);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {  // 8 steps of 16 tile rows
-          const uint64_t dgh = make_sdesc_sw128(g_hi + ks * 2048, g_lbo, 1024);
-          const uint64_t dgl = make_sdesc_sw128(g_lo + ks * 2048, g_lbo, 1024);
-          const uint64_t dsh = make_sdesc_sw128(sbase + ks * 2048, 1024, 1024);
-          const uint64_t dsl = make_sdesc_sw128(sbase + s_img + ks * 2048, 1024, 1024);
-          umma_bf16(d_tmem, dgh, dsh, idesc_w, (first && ks == 0) ? 0u : 1u);
-          if (!BF) {
-            umma_bf16(d_tmem, dgh, dsl, idesc_w, 1u);
-            umma_bf16(d_tmem, dgl, dsh, idesc_w, 1u);
+          for (int ks = 0; ks < 8; ++ks) {  // 8 steps of 16 tile rows
+            const uint64_t dgh = make_sdesc_sw128(g_hi + ks * 2048, g_lbo, 1024);
+            const uint64_t dgl = make_sdesc_sw128(g_lo + ks * 2048, g_lbo, 1024);
+            const uint64_t dsh = make_sdesc_sw128(sbase + ks * 2048, 1024, 1024);
+            const uint64_t dsl = make_sdesc_sw128(sbase + s_img + ks * 2048, 1024, 1024);
+            umma_bf16(d_tmem, dgh, dsh, idesc_w, (first && ks == 0) ? 0u : 1u);
+            if (!BF) {
+              umma_bf16(d_tmem, dgh, dsl, idesc_w, 1u);
+              umma_bf16(d_tmem, dgl, dsh, idesc_w, 1u);
+            }
+          }
+        } else {
+          // Jittor layout: gW^T[j of this lane block, o] += S^T[j, pixels] * g[pixels, o]: A = the sample operand,
+          // the same image read K-major (K = the tile's 64 pixels), B = the resident grad_out pixels read MN-major
+          // (o contiguous; 64-o atoms = consecutive images): no padded operand rows at all
+          const uint32_t g_lbo = NIMG * P.g_img;
+          const uint32_t d_tmem = d2_base + (uint32_t)((cb - cb0) * P.o_cols);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {  // 4 steps of 16 pixels
+            const uint64_t dsh = make_sdesc_sw128(sbase + k4 * 32, 16, 1024);
+            const uint64_t dsl = make_sdesc_sw128(sbase + s_img + k4 * 32, 16, 1024);
+            const uint64_t dgh = make_sdesc_sw128(g_hi + k4 * 2048, g_lbo, 1024);
+            const uint64_t dgl = make_sdesc_sw128(g_lo + k4 * 2048, g_lbo, 1024);
+            umma_bf16(d_tmem, dsh, dgh, idesc_wj, (first && k4 == 0) ? 0u : 1u);
+            if (!BF) {
+              umma_bf16(d_tmem, dsh, dgl, idesc_wj, 1u);
+              umma_bf16(d_tmem, dsl, dgh, idesc_wj, 1u);
+            }
           }
         }
         umma_commit(&sempty[sb]);
@@ -830,6 +875,42 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
   // Jittor: a lane block of 128 columns must hold whole taps
   if (!(g.C % 128 == 0 || g.C == 64 || g.C == 32 || g.C == 16)) return false;
   const int taps = g.C >= 128 ? 1 : 128 / g.C;
+  P->o_cols = 0;
+  // fused weight gradient: 64-pixel tiles, gW^T accumulator blocks of O columns next to the 2 gA buffers
+  if (allow_fuse && g.O <= 128) {
+    const int ncols = 64, o_cols = (g.O + 15) / 16 * 16;
+    const size_t plan = 2 * (size_t)taps * ncols * sizeof(bd::ScatEntry);
+    const size_t real = (size_t)P->OB * nimg * (ncols * 128);
+    const size_t rest = 2 * (size_t)(nimg * 128 * 128) + 2 * nimg * (size_t)(128 * 128) + plan + 256 + 1024;
+    int max_cb = (512 - 2 * ncols) / o_cols;
+    if (max_cb > 8) max_cb = 8;
+    if (taps * ncols <= bd::plan_max_of(4) && real + rest <= 227 * 1024 && max_cb >= 1) {
+      P->fuse_w = 1;
+      P->o_cols = o_cols;
+      P->g_nbuf = (2 * real + rest <= 227 * 1024) ? 2 : 1;
+      P->ncols = ncols;
+      P->pix_blocks = (g.HW + ncols - 1) / ncols;
+      P->num_tiles = g.B * P->pix_blocks;
+      P->cblocks = (g.K + 127) / 128;
+      P->plan_cap = taps * ncols;
+      P->g_img = (uint32_t)ncols * 128;
+      P->w_stage = (uint32_t)nimg * 128 * 128;
+      P->tmem_cols = 512;
+      const int ns_min = (P->cblocks + max_cb - 1) / max_cb;
+      double best = 1e30;
+      for (int ns = ns_min; ns <= ns_min + 2 && ns <= P->cblocks; ++ns) {
+        const int cbp = (P->cblocks + ns - 1) / ns;
+        const int ns_eff = (P->cblocks + cbp - 1) / cbp;
+        const double waste = (double)ns_eff * cbp / P->cblocks * 148.0 / (ns_eff * (148 / ns_eff));
+        if (waste < best - 1e-9) {
+          best = waste;
+          P->nslices = ns_eff;
+          P->cb_per_slice = cbp;
+        }
+      }
+      return true;
+    }
+  }
   for (int ncols : {128, 64}) {
     const size_t plan = 2 * (size_t)taps * ncols * sizeof(bd::ScatEntry);
     const size_t real = (size_t)P->OB * nimg * (ncols * 128);
@@ -1008,6 +1089,9 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
       else if (slim) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32, false, 2);
       else DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32, false, 4);
     }
+  } else if (P.fuse_w) {
+    if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 16, true, 4);
+    else DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 32, true, 4);
   } else {
     if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 16, false, 4);
     else DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 32, false, 4);
