@@ -405,16 +405,18 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(Geo g, int b_per_block, 
   const int o = blockIdx.x, b0 = blockIdx.y * b_per_block, b1 = min(g.B, b0 + b_per_block);
   float s = 0.f;
   const bool vec = sizeof(T) == 4 && (g.HW & 3) == 0;
-  for (int b = b0; b < b1; ++b) {
-    const T* row = gout + ((size_t)b * g.O + o) * g.HW;
+  // the (batch element, pixel) pairs of this block's slice are walked as ONE flat index space, so that small
+  // planes (8 x 8 pixels in the detector's last layer) keep all 256 threads busy
+  const int per_b = vec ? (g.HW >> 2) : g.HW, total = (b1 - b0) * per_b;
+  const size_t b_stride = (size_t)g.O * g.HW;
+  const T* base = gout + ((size_t)b0 * g.O + o) * g.HW;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int b = i / per_b, r = i - b * per_b;
     if (vec) {
-      const float4* r4 = reinterpret_cast<const float4*>(row);
-      for (int r = threadIdx.x; r < (g.HW >> 2); r += blockDim.x) {
-        const float4 v = __ldg(r4 + r);
-        s += (v.x + v.y) + (v.z + v.w);
-      }
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)b * b_stride) + r);
+      s += (v.x + v.y) + (v.z + v.w);
     } else {
-      for (int r = threadIdx.x; r < g.HW; r += blockDim.x) s += (float)row[r];
+      s += (float)base[(size_t)b * b_stride + r];
     }
   }
   __shared__ float red[8];

@@ -18,15 +18,14 @@
 //                 TMEM columns are 128 consecutive output pixels.  Streamed operand A = Wm^T,
 //                 resident operand B = converted grad_out pixels.
 //
-// Warp roles (704 threads Torch layout / 768 Jittor layout, 1 CTA / SM, persistent over row tiles):
+// Warp roles (640 or 704 threads, 1 CTA / SM, persistent over row tiles):
 //   warps  0-15  scatter / coord-grad epilogue (quarter = w % 4 of the TMEM lanes, w / 4 = column part)
-//   warp   16    MMA issuer          warp 17  loader: lane 0 streams the Wm^T tiles, lane 1 (Torch
-//                layout) the staged grad_out tiles (cp.async.bulk)
-//   warps 18-21  plan: offsets -> bit-exact coordinate chain -> scatter entries (2-deep ring)
-//   warps 22-23  (Jittor layout only) grad_out converter fp32 -> bf16 hi/lo, coalesced along the
-//                pixels.  Torch-layout rows are R floats apart, so a staging kernel
-//                (gout_tiles_torch_kernel) pre-builds every tile's UMMA images instead; without the
-//                two converter warps the scatter warps get 88 registers.
+//   warp   16    MMA issuer          warp 17  loader: lane 0 streams the Wm^T tiles, lane 1 the staged
+//                grad_out tiles (cp.async.bulk)
+//   warps 18-19 / 18-21  plan: offsets -> bit-exact coordinate chain -> scatter entries (2-deep ring)
+// The grad_out operand is never converted here: staging kernels (gout_tiles_torch_kernel — Torch-layout
+// rows are R floats apart — and gout_tiles_pix_kernel for the pixel-row layouts) pre-build every tile's
+// UMMA images once per backward pass.
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -40,18 +39,14 @@ using namespace ptx;
 
 namespace bd {
 
-constexpr int kScatWarps = 16, kConvWarps = 2;
+constexpr int kScatWarps = 16;
 constexpr int kMmaWarp = kScatWarps, kLoadWarp = kScatWarps + 1;
 constexpr int kFirstPlanWarp = kScatWarps + 2;
 // Role layout by the number of plan warps PW:
-//   Torch layout, Gt = 64 (Rt = 2, <= 256 entries per block): PW = 2 and no converter warps = 20 warps, i.e.
-//                 5 per SM sub-partition and 96 registers per thread for the scatter loop;
-//   Torch layout, Rt >= 4 (more sampling points per block): PW = 4, 22 warps, 80 registers;
-//   Jittor layout: PW = 4 plus the 2 converter warps, 24 warps, 80 registers.
-__host__ __device__ constexpr int first_conv_warp_of(int pw) { return kFirstPlanWarp + pw; }
-__host__ __device__ constexpr int threads_of(int variant, int pw) {
-  return (first_conv_warp_of(pw) + (variant == DCN_VARIANT_TORCH ? 0 : kConvWarps)) * 32;
-}
+//   <= 128 plan entries per block (Torch layout with Gt = 64, Jittor layout with C >= 64): PW = 2 = 20 warps,
+//                 i.e. 5 per SM sub-partition and 96 registers per thread for the scatter loop;
+//   more sampling points per block: PW = 4, 22 warps, 80 registers.
+__host__ __device__ constexpr int threads_of(int pw) { return (kFirstPlanWarp + pw) * 32; }
 constexpr int kPlanPerThread = 8;
 __host__ __device__ constexpr int plan_max_of(int pw) { return pw * 32 * kPlanPerThread; }
 constexpr uint32_t kGImg = 128 * 64 * 2;                 // one bf16 image of a grad_out K block
@@ -182,7 +177,7 @@ __device__ __forceinline__ ScatEntry plan_finish(const Geo& g, const PlanWork& p
 // RW = lanes that share one sampling point (32, or 16 when only 16 channels do)
 // BF  = bf16 operand mode: x / weight / grad_out are bfloat16, one image per operand, one MMA per K step
 template <int VARIANT, int RW, bool FUSE, bool BF, int PW>
-__global__ void __launch_bounds__(threads_of(VARIANT, PW), 1) bwd_data_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __grid_constant__ Params P) {
   constexpr int NIMG = BF ? 1 : 2;
   typedef typename std::conditional<BF, __nv_bfloat16, float>::type XT;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -226,7 +221,7 @@ __global__ void __launch_bounds__(threads_of(VARIANT, PW), 1) bwd_data_kernel(co
       mbar_init(&pempty[a], kScatWarps);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&gfull[a], VARIANT == DCN_VARIANT_TORCH ? 1 : kConvWarps);
+      mbar_init(&gfull[a], 1);
       mbar_init(&gempty[a], 1);
       mbar_init(&sfull[a], kScatWarps);
       mbar_init(&sempty[a], 1);
@@ -244,7 +239,7 @@ __global__ void __launch_bounds__(threads_of(VARIANT, PW), 1) bwd_data_kernel(co
   if (FUSE) {
     // images beyond OB (the o >= 64*OB half of the M = 128 weight-gradient MMA) stay zero
     const uint32_t zero_end = g_zero_off + (uint32_t)(P.g_imgs - P.OB) * NIMG * P.g_img;
-    for (uint32_t i = g_zero_off + tid * 16; i < zero_end; i += threads_of(VARIANT, PW) * 16)
+    for (uint32_t i = g_zero_off + tid * 16; i < zero_end; i += threads_of(PW) * 16)
       *reinterpret_cast<uint4*>(gtile + i) = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
@@ -596,58 +591,24 @@ __global__ void __launch_bounds__(threads_of(VARIANT, PW), 1) bwd_data_kernel(co
             if (s == 0) phase ^= 1;
           }
       }
-    } else if (VARIANT == DCN_VARIANT_TORCH && lane == 1) {
-      // the tile's grad_out images were staged by gout_tiles_torch_kernel: one bulk copy per tile
+    } else if (lane == 1) {
+      // the tile's grad_out operand images were staged by gout_tiles_*_kernel: bulk copies, no conversion here
       uint32_t gphase = 0;
       int gb = 0;
       for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
         mbar_wait_relaxed(&gempty[gb], gphase ^ 1, 64);
         mbar_arrive_expect_tx(&gfull[gb], g_buf);
-        bulk_g2s(gtile + (size_t)gb * g_buf, P.gtiles + (size_t)tile * g_buf, g_buf, &gfull[gb]);
-        if (++gb == P.g_nbuf) {
-          gb = 0;
-          gphase ^= 1;
+        if (VARIANT == DCN_VARIANT_TORCH || ncols == 128) {
+          // the tile's images are contiguous: one copy
+          bulk_g2s(gtile + (size_t)gb * g_buf, P.gtiles + (size_t)tile * g_buf, g_buf, &gfull[gb]);
+        } else {
+          // Jittor layout, 64-pixel tiles: one half (64 rows = 8 KB) of every 128-pixel image
+          const int b = tile / P.pix_blocks, pblk = tile - b * P.pix_blocks;
+          const int pb128 = (g.HW + 127) / 128;
+          const uint8_t* src = P.gtiles + ((size_t)(b * pb128 + (pblk >> 1)) * P.OB * NIMG) * kGImg + (pblk & 1) * (kGImg / 2);
+          for (int i = 0; i < P.OB * NIMG; ++i)
+            bulk_g2s(gtile + (size_t)gb * g_buf + (size_t)i * P.g_img, src + (size_t)i * kGImg, P.g_img, &gfull[gb]);
         }
-      }
-    }
-  } else if (warp >= first_conv_warp_of(PW)) {
-    // ================================================================ grad_out converter (Jittor layout only)
-    // A operand of GEMM-1: g[row m, o] = gout[b, o, r0 + (chunk*Gt + i_lo)*R], K-major, per 64 o's
-    const int ct = tid - first_conv_warp_of(PW) * 32;  // 0..63
-    uint32_t gphase = 0;
-    int gb = 0;
-    {
-      for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
-        mbar_wait_relaxed(&gempty[gb], gphase ^ 1, 64);
-        uint8_t* gdst = gtile + (size_t)gb * g_buf;
-        const int groups = P.OB * 8;  // groups of 8 output channels
-        const int rows = ncols;       // rows of the resident operand: the tile's pixels
-        for (int item = ct; item < rows * groups; item += kConvWarps * 32) {
-          const int mm = item % rows, og = item / rows;  // lanes run along the pixels
-          float v[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = 0.f;
-          const XT* gsrc = reinterpret_cast<const XT*>(P.gout);
-          const int b = tile / P.pix_blocks, p = (tile - b * P.pix_blocks) * ncols + mm;
-          if (p < g.HW) {
-            const XT* src = gsrc + ((size_t)b * g.O + og * 8) * g.HW + p;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (og * 8 + k < g.O) v[k] = (float)__ldg(src + (size_t)k * g.HW);
-          }
-          uint4 hi, lo;
-          split_pair(v[0], v[1], hi.x, lo.x);
-          split_pair(v[2], v[3], hi.y, lo.y);
-          split_pair(v[4], v[5], hi.z, lo.z);
-          split_pair(v[6], v[7], hi.w, lo.w);
-          uint8_t* img = gdst + (size_t)(og >> 3) * NIMG * P.g_img;
-          const uint32_t so = kmajor_sw128_off(mm, (og & 7) * 8);
-          *reinterpret_cast<uint4*>(img + so) = hi;
-          if (!BF) *reinterpret_cast<uint4*>(img + P.g_img + so) = lo;
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&gfull[gb]);
         if (++gb == P.g_nbuf) {
           gb = 0;
           gphase ^= 1;
@@ -764,6 +725,45 @@ __global__ void __launch_bounds__(256) gout_tiles_torch_kernel(const __grid_cons
     uint8_t* img = gtiles + ((size_t)tile * P.OB + ob) * NIMG * img_bytes + kmajor_sw128_off(m, (c_base + ck) * 8);
     *reinterpret_cast<uint4*>(img) = hi;
     if (NIMG == 2) *reinterpret_cast<uint4*>(img + img_bytes) = lo;
+  }
+}
+
+// Pixel-row layouts (Jittor / DCNv1): operand row = output pixel.  gout[b][o][p] -> images
+//   gtiles[b][pixel block of 128][ob][hi | lo][128 pixels x 64 o]  bf16, K-major, 128-byte swizzle,
+// i.e. a transposition (pixels are contiguous in gout, output channels in the image).  A 64-pixel tile of
+// the data-gradient kernel is one half (64 rows = 8 KB) of an image.  Block = 128 pixels x 64 output channels.
+template <typename T>
+__global__ void __launch_bounds__(256) gout_tiles_pix_kernel(Geo g, int OB, const T* __restrict__ gout,
+                                                             uint8_t* __restrict__ gtiles) {
+  constexpr int NIMG = sizeof(T) == 2 ? 1 : 2;
+  __shared__ float tile[64][129];
+  const int pb = blockIdx.x, ob = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, px = tid & 127, p = pb * 128 + px;
+  const T* src = gout + ((size_t)b * g.O + ob * 64) * g.HW + p;
+#pragma unroll 8
+  for (int it = 0; it < 32; ++it) {
+    const int ol = (tid >> 7) + 2 * it;
+    float v = 0.f;
+    if (p < g.HW && ob * 64 + ol < g.O) v = (float)__ldg(src + (size_t)ol * g.HW);
+    tile[ol][px] = v;
+  }
+  __syncthreads();
+  const uint32_t img_bytes = 128u * 128u;
+  uint8_t* img = gtiles + (((size_t)b * gridDim.x + pb) * OB + ob) * NIMG * img_bytes;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int it = tid + 256 * k, ck = it & 7, row = it >> 3;  // lanes: 8 chunks x 4 pixel rows
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = tile[ck * 8 + q][row];
+    uint4 hi, lo;
+    split_pair(v[0], v[1], hi.x, lo.x);
+    split_pair(v[2], v[3], hi.y, lo.y);
+    split_pair(v[4], v[5], hi.z, lo.z);
+    split_pair(v[6], v[7], hi.w, lo.w);
+    const uint32_t so = kmajor_sw128_off(row, ck * 8);
+    *reinterpret_cast<uint4*>(img + so) = hi;
+    if (NIMG == 2) *reinterpret_cast<uint4*>(img + img_bytes + so) = lo;
   }
 }
 
@@ -972,14 +972,33 @@ static int launch_gout_tiles(const bd::Params& P, bool bf, uint8_t* gtiles, cuda
   return DCN_OK;
 }
 
+// pixel-row layouts: [b][ceil(HW / 128)][OB][hi | lo][128 x 64] images (see gout_tiles_pix_kernel)
+static size_t gtile_pix_bytes(const Geo& g, int operand) {
+  return align_up((size_t)g.B * ((g.HW + 127) / 128) * ((g.O + 63) / 64) * (operand == DCN_OPERAND_BF16 ? 1 : 2) *
+                      bd::kGImg, 1024);
+}
+int launch_gout_tiles_pix(const Geo& g, int operand, const void* gout, uint8_t* gtiles, cudaStream_t st) {
+  const int OB = (g.O + 63) / 64;
+  const dim3 grid((unsigned)((g.HW + 127) / 128), (unsigned)OB, (unsigned)g.B);
+  KernelScope scope("gout_tiles_kernel", st);
+  if (operand == DCN_OPERAND_BF16)
+    bd::gout_tiles_pix_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(g, OB, (const __nv_bfloat16*)gout, gtiles);
+  else
+    bd::gout_tiles_pix_kernel<float><<<grid, 256, 0, st>>>(g, OB, (const float*)gout, gtiles);
+  DCN_KERNEL_CHECK("gout_tiles_kernel");
+  return DCN_OK;
+}
+
 // grad_out tile images in the FORWARD kernel's row order, for its weight-gradient mode (MODE_WGRAD):
 // [tile][OB = ceil(O / 64)][hi | lo][128 rows x 64 o].  V = channels per gather item (4 fp32 / 8 bf16).
 size_t umma_wgrad_gtile_bytes(const Geo& g, int operand) {
   Tiling t;
-  if (g.variant != DCN_VARIANT_TORCH || !make_tiling(g, &t)) return 0;
+  if (!make_tiling(g, &t)) return 0;
+  if (g.variant != DCN_VARIANT_TORCH) return gtile_pix_bytes(g, operand);
   return align_up((size_t)t.num_tiles * ((g.O + 63) / 64) * (operand == DCN_OPERAND_BF16 ? 1 : 2) * bd::kGImg, 1024);
 }
 int launch_gout_tiles_fwd_order(const Geo& g, int operand, const void* gout, uint8_t* gtiles, cudaStream_t st) {
+  if (g.variant != DCN_VARIANT_TORCH) return launch_gout_tiles_pix(g, operand, gout, gtiles, st);
   bd::Params P;
   memset(&P, 0, sizeof(P));
   P.g = g;
@@ -997,11 +1016,12 @@ int launch_gout_tiles_fwd_order(const Geo& g, int operand, const void* gout, uin
   return launch_gout_tiles(P, operand == DCN_OPERAND_BF16, gtiles, st);
 }
 
-// staged grad_out operand images (Torch layout only)
+// staged grad_out operand images
 size_t umma_bwd_data_gtile_bytes(const Geo& g, int operand) {
   bd::Params P;
   P.g = g;
-  if (g.variant != DCN_VARIANT_TORCH || !bwd_data_tiling(g, operand, &P, fuse_allowed())) return 0;
+  if (!bwd_data_tiling(g, operand, &P, fuse_allowed())) return 0;
+  if (g.variant != DCN_VARIANT_TORCH) return gtile_pix_bytes(g, operand);
   return align_up((size_t)P.num_tiles * P.OB * (operand == DCN_OPERAND_BF16 ? 1 : 2) * bd::kGImg, 1024);
 }
 
@@ -1038,8 +1058,9 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
   P.wtiles = wtiles;
   P.gtiles = gtiles;
   P.row_v = 0;
-  if (g.variant == DCN_VARIANT_TORCH) {
-    int rc = launch_gout_tiles(P, bf, gtiles, st);
+  {
+    int rc = g.variant == DCN_VARIANT_TORCH ? launch_gout_tiles(P, bf, gtiles, st)
+                                            : launch_gout_tiles_pix(g, operand, gout, gtiles, st);
     if (rc) return rc;
   }
   P.goff = goff;
@@ -1071,31 +1092,37 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
     if (bf) {                                                                                             \
       DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<V, RW, F, true, PW>,                          \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-      bd::bwd_data_kernel<V, RW, F, true, PW><<<grid, bd::threads_of(V, PW), smem, st>>>(P);              \
+      bd::bwd_data_kernel<V, RW, F, true, PW><<<grid, bd::threads_of(PW), smem, st>>>(P);              \
     } else {                                                                                              \
       DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<V, RW, F, false, PW>,                         \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-      bd::bwd_data_kernel<V, RW, F, false, PW><<<grid, bd::threads_of(V, PW), smem, st>>>(P);             \
+      bd::bwd_data_kernel<V, RW, F, false, PW><<<grid, bd::threads_of(PW), smem, st>>>(P);             \
     }                                                                                                     \
   } while (0)
+  // <= 128 plan entries per block (2 per plan thread): 2 plan warps are enough (20 warps, 96 registers for
+  // the scatter loop); with more sampling points per block the plan would become the bottleneck: 4 warps
+  const bool slim = P.plan_cap <= 128;
+#define DCN_LAUNCH_BD2(V, RW, F)                       \
+  do {                                                 \
+    if (slim) DCN_LAUNCH_BD(V, RW, F, 2);              \
+    else DCN_LAUNCH_BD(V, RW, F, 4);                   \
+  } while (0)
   if (g.variant == DCN_VARIANT_TORCH) {
-    const bool slim = P.Rt == 2 && P.plan_cap <= bd::plan_max_of(2);  // Gt = 64: 2 plan warps are enough
     if (P.fuse_w) {
       if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 16, true, 4);
-      else if (slim) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32, true, 2);
-      else DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32, true, 4);
+      else DCN_LAUNCH_BD2(DCN_VARIANT_TORCH, 32, true);
     } else {
       if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 16, false, 4);
-      else if (slim) DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32, false, 2);
-      else DCN_LAUNCH_BD(DCN_VARIANT_TORCH, 32, false, 4);
+      else DCN_LAUNCH_BD2(DCN_VARIANT_TORCH, 32, false);
     }
   } else if (P.fuse_w) {
-    if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 16, true, 4);
-    else DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 32, true, 4);
+    if (narrow) DCN_LAUNCH_BD2(DCN_VARIANT_JITTOR, 16, true);
+    else DCN_LAUNCH_BD2(DCN_VARIANT_JITTOR, 32, true);
   } else {
-    if (narrow) DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 16, false, 4);
-    else DCN_LAUNCH_BD(DCN_VARIANT_JITTOR, 32, false, 4);
+    if (narrow) DCN_LAUNCH_BD2(DCN_VARIANT_JITTOR, 16, false);
+    else DCN_LAUNCH_BD2(DCN_VARIANT_JITTOR, 32, false);
   }
+#undef DCN_LAUNCH_BD2
 #undef DCN_LAUNCH_BD
   DCN_KERNEL_CHECK("umma_bwd_data_kernel");
   return DCN_OK;

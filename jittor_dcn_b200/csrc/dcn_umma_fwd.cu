@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       mbar_init(&tempty[a], kEpiWarps);
       mbar_init(&pfull[a], kPlanWarps);
       mbar_init(&pempty[a], kProdWarps);
-      mbar_init(&afull[a], (MODE == MODE_WGRAD && VARIANT == DCN_VARIANT_TORCH) ? 1 : kEpiWarps);
+      mbar_init(&afull[a], 1);
       mbar_init(&aempty[a], 1);
     }
     fence_barrier_init();
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (MODE == MODE_WGRAD && VARIANT == DCN_VARIANT_TORCH && (P.g_OB & 1)) {
+  if (MODE == MODE_WGRAD && (P.g_OB & 1)) {
     // O is not a multiple of 128: the upper 64-o half of the last M = 128 operand stays zero
     for (int ab = 0; ab < P.n_gbuf; ++ab) {
       uint8_t* z = gbuf_base + (size_t)ab * gbuf_bytes + (size_t)P.g_OB * NIMG * kATile;
@@ -344,67 +344,23 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     if (VARIANT == DCN_VARIANT_TORCH && P.tma_out && tid == 0)
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
-    // ================================================================ grad_out converter, then the
-    // one-shot epilogue (weight gradient).  Per row tile: g[row m, o] = gout[b(m), o, r(m)] is
-    // split into bf16 hi/lo and stored K-major ([o][64 rows] per row half) as the A operand.
-    const int ct = tid;  // 0..127
-    const int O_pad = P.o_blocks * 128;
-    int ab = 0;
-    uint32_t aphase = 0;
-    for (int tile = tile0; tile < t.num_tiles; tile = next_tile(tile)) {
-      if (VARIANT == DCN_VARIANT_TORCH) {
-        // Torch-layout rows are R floats apart in gout: the tile's images were staged by
-        // gout_tiles_torch_kernel (in this kernel's row order); one bulk copy fetches them
-        if (tid == 0) {
-          const uint32_t bytes = (uint32_t)P.g_OB * NIMG * kATile;
-          mbar_wait_relaxed(&aempty[ab], aphase ^ 1);
-          mbar_arrive_expect_tx(&afull[ab], bytes);
-          bulk_g2s(gbuf_base + (size_t)ab * gbuf_bytes, P.gtiles + (size_t)tile * bytes, bytes, &afull[ab]);
-        }
+    // ================================================================ grad_out tile loader, then the
+    // one-shot epilogue (weight gradient).  The tile's operand images [ob][hi | lo][128 rows x 64 o] were staged
+    // once per backward pass (gout_tiles_*_kernel, rows in this kernel's order): one bulk copy per tile.
+    if (tid == 0) {
+      int ab = 0;
+      uint32_t aphase = 0;
+      const uint32_t bytes = (uint32_t)P.g_OB * NIMG * kATile;
+      for (int tile = tile0; tile < t.num_tiles; tile = next_tile(tile)) {
+        mbar_wait_relaxed(&aempty[ab], aphase ^ 1);
+        mbar_arrive_expect_tx(&afull[ab], bytes);
+        bulk_g2s(gbuf_base + (size_t)ab * gbuf_bytes, P.gtiles + (size_t)tile * bytes, bytes, &afull[ab]);
         if (P.n_gbuf == 2) {
           ab ^= 1;
           if (ab == 0) aphase ^= 1;
         } else {
           aphase ^= 1;
         }
-        continue;
-      }
-      mbar_wait_relaxed(&aempty[ab], aphase ^ 1);
-      uint8_t* gb = gbuf_base + (size_t)ab * gbuf_bytes;
-      // items: (o, group of 4 consecutive tile rows); lanes run along the row groups
-      for (int item = ct; item < O_pad * 32; item += kEpiWarps * 32) {
-        const int o = item >> 5, mq = item & 31, m = mq * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (o < O) {
-          {
-            const int b = tile / t.pix_blocks, p = (tile - b * t.pix_blocks) * 128 + m;
-            const XT* src = reinterpret_cast<const XT*>(P.gout) + ((size_t)b * O + o) * g.HW + p;
-            if (!BF && p + 3 < g.HW && (g.HW & 3) == 0) {
-              v = __ldg(reinterpret_cast<const float4*>(src));
-            } else {
-              if (p < g.HW) v.x = (float)__ldg(src);
-              if (p + 1 < g.HW) v.y = (float)__ldg(src + 1);
-              if (p + 2 < g.HW) v.z = (float)__ldg(src + 2);
-              if (p + 3 < g.HW) v.w = (float)__ldg(src + 3);
-            }
-          }
-        }
-        uint2 hi, lo;
-        split4(v, hi, lo);  // bf16 mode: the inputs are bf16 already, hi is exact and lo unused
-        // image of row half h: [hi: O_pad x 64][lo: O_pad x 64]
-        uint8_t* img_h = gb + (size_t)(m >> 6) * NIMG * P.g_img;
-        const uint32_t so = kmajor_sw128_off(o, m & 63);
-        *reinterpret_cast<uint2*>(img_h + so) = hi;
-        if (!BF) *reinterpret_cast<uint2*>(img_h + P.g_img + so) = lo;
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&afull[ab]);
-      if (P.n_gbuf == 2) {
-        ab ^= 1;
-        if (ab == 0) aphase ^= 1;
-      } else {
-        aphase ^= 1;
       }
     }
     // ---- epilogue: accumulators -> gW (one red.global.add per element; each CTA owns a K slice
@@ -484,9 +440,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     //          row half h at +1024;
     //   Jittor image (columns contiguous per row) = MN-major B, 8-row groups 1024 B apart.
     if (lane == 0) {
-      // Torch: A = staged grad_out images [row][64 o] read MN-major (o contiguous, 64-o atoms = consecutive
-      // images), B = sample image K-major; Jittor: A = converted [o][64 rows] K-major, B MN-major
-      const uint32_t idesc = make_idesc_bf16(128, 64, VARIANT == DCN_VARIANT_TORCH, VARIANT != DCN_VARIANT_TORCH);
+      // A = staged grad_out images [row][64 o] read MN-major (o contiguous, 64-o atoms = consecutive images);
+      // B = the sample image: K-major for the Torch layout, MN-major for the pixel-row layouts
+      const uint32_t idesc = make_idesc_bf16(128, 64, true, VARIANT != DCN_VARIANT_TORCH);
       const int ncols = (kb1 - kb0) * 64;
       int s = 0, ab = 0;
       uint32_t phase = 0, aphase = 0;
@@ -511,16 +467,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
               dsl = make_sdesc_sw128(s_lo + ks * 2048, 1024, 1024);
             }
             for (int ob = 0; ob < P.o_blocks; ++ob) {
-              uint64_t dgh, dgl;
-              if (VARIANT == DCN_VARIANT_TORCH) {
-                const uint32_t g_hi = gb + (uint32_t)(2 * ob) * NIMG * kATile + ks * 2048;
-                dgh = make_sdesc_sw128(g_hi, NIMG * kATile, 1024);
-                dgl = make_sdesc_sw128(g_hi + kATile, NIMG * kATile, 1024);
-              } else {
-                const uint32_t g_hi = gb + h * NIMG * P.g_img + ob * (128 * 128) + k4 * 32;
-                dgh = make_sdesc_sw128(g_hi, 16, 1024);
-                dgl = make_sdesc_sw128(g_hi + P.g_img, 16, 1024);
-              }
+              const uint32_t g_hi = gb + (uint32_t)(2 * ob) * NIMG * kATile + ks * 2048;
+              const uint64_t dgh = make_sdesc_sw128(g_hi, NIMG * kATile, 1024);
+              const uint64_t dgl = make_sdesc_sw128(g_hi + kATile, NIMG * kATile, 1024);
               const uint32_t d_tmem = tmem_base + (uint32_t)(ob * ncols + (kb - kb0) * 64);
               umma_bf16(d_tmem, dgh, dsh, idesc, (first_tile && ks == 0) ? 0u : 1u);
               if (!BF) {
@@ -994,7 +943,7 @@ int umma_wgrad_any(const Geo& g, int operand, const void* xt, const float* off, 
   P.gw = gw;
   P.gtiles = gtiles;
   P.g_OB = (g.O + 63) / 64;
-  if (g.variant == DCN_VARIANT_TORCH) {
+  {
     int rc = launch_gout_tiles_fwd_order(g, operand, gout, gtiles, st);
     if (rc) return rc;
   }
