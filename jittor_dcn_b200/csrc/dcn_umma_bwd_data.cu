@@ -877,7 +877,7 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
   const int taps = g.C >= 128 ? 1 : 128 / g.C;
   P->o_cols = 0;
   // fused weight gradient: 64-pixel tiles, gW^T accumulator blocks of O columns next to the 2 gA buffers
-  if (allow_fuse && g.O <= 128) {
+  if (allow_fuse && g.O <= 256) {
     const int ncols = 64, o_cols = (g.O + 15) / 16 * 16;
     const size_t plan = 2 * (size_t)taps * ncols * sizeof(bd::ScatEntry);
     const size_t real = (size_t)P->OB * nimg * (ncols * 128);
