@@ -385,6 +385,109 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
                         part_g[0] * (vi < 8 * NB ? P.scale_ix : P.scale_iy));
           }
         };
+        // PAIR mode (all 32 lanes of the warp share the sampling points): lane pairs (2k, 2k+1) swap half of their
+        // accumulator values, so that a thread owns TWO adjacent channels for FOUR of the 8 columns.  Every corner
+        // is then one 8-byte load and one red.global.add.v2.f32, entries and weights are needed for 4 columns
+        // instead of 8, and the coordinate gradient (summed over the thread's two channels first) is an 8-value
+        // reduce-scatter over the 16 lanes of equal parity: 15 shuffles instead of 31.  Per 8 columns the warp
+        // issues 16 + 16 + 4 + 19 load/store-unit instructions instead of 32 + 33 + 8 + 31.
+        auto pass2 = [&](const int cc, const uint32_t* raw) {
+          const int odd = lane & 1;
+          float ga[4], gb[4];  // accumulator values of the lower / upper channel of the pair, columns cu0 .. cu0+3
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float own = __uint_as_float(odd ? raw[u + 4] : raw[u]);
+            const float send = __uint_as_float(odd ? raw[u] : raw[u + 4]);
+            const float got = __shfl_xor_sync(0xffffffffu, send, 1);
+            ga[u] = odd ? got : own;
+            gb[u] = odd ? own : got;
+          }
+          const int cu0 = cc + 4 * odd;
+          // image pointers of the channel PAIR
+          const char* xpair = ximg - odd * (int)sizeof(XT);
+          char* gpair = gimg ? gimg - odd * 4 : nullptr;
+          float part_g[8];  // [0..3] g_ix of this thread's 4 columns (both channels), [4..7] g_iy
+          float sa[4], sb2[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint4 e4 = *reinterpret_cast<const uint4*>(pl + cu0 + u);  // {base, fx, fy, gidx}
+            const float fx = __uint_as_float(e4.y), fy = __uint_as_float(e4.z);
+            constexpr int XS = BF ? 1 : 0;
+            const char* xp = xpair + (e4.x >> XS);
+            float2 v0, v1, v2, v3;
+            if (BF) {
+              const uint32_t r0 = __ldg(reinterpret_cast<const uint32_t*>(xp));
+              const uint32_t r1 = __ldg(reinterpret_cast<const uint32_t*>(xp + dx1));
+              const uint32_t r2 = __ldg(reinterpret_cast<const uint32_t*>(xp + dx2));
+              const uint32_t r3 = __ldg(reinterpret_cast<const uint32_t*>(xp + dx2 + dx1));
+              v0 = make_float2(__uint_as_float(r0 << 16), __uint_as_float(r0 & 0xffff0000u));
+              v1 = make_float2(__uint_as_float(r1 << 16), __uint_as_float(r1 & 0xffff0000u));
+              v2 = make_float2(__uint_as_float(r2 << 16), __uint_as_float(r2 & 0xffff0000u));
+              v3 = make_float2(__uint_as_float(r3 << 16), __uint_as_float(r3 & 0xffff0000u));
+            } else {
+              v0 = __ldg(reinterpret_cast<const float2*>(xp));
+              v1 = __ldg(reinterpret_cast<const float2*>(xp + dx1));
+              v2 = __ldg(reinterpret_cast<const float2*>(xp + dx2));
+              v3 = __ldg(reinterpret_cast<const float2*>(xp + dx2 + dx1));
+            }
+            const float ex = __fsub_rn(1.0f, fx), sy = __fsub_rn(1.0f, fy);
+            const float w0 = __fmul_rn(sy, ex), w1 = __fmul_rn(sy, fx), w2 = __fmul_rn(fy, ex),
+                        w3 = __fmul_rn(fy, fx);
+            if (gpair && (int)e4.w >= 0) {
+              char* gp = gpair + e4.x;
+              atomicAdd(reinterpret_cast<float2*>(gp), make_float2(ga[u] * w0, gb[u] * w0));
+              atomicAdd(reinterpret_cast<float2*>(gp + dg1), make_float2(ga[u] * w1, gb[u] * w1));
+              atomicAdd(reinterpret_cast<float2*>(gp + dg2), make_float2(ga[u] * w2, gb[u] * w2));
+              atomicAdd(reinterpret_cast<float2*>(gp + dg2 + dg1), make_float2(ga[u] * w3, gb[u] * w3));
+            }
+            part_g[u] = ga[u] * ((v1.x - v0.x) * sy + (v3.x - v2.x) * fy) +
+                        gb[u] * ((v1.y - v0.y) * sy + (v3.y - v2.y) * fy);
+            part_g[4 + u] = ga[u] * ((v2.x - v0.x) * ex + (v3.x - v1.x) * fx) +
+                            gb[u] * ((v2.y - v0.y) * ex + (v3.y - v1.y) * fx);
+            if (FUSE) {
+              sa[u] = fmaf(v3.x, w3, fmaf(v2.x, w2, fmaf(v1.x, w1, v0.x * w0)));
+              sb2[u] = fmaf(v3.y, w3, fmaf(v2.y, w2, fmaf(v1.y, w1, v0.y * w0)));
+            }
+          }
+          if (FUSE) {
+            // 4 columns of the two rows m & ~1, m | 1: the lower / upper 8 bytes of the rows' 16-byte chunk
+            const int ma = m & ~1;
+            uint8_t* ra = sbuf + (size_t)sb * s_buf + (size_t)(ma >> 3) * 1024 + (ma & 7) * 128;
+            const uint32_t soa = (uint32_t)((((cc >> 3) ^ ma) & 7) << 4) + 8u * odd;
+            const uint32_t sob = (uint32_t)((((cc >> 3) ^ (ma + 1)) & 7) << 4) + 8u * odd;
+            uint2 hi, lo;
+            split_pair(sa[0], sa[1], hi.x, lo.x);
+            split_pair(sa[2], sa[3], hi.y, lo.y);
+            *reinterpret_cast<uint2*>(ra + soa) = hi;
+            if (!BF) *reinterpret_cast<uint2*>(ra + s_img + soa) = lo;
+            split_pair(sb2[0], sb2[1], hi.x, lo.x);
+            split_pair(sb2[2], sb2[3], hi.y, lo.y);
+            *reinterpret_cast<uint2*>(ra + 128 + sob) = hi;
+            if (!BF) *reinterpret_cast<uint2*>(ra + 128 + s_img + sob) = lo;
+          }
+          // reduce-scatter of the 8 values over the 16 lanes of equal parity (lane bits 4..1)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) part_g[k] += __shfl_xor_sync(0xffffffffu, part_g[k], 16);
+#pragma unroll
+          for (int s2 = 8, n = 4; s2 >= 2; s2 >>= 1, n >>= 1) {
+            const bool up = (lane & s2) != 0;
+#pragma unroll
+            for (int k = 0; k < n; ++k) {
+              const float send = up ? part_g[k] : part_g[k + n];
+              const float keep = up ? part_g[k + n] : part_g[k];
+              part_g[k] = keep + __shfl_xor_sync(0xffffffffu, send, s2);
+            }
+          }
+          if (lane < 16) {
+            // value index: lane bit 3 -> component (0 g_ix, 1 g_iy), bits 2..1 -> column inside the thread's four
+            const int vi = (lane >> 1) & 7, col = cu0 + (vi & 3);
+            const int gidx = pl[col].gidx;
+            if (gidx >= 0 && part_g[0] != 0.f)
+              atomicAdd(P.goff + (size_t)gidx + (vi < 4 ? (size_t)P.ix_delta : 0),
+                        part_g[0] * (vi < 4 ? P.scale_ix : P.scale_iy));
+          }
+        };
+        constexpr bool PAIR = RW == 32;
         // (fetching both passes' accumulator values up front with one x16 load lets the compiler overlap the
         // second pass's loads with the first pass's shuffles, but measured slower: 11.85 vs 11.36 ms)
         {
@@ -399,7 +502,8 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
                            : "memory");
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            pass(cc, raw);
+            if (PAIR) pass2(cc, raw);
+            else pass(cc, raw);
           }
         }
         tc_fence_before();
