@@ -43,7 +43,15 @@ WORKLOADS = {
            128, 128, 128, 56, 56, 3, 1, 1),
     "c4": ("ResNet-50 C4 DCN layer 256->256 3x3 s1 p1, 28x28, batch 128 per GPU (BASELINE configs[3] layer), fwd+bwd",
            128, 256, 256, 28, 28, 3, 1, 1),
+    "c5": ("ResNet-50 C5 DCN layer 512->512 3x3 s1 p1, 14x14, batch 128 per GPU (BASELINE configs[3] layer; O = 512 "
+           "runs as two output-channel groups), fwd+bwd",
+           128, 512, 512, 14, 14, 3, 1, 1),
 }
+# BASELINE configs[3]: the 13 DCN layers of ResNet-50's C3-C5 stages, interleaved so that no
+# layer finds its own inputs still in L2
+STACK_ORDER = ["c3", "c4", "c5", "c4", "c3", "c4", "c5", "c4", "c3", "c4", "c5", "c4", "c3"]
+STACK_DESC = ("stack: DCN ResNet-50 C3-C5 stage stack, 13 independent DeformConv2d layers fwd+bwd (4x 128->128 @56x56, "
+              "6x 256->256 @28x28, 3x 512->512 @14x14), batch 128 per GPU (BASELINE configs[3])")
 # BASELINE configs[4]: whole toy-detector training step, global batch 1024 sharded over the GPUs
 DETECTOR_DESC = ("detector: data-parallel DCN detector training step (train.py:142-175 topology, 4 DeformConv2d "
                  "layers), 1x128x128 synthetic canvases, global batch 1024 sharded over the GPUs, Adam, one "
@@ -55,7 +63,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["detector"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["detector", "stack"])
     ap.add_argument("--global-batch", type=int, default=1024, help="detector workload: global batch")
     ap.add_argument("--variant", default="torch", choices=["torch", "jittor"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -335,8 +343,132 @@ def run_detector(args):
     return 0
 
 
+def run_stack(args):
+    """BASELINE configs[3]: every step runs the 13 layers of STACK_ORDER forward + backward through the C ABI
+    (inputs resident in HBM); images/s = batch / time of the whole stack."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+    import jittor_dcn_b200 as dcn
+    from jittor_dcn_b200 import _lib
+    from jittor_dcn_b200.functional import staged_workspace
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = dcn.load()
+    variant = dcn.VARIANT_TORCH if args.variant == "torch" else dcn.VARIANT_JITTOR
+    operand = dcn.OPERAND_BF16 if args.operand == "bf16" else dcn.OPERAND_FP32
+    act = torch.bfloat16 if operand == dcn.OPERAND_BF16 else torch.float32
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    layers, paths, work = {}, {}, {"fwd": {"bytes": 0, "flops": 0}, "bwd": {"bytes": 0, "flops": 0}}
+    for name in sorted(set(STACK_ORDER)):
+        _, B, C, O, H, W, k, s, p = WORKLOADS[name]
+        N = k * k
+        shp = dcn.make_shape(B, C, O, H, W, k, s, p, variant, operand=operand)
+        Ho, Wo = _lib.output_hw(shp)
+        x = torch.randn(B, C, H, W, device=dev, generator=gen).to(act)
+        off = torch.randn(B, 2 * N, Ho, Wo, device=dev, generator=gen) * args.offset_sigma
+        wt = (torch.randn(O, C, k, k, device=dev, generator=gen) * (2.0 / (C * N)) ** 0.5).to(act)
+        bias = torch.randn(O, device=dev, generator=gen) * 0.1
+        gout = torch.randn(B, O, Ho, Wo, device=dev, generator=gen).to(act)
+        ws = staged_workspace(x, wt, k, s, p, variant, operand, 0)
+        layers[name] = (x, off, wt, bias, gout, ws, (k, s, p))
+        paths[name] = [lib.dcn_path_name(ctypes.byref(shp), ph).decode() for ph in (0, 1)]
+        w1 = layer_bytes_flops(B, C, O, H, W, Ho, Wo, N, act_bytes=x.element_size())
+        for ph in ("fwd", "bwd"):
+            for q in ("bytes", "flops"):
+                work[ph][q] += w1[ph][q] * STACK_ORDER.count(name)
+    B = WORKLOADS["c3"][1]
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        for name in STACK_ORDER:
+            x, off, wt, bias, gout, ws, (k, s, p) = layers[name]
+            dcn.dcn_forward(x, off, wt, bias, k, s, p, variant, operand=operand, ws=ws)
+            dcn.dcn_backward(x, off, wt, gout, True, k, s, p, variant, operand=operand, ws=ws,
+                             xt_staged=ws is not None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    lib.dcn_launch_count_reset()
+    _lib.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = int(lib.dcn_launch_count())
+    prof = _lib.profile_end()
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    pk = peaks()
+    kernels = {n: {"launches": c, "ms_per_step": tot / args.steps, "share": tot / max(elapsed_ms, 1e-9)}
+               for n, (c, tot) in prof.items()}
+    roofline = None
+    ranked = sorted((n for n in prof if n in KERNEL_ROLE), key=lambda n: -prof[n][1])
+    if ranked:
+        top = ranked[0]
+        role = KERNEL_ROLE[top]
+        if top == "umma_bwd_data_kernel" and "umma_bwd_weight_kernel" not in prof and "bwd_weight_kernel" not in prof:
+            role = "bwd"
+        # all launches of the dominant kernel in one step, against the work of all 13 layers in that role
+        tot_s = prof[top][1] / args.steps * 1e-3
+        ach = work[role]["flops"] / tot_s / 1e12
+        roofline = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16_sustained"], "traffic": None, "kernel": top,
+                    "avg_ms": tot_s * 1e3 / len(STACK_ORDER), "peak_source": pk["source"],
+                    "algorithmic_bytes": work[role]["bytes"], "algorithmic_flops": work[role]["flops"],
+                    "note": "sum over the 13 layers' launches of this kernel in one step"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "DeformConv2d fwd+bwd images/sec", "value": world * B / (ms_per_step * 1e-3),
+            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if operand == dcn.OPERAND_BF16 else "f32", "data": "synthetic",
+            "config": {"workload": STACK_DESC, "variant": args.variant, "operand": args.operand,
+                       "batch_per_gpu": B, "global_batch": world * B, "offset_sigma_px": args.offset_sigma,
+                       "paths_fwd_bwd": paths, "order": STACK_ORDER,
+                       "l2": "layers interleaved; every layer's inputs are evicted by the others' traffic "
+                             "(1.4 GB of operands per step)", "allreduce": "none", "parallelism": f"dp{world}"},
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": None, "e2e": None,
+            "gpu_launches": launches, "clocks": clocks}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse_args()
+    if args.workload == "stack":
+        if args.impl == "reference":
+            raise SystemExit("--impl reference supports the single-layer workloads")
+        return run_stack(args)
     if args.workload == "detector":
         if args.impl == "reference":
             raise SystemExit("--impl reference supports the single-layer workloads")

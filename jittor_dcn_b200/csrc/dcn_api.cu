@@ -86,6 +86,20 @@ static int geo_or_error(const DcnShape* s, Geo* g) {
 
 static size_t plan_bytes(const Geo& g) { return align_up(sizeof(Tap) * (size_t)g.B * g.P, 256); }
 
+// Generic kernels in bf16 storage mode: fp32 scratch copies of the bfloat16 operands, behind the plan.
+static size_t f32_copy_bytes(size_t n) { return align_up(sizeof(float) * n, 256); }
+static size_t n_x(const Geo& g) { return (size_t)g.B * g.C * g.H * g.W; }
+static size_t n_w(const Geo& g) { return (size_t)g.O * g.K; }
+static size_t n_out(const Geo& g) { return (size_t)g.B * g.O * g.HW; }
+static size_t simt_workspace(const Geo& g, int operand, int phase) {
+  size_t b = plan_bytes(g);
+  if (operand == DCN_OPERAND_BF16) {
+    b += f32_copy_bytes(n_x(g)) + f32_copy_bytes(n_w(g));
+    if (phase == DCN_PHASE_BACKWARD) b += f32_copy_bytes(n_out(g));
+  }
+  return b;
+}
+
 static bool use_umma(const DcnShape* s, const Geo& g, int phase) {
   if (s->flags & DCN_FLAG_FORCE_SIMT) return false;
   return umma_supported(g, s->operand, phase);
@@ -129,8 +143,7 @@ size_t dcn_workspace_bytes(const DcnShape* s, int phase) {
   if (geo_or_error(s, &g)) return 0;
   if (phase == DCN_PHASE_CORNERS) return 0;
   if (use_umma(s, g, phase)) return umma_workspace_bytes(g, s->operand, phase);
-  if (s->operand != DCN_OPERAND_FP32) return 0;
-  return plan_bytes(g);
+  return simt_workspace(g, s->operand, phase);
 }
 
 const char* dcn_path_name(const DcnShape* s, int phase) {
@@ -209,11 +222,15 @@ int dcn_forward(const DcnShape* s, const void* x, const void* offset, const void
   if (use_umma(s, g, DCN_PHASE_FORWARD))
     return umma_forward(g, s->operand, s->flags, x, (const float*)offset, weight, (const float*)bias,
                         out, workspace, st);
-  if (s->operand != DCN_OPERAND_FP32) {
-    set_error("operand mode %d needs the tcgen05 path, which does not cover this shape", s->operand);
-    return DCN_ERR_UNSUPPORTED;
-  }
   Tap* plan = (Tap*)workspace;
+  if (s->operand == DCN_OPERAND_BF16) {
+    // shapes the tensor path does not tile: widen the bf16 operands once, run the fp32 kernels
+    float* xf = (float*)((uint8_t*)workspace + plan_bytes(g));
+    float* wf = (float*)((uint8_t*)xf + f32_copy_bytes(n_x(g)));
+    if ((rc = launch_widen_bf16(x, xf, n_x(g), st)) || (rc = launch_widen_bf16(weight, wf, n_w(g), st))) return rc;
+    x = xf;
+    weight = wf;
+  }
   if ((rc = launch_plan(g, (const float*)offset, plan, st))) return rc;
   return simt_forward(g, (const float*)x, plan, (const float*)weight, (const float*)bias, (float*)out,
                       st);
@@ -242,11 +259,18 @@ int dcn_backward(const DcnShape* s, const void* x, const void* offset, const voi
     return umma_backward(g, s->operand, s->flags, x, (const float*)offset, weight, grad_out,
                          (float*)grad_x, (float*)grad_offset, (float*)grad_weight,
                          (float*)grad_bias, workspace, st);
-  if (s->operand != DCN_OPERAND_FP32) {
-    set_error("operand mode %d needs the tcgen05 path, which does not cover this shape", s->operand);
-    return DCN_ERR_UNSUPPORTED;
-  }
   Tap* plan = (Tap*)workspace;
+  if (s->operand == DCN_OPERAND_BF16) {
+    float* xf = (float*)((uint8_t*)workspace + plan_bytes(g));
+    float* wf = (float*)((uint8_t*)xf + f32_copy_bytes(n_x(g)));
+    float* gf = (float*)((uint8_t*)wf + f32_copy_bytes(n_w(g)));
+    if ((rc = launch_widen_bf16(x, xf, n_x(g), st)) || (rc = launch_widen_bf16(weight, wf, n_w(g), st)) ||
+        (rc = launch_widen_bf16(grad_out, gf, n_out(g), st)))
+      return rc;
+    x = xf;
+    weight = wf;
+    grad_out = gf;
+  }
   if ((rc = launch_plan(g, (const float*)offset, plan, st))) return rc;
   return simt_backward(g, s->flags, (const float*)x, plan, (const float*)weight,
                        (const float*)grad_out, (float*)grad_x, (float*)grad_offset,

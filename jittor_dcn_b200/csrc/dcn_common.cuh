@@ -15,6 +15,8 @@ namespace dcn {
 // Device-side problem geometry (passed by value to every kernel).
 struct Geo {
   int B, C, O, H, W;
+  int Oimg;     // channels per image of out / grad_out IN MEMORY (== O unless this Geo describes a
+                // group of O output channels of a wider layer: dcn_umma_host.cu splits O > 256)
   int N;        // taps = kh*kw
   int Ho, Wo;   // output extent
   int HW;       // Ho*Wo   rows of the GEMM per batch element
@@ -61,6 +63,7 @@ __host__ inline int make_geo(const DcnShape* s, Geo* g) {
   if (s->variant != DCN_VARIANT_JITTOR && s->variant != DCN_VARIANT_TORCH && s->variant != DCN_VARIANT_DCNV1)
     return DCN_ERR_BAD_SHAPE;
   g->B = s->B; g->C = s->C; g->O = s->O; g->H = s->H; g->W = s->W;
+  g->Oimg = s->O;
   g->N = s->kh * s->kw;
   g->Ho = (s->H + 2 * s->ph - s->kh) / s->sh + 1;
   g->Wo = (s->W + 2 * s->pw - s->kw) / s->sw + 1;
@@ -204,6 +207,7 @@ int simt_forward(const Geo& g, const float* x, const Tap* plan, const float* wt,
                  float* out, cudaStream_t st);
 int launch_offset_scale(const Geo& g, float* goff, cudaStream_t st);
 int launch_bias_grad(const Geo& g, const void* gout, int operand, float* gb, cudaStream_t st);
+int launch_widen_bf16(const void* src, float* dst, size_t n, cudaStream_t st);
 enum { SIMT_BWD_DATA = 1, SIMT_BWD_WEIGHT = 2, SIMT_BWD_BIAS = 4, SIMT_BWD_ALL = 7 };
 int simt_backward(const Geo& g, int flags, const float* x, const Tap* plan, const float* wt,
                   const float* gout, float* gx, float* goff, float* gw, float* gb, cudaStream_t st,

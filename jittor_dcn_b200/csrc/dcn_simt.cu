@@ -447,6 +447,27 @@ int launch_bias_grad(const Geo& g, const void* gout, int operand, float* gb, cud
   return DCN_OK;
 }
 
+// bf16 storage mode on the generic kernels: the bfloat16 operands are widened (exactly) into fp32
+// scratch copies and the fp32 kernels run on those.  n must be even (every tensor here is).
+__global__ void __launch_bounds__(256) widen_bf16_kernel(const __nv_bfloat162* __restrict__ src,
+                                                         float2* __restrict__ dst, size_t n2) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __bfloat1622float2(src[i]);
+}
+
+int launch_widen_bf16(const void* src, float* dst, size_t n, cudaStream_t st) {
+  if (n & 1) {
+    set_error("widen_bf16: odd element count %zu", n);
+    return DCN_ERR_UNSUPPORTED;
+  }
+  const size_t n2 = n / 2;
+  KernelScope scope("widen_bf16_kernel", st);
+  widen_bf16_kernel<<<(unsigned)min((n2 + 255) / 256, (size_t)148 * 16), 256, 0, st>>>(
+      (const __nv_bfloat162*)src, (float2*)dst, n2);
+  DCN_KERNEL_CHECK("widen_bf16_kernel");
+  return DCN_OK;
+}
+
 int launch_offset_scale(const Geo& g, float* goff, cudaStream_t st) {
   if (g.variant == DCN_VARIANT_DCNV1) return DCN_OK;  // coordinates are pixels already: factor 1
   const size_t total = (size_t)g.B * 2 * g.N * g.HW;

@@ -56,12 +56,22 @@ size_t umma_bwd_workspace(const Geo& g, int operand) {
   return umma_xt_bytes(g, operand) + (m > c ? m : c);
 }
 
+bool o_groups(const Geo& g, int* size);
+Geo o_group_geo(const Geo& g, int o0, int size);
+
+// g is the whole layer; the kernels run per output-channel group (dcn_umma_host.cu) — one group unless
+// O > 256.  grad_x (via gxt) and grad_offset accumulate over the groups.
 int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, const float* off, const void* wtv,
                       const void* goutv, float* gx, float* goff, float* gw, float* gb, void* workspace,
                       cudaStream_t st) {
+  int gsize;
+  if (!o_groups(g, &gsize)) {
+    set_error("umma backward: O = %d cannot be split into groups", g.O);
+    return DCN_ERR_UNSUPPORTED;
+  }
+  const Geo g0 = o_group_geo(g, 0, gsize);  // the largest group: sizes every scratch region
+  const size_t esz = operand == DCN_OPERAND_BF16 ? 2 : 4;
   const void* x = xv;
-  const void* wt = wtv;
-  const void* gout = goutv;
   void* xt = workspace;
   uint8_t* rest = (uint8_t*)workspace + umma_xt_bytes(g, operand);
   Tiling t;
@@ -74,29 +84,47 @@ int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, cons
   // wrote for this very shape / operand (same layout in both phases) — skip the transpose
   if (!(flags & DCN_FLAG_XT_STAGED) && (rc = launch_nchw_to_nhwc(g, t, x, xt, operand, st))) return rc;
   const bool want_gx = !(flags & DCN_FLAG_NO_GRAD_X) && gx != nullptr;
-  if (operand != DCN_OPERAND_FP32 || use_umma_data(g, operand)) {
+  bool all_fused = true;
+  if (operand != DCN_OPERAND_FP32 || use_umma_data(g0, operand)) {
     float* gxt = (float*)rest;
     uint8_t* wtiles = rest + umma_xt_bytes(g, DCN_OPERAND_FP32);
-    uint8_t* gtiles = wtiles + umma_bwd_data_wtile_bytes(g, operand);
+    uint8_t* gtiles = wtiles + umma_bwd_data_wtile_bytes(g0, operand);
     if (want_gx) DCN_CUDA_TRY(cudaMemsetAsync(gxt, 0, sizeof(float) * (size_t)g.B * xt_image_stride(g), st));
     DCN_CUDA_TRY(cudaMemsetAsync(goff, 0, sizeof(float) * (size_t)g.B * 2 * g.N * g.HW, st));
-    const bool fused = umma_bwd_data_fuses_wgrad(g, operand);  // one pass over the samples yields gW as well
-    if (fused) DCN_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.O * g.K, st));
-    if ((rc = umma_bwd_data_any(g, operand, xt, want_gx ? gxt : nullptr, off, wt, gout, goff, gw, wtiles, gtiles, st)))
-      return rc;
+    for (int o0 = 0; o0 < g.O; o0 += gsize) {
+      const Geo gc = o_group_geo(g, o0, gsize);
+      const bool fused = umma_bwd_data_fuses_wgrad(gc, operand);  // one pass over the samples yields gW as well
+      all_fused = all_fused && fused;
+      float* gwc = gw + (size_t)o0 * g.K;
+      if (fused) DCN_CUDA_TRY(cudaMemsetAsync(gwc, 0, sizeof(float) * (size_t)gc.O * g.K, st));
+      if ((rc = umma_bwd_data_any(gc, operand, xt, want_gx ? gxt : nullptr, off,
+                                  (const uint8_t*)wtv + (size_t)o0 * g.K * esz,
+                                  (const uint8_t*)goutv + (size_t)o0 * g.HW * esz, goff, gwc, wtiles, gtiles, st)))
+        return rc;
+    }
     if (want_gx && (rc = launch_nhwc_to_nchw_add(g, t, gxt, gx, (flags & DCN_FLAG_ACCUM_GRAD_X) ? 1 : 0, st)))
       return rc;
-    if ((rc = launch_bias_grad(g, gout, operand, gb, st))) return rc;
-    if (fused) return DCN_OK;
+    if ((rc = launch_bias_grad(g, goutv, operand, gb, st))) return rc;
+    if (all_fused) return DCN_OK;
   } else {
+    all_fused = false;
     Tap* plan = (Tap*)rest;
     if ((rc = launch_plan(g, off, plan, st))) return rc;
-    if ((rc = simt_backward(g, flags, (const float*)x, plan, (const float*)wt, (const float*)gout, gx, goff, gw,
+    if ((rc = simt_backward(g, flags, (const float*)x, plan, (const float*)wtv, (const float*)goutv, gx, goff, gw,
                             gb, st, SIMT_BWD_DATA | SIMT_BWD_BIAS)))
       return rc;
   }
-  // everything that lived in `rest` (gxt, tiles, plan) is dead by now
-  return umma_wgrad_any(g, operand, xt, off, gout, gw, rest, st);
+  // everything that lived in `rest` (gxt, tiles, plan) is dead by now: the unfused weight-gradient
+  // pass of the remaining groups stages its grad_out tiles there
+  for (int o0 = 0; o0 < g.O; o0 += gsize) {
+    const Geo gc = o_group_geo(g, o0, gsize);
+    const bool data_on_umma = operand != DCN_OPERAND_FP32 || use_umma_data(g0, operand);
+    if (data_on_umma && umma_bwd_data_fuses_wgrad(gc, operand)) continue;
+    if ((rc = umma_wgrad_any(gc, operand, xt, off, (const uint8_t*)goutv + (size_t)o0 * g.HW * esz,
+                             gw + (size_t)o0 * g.K, rest, st)))
+      return rc;
+  }
+  return DCN_OK;
 }
 
 }  // namespace dcn

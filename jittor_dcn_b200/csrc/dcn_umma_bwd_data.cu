@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(256) gout_tiles_torch_kernel(const __grid_cons
     // lanes: 16 instances (one 64-byte run) x 2 channels; the instance of a thread is fixed
     const int r = tid & 15;
     const RowInfo ri = decode(P, blockIdx.x * kGtInst + r);
-    const T* src = reinterpret_cast<const T*>(P.gout) + ((size_t)ri.b * g.O + o0) * g.HW + ri.r0 +
+    const T* src = reinterpret_cast<const T*>(P.gout) + ((size_t)ri.b * g.Oimg + o0) * g.HW + ri.r0 +
                    ((size_t)ri.chunk * Gt + i0) * P.t.R;
     float* dst = gt_buf + r * kGtIS;
     const int p0 = tid >> 4;  // 0..15: (ol, i2) pairs, i2 fastest
@@ -843,7 +843,7 @@ __global__ void __launch_bounds__(256) gout_tiles_pix_kernel(Geo g, int OB, cons
   __shared__ float tile[64][129];
   const int pb = blockIdx.x, ob = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, px = tid & 127, p = pb * 128 + px;
-  const T* src = gout + ((size_t)b * g.O + ob * 64) * g.HW + p;
+  const T* src = gout + ((size_t)b * g.Oimg + ob * 64) * g.HW + p;
 #pragma unroll 8
   for (int it = 0; it < 32; ++it) {
     const int ol = (tid >> 7) + 2 * it;

@@ -272,12 +272,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         const TileRowInfo ri = decode_inst(t, tile * t.Rt + il);
         valid = ri.valid;
         const int i = ri.chunk * t.Gt + ich;
-        out_off = (size_t)ri.b * O * g.HW + (size_t)(ri.r0 + i * t.R);
+        out_off = (size_t)ri.b * g.Oimg * g.HW + (size_t)(ri.r0 + i * t.R);
         if (P.tma_out) ri0 = decode_inst(t, (tile - (tile % P.tpg)) * t.Rt);  // first instance of the group
       } else {
         const int b = tile / t.pix_blocks, p = (tile - b * t.pix_blocks) * 128 + m;
         valid = p < g.HW;
-        out_off = (size_t)b * O * g.HW + p;
+        out_off = (size_t)b * g.Oimg * g.HW + p;
       }
       mbar_wait_relaxed(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -804,7 +804,7 @@ static bool make_out_tensor_map(const Geo& g, const Tiling& t, int box_r, float*
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return false;
   const cuuint64_t dims[4] = {(cuuint64_t)t.R, (cuuint64_t)t.G, (cuuint64_t)g.O, (cuuint64_t)g.B};
-  const cuuint64_t strides[3] = {(cuuint64_t)t.R * 4, (cuuint64_t)g.HW * 4, (cuuint64_t)g.O * g.HW * 4};
+  const cuuint64_t strides[3] = {(cuuint64_t)t.R * 4, (cuuint64_t)g.HW * 4, (cuuint64_t)g.Oimg * g.HW * 4};
   const cuuint32_t box[4] = {(cuuint32_t)box_r, (cuuint32_t)t.Gt, (cuuint32_t)g.O, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -851,8 +851,10 @@ static int launch_gemm(const Geo& g, int operand, const FwdParams& P, const CUte
   return DCN_OK;
 }
 
+// stage_x = false: the head of the workspace already holds the staged copy of x (an earlier
+// output-channel group of the same call wrote it)
 int umma_forward_any(const Geo& g, int operand, const void* x, const float* off, const void* wt,
-                     const float* bias, float* out, void* workspace, cudaStream_t st) {
+                     const float* bias, float* out, void* workspace, cudaStream_t st, bool stage_x) {
   FwdParams P;
   P.g = g;
   if (!make_tiling(g, &P.t)) {
@@ -864,7 +866,7 @@ int umma_forward_any(const Geo& g, int operand, const void* x, const float* off,
   void* xt = workspace;
   uint8_t* wtiles = (uint8_t*)workspace + umma_xt_bytes(g, operand);
   int rc;
-  if ((rc = launch_nchw_to_nhwc(g, P.t, x, xt, operand, st))) return rc;
+  if (stage_x && (rc = launch_nchw_to_nhwc(g, P.t, x, xt, operand, st))) return rc;
   if ((rc = launch_weight_tiles_fwd(g, P.t, wt, wtiles, operand, st))) return rc;
   P.xt = xt;
   P.off = off;

@@ -383,3 +383,73 @@ def test_dcnv1_functional_matches_torchvision_live():
     assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < FWD_TOL
     for a, b, nm in zip(og, rg, ("gx", "goff", "gw", "gb")):
         assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < GRAD_TOL, nm
+
+
+# ---- wide layers: O > 256 runs as balanced output-channel groups (dcn_umma_host.cu) ------------
+# ResNet-50 C5 (512 -> 512 @ 14 x 14, BASELINE configs[3]) is the shape that needs it.  The Jittor and
+# DCNv1 layouts tile it on the tensor path; the Torch layout has gcd(Ho*Wo, C) = 4 there (4 channels
+# per sampling point) and runs on the generic kernels — in bf16 storage mode through widened copies.
+WIDE_CASES = [
+    # B  C    O    H   W   sigma
+    (1, 512, 512, 14, 14, 1.0),     # C5 itself
+    (2, 64,  384, 12, 16, 2.0),     # two groups of 192
+    (1, 128, 272, 10, 10, 1.5),     # two groups of 144 + 128
+    (1, 64,  768, 8,  8,  1.0),     # three groups of 256
+]
+
+
+def _wide_inputs(case, variant, bf16):
+    B, C, O, H, W, sigma = case
+    rng = np.random.default_rng(31)
+    sh = orc.make_shape(B, C, O, H, W, 3, 1, 1, variant)
+    rnd = _bf16_round if bf16 else (lambda a: a)
+    x = rnd(rng.standard_normal((B, C, H, W)).astype(np.float32))
+    off = (rng.standard_normal((B, 18, H, W)) * sigma).astype(np.float32)
+    wt = rnd((rng.standard_normal((O, C, 3, 3)) * (2.0 / (C * 9)) ** 0.5).astype(np.float32))
+    bias = rng.standard_normal(O).astype(np.float32)
+    gout = rnd(rng.standard_normal((B, O, H, W)).astype(np.float32))
+    return sh, x, off, wt, bias, gout
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+@pytest.mark.parametrize("variant", [dcn.VARIANT_TORCH, dcn.VARIANT_JITTOR, dcn.VARIANT_DCNV1])
+@pytest.mark.parametrize("case", WIDE_CASES)
+def test_wide_layer_against_oracle(case, variant, bf16):
+    import ctypes
+    sh, x, off, wt, bias, gout = _wide_inputs(case, variant, bf16)
+    operand = dcn.OPERAND_BF16 if bf16 else dcn.OPERAND_FP32
+    act = torch.bfloat16 if bf16 else torch.float32
+    if variant != dcn.VARIANT_TORCH:
+        shp = dcn.make_shape(*case[:5], 3, 1, 1, variant, operand)
+        for phase in (0, 1):
+            assert dcn.load().dcn_path_name(ctypes.byref(shp), phase) == b"umma"
+    ref_out = orc.forward(sh, x, off, wt, bias)
+    ref = orc.backward(sh, x, off, wt, gout)
+    tx, tw, tg = _cuda(x).to(act), _cuda(wt).to(act), _cuda(gout).to(act)
+    out = dcn.dcn_forward(tx, _cuda(off), tw, _cuda(bias), 3, 1, 1, variant, operand=operand)
+    got = dcn.dcn_backward(tx, _cuda(off), tw, tg, True, 3, 1, 1, variant, operand=operand)
+    assert rel_err(out.cpu().numpy(), ref_out) < (BF16_FWD_TOL if bf16 else FWD_TOL)
+    for g_, r_, nm in zip(got, ref, ("gx", "goff", "gw", "gb")):
+        assert rel_err(g_.cpu().numpy(), r_) < (BF16_GRAD_TOL if bf16 else GRAD_TOL), nm
+
+
+def test_wide_layer_staged_backward_and_flags():
+    """O = 512 through the module-level staging contract (DCN_FLAG_XT_STAGED) and grad_x accumulation."""
+    from jittor_dcn_b200.functional import staged_workspace
+    torch.manual_seed(9)
+    B, C, O, H, W = 2, 64, 512, 16, 16
+    x = torch.randn(B, C, H, W, device="cuda")
+    off = torch.randn(B, 18, H, W, device="cuda") * 1.5
+    w = torch.randn(O, C, 3, 3, device="cuda") * 0.05
+    gout = torch.randn(B, O, H, W, device="cuda")
+    for variant in (dcn.VARIANT_TORCH, dcn.VARIANT_JITTOR):
+        ws = staged_workspace(x, w, 3, 1, 1, variant)
+        assert ws is not None
+        ref_out = dcn.dcn_forward(x, off, w, None, 3, 1, 1, variant, flags=dcn.FLAG_FORCE_SIMT)
+        ref = dcn.dcn_backward(x, off, w, gout, True, 3, 1, 1, variant, flags=dcn.FLAG_FORCE_SIMT)
+        ws.fill_(0xff)
+        out = dcn.dcn_forward(x, off, w, None, 3, 1, 1, variant, ws=ws)
+        got = dcn.dcn_backward(x, off, w, gout, True, 3, 1, 1, variant, ws=ws, xt_staged=True)
+        assert rel_err(out.cpu().numpy(), ref_out.cpu().numpy()) < FWD_TOL
+        for a, b, nm in zip(got, ref, ("gx", "goff", "gw", "gb")):
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < GRAD_TOL, nm
