@@ -96,6 +96,10 @@ struct Params {
   uint32_t g_img;        // bytes of one bf16 image of the resident grad_out operand (rows x 128 B)
   uint32_t w_stage;      // bytes of one Wm^T stage (hi | lo)
   uint32_t tmem_cols;
+  // fused kernels give every CTA a FIXED slice of column blocks for all its tiles: when the slice's Wm^T
+  // images (cb_per_slice * OB stages) fit in shared memory they are loaded ONCE and stay resident instead of
+  // being re-streamed from L2 for every tile through the 2-stage ring
+  int w_resident;        // 0 = 2-stage ring, else the number of resident stages
 };
 
 struct RowInfo {
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
   uint8_t* wstage = gtile + g_zero_off + (size_t)(P.g_imgs - P.OB) * NIMG * P.g_img;
   // fused: 2 buffers of the sample operand S, each [hi | lo][128 tile rows x 64 columns], MN-major
   // (the 64 columns of a block are contiguous in a row, so a lane stores 8 columns with one STS.128)
-  uint8_t* sbuf = wstage + 2 * (size_t)P.w_stage;
+  uint8_t* sbuf = wstage + (size_t)(P.w_resident ? P.w_resident : 2) * P.w_stage;
   const uint32_t s_img = 128u * 128u, s_buf = FUSE ? NIMG * s_img : 0u;
   ScatEntry* plan = reinterpret_cast<ScatEntry*>(sbuf + 2 * (size_t)s_buf);
   uint64_t* bars = reinterpret_cast<uint64_t*>(plan + 2 * P.plan_cap);
@@ -582,7 +586,7 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
       // gW[o, cols of block] += g^T[o, 128 rows] * S[128 rows, cols]; A = the resident grad_out
       // images read MN-major (o contiguous, 64-o atoms = consecutive images), B = sample operand
       const uint32_t idesc_wj = make_idesc_bf16(128, P.o_cols > 0 ? P.o_cols : 16, false, true);
-      auto wgrad_mmas = [&](int cb, bool first) {
+      auto wgrad_mmas = [&](int cb, bool first, int gb) {
         mbar_wait_relaxed(&sfull[sb], sphase, 32);
         tc_fence_after();
         const uint32_t g_hi = smem_u32(gtile) + (uint32_t)gb * g_buf, g_lo = g_hi + P.g_img;
@@ -628,6 +632,22 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
         sb ^= 1;
         if (sb == 0) sphase ^= 1;
       };
+      if (P.w_resident && tile0 < P.num_tiles) {
+        mbar_wait_relaxed(&wfull[0], 0, 32);  // the slice's Wm^T images, loaded once
+        tc_fence_after();
+      }
+      // The weight-gradient MMAs of a block need its scatter pass finished (sfull), so they trail GEMM-1 by one
+      // block: GEMM-1 of block i + 1 is in flight while the scatter warps work on block i.  With two grad_out
+      // buffers the trailing continues across the tile boundary (a slice of ONE block per tile would otherwise
+      // serialise GEMM-1 and scatter completely); with one buffer the tile is drained before the next begins.
+      bool pend = false, pend_first = false, pend_last = false;
+      int pend_cb = 0, pend_gb = 0;
+      auto drain = [&]() {
+        if (!pend) return;
+        wgrad_mmas(pend_cb, pend_first, pend_gb);
+        if (pend_last) umma_commit(&gempty[pend_gb]);  // grad_out tile buffer may be overwritten
+        pend = false;
+      };
       for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
         mbar_wait_relaxed(&gfull[gb], gphase, 32);
         for (int cb = cb0; cb < cb1; ++cb) {
@@ -635,8 +655,12 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ncols);
           for (int ob = 0; ob < P.OB; ++ob) {
-            mbar_wait_relaxed(&wfull[s], phase, 32);
-            tc_fence_after();
+            if (P.w_resident) {
+              s = (cb - cb0) * P.OB + ob;
+            } else {
+              mbar_wait_relaxed(&wfull[s], phase, 32);
+              tc_fence_after();
+            }
             // resident converted grad_out image and streamed Wm^T image; Torch: A = grad_out rows,
             // B = Wm^T columns; Jittor: A = Wm^T lanes, B = grad_out pixels
             const uint32_t r_hi = smem_u32(gtile) + (uint32_t)gb * g_buf + (uint32_t)ob * NIMG * P.g_img;
@@ -659,24 +683,33 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
                 umma_bf16(d_tmem, dal, dbh, idesc, 1u);
               }
             }
-            umma_commit(&wempty[s]);
-            s ^= 1;
-            if (s == 0) phase ^= 1;
+            if (!P.w_resident) {
+              umma_commit(&wempty[s]);
+              s ^= 1;
+              if (s == 0) phase ^= 1;
+            }
           }
           umma_commit(&tfull[acc]);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
-          // the weight-gradient MMAs trail GEMM-1 by one block so the scatter warps never wait
-          if (FUSE && cb > cb0) wgrad_mmas(cb - 1, first_tile);
+          if (FUSE) {
+            drain();
+            pend = true;
+            pend_cb = cb;
+            pend_gb = gb;
+            pend_first = first_tile;
+            pend_last = cb == cb1 - 1;
+          }
         }
-        if (FUSE) wgrad_mmas(cb1 - 1, first_tile);
-        umma_commit(&gempty[gb]);  // grad_out tile buffer may be overwritten
+        if (!FUSE) umma_commit(&gempty[gb]);
+        else if (P.g_nbuf == 1) drain();
         if (++gb == P.g_nbuf) {
           gb = 0;
           gphase ^= 1;
         }
         first_tile = false;
       }
+      if (FUSE) drain();
       if (FUSE) umma_commit(dfull);
     }
   } else if (warp == kLoadWarp) {
@@ -684,6 +717,16 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
     if (lane == 0) {
       int s = 0;
       uint32_t phase = 0;
+      if (P.w_resident) {
+        if (tile0 < P.num_tiles) {
+          // the slice's images are contiguous in wtiles ([cb][ob] order): stage i = (cb - cb0) * OB + ob
+          const int n = (cb1 - cb0) * P.OB;
+          mbar_arrive_expect_tx(&wfull[0], (uint32_t)n * P.w_stage);
+          for (int i = 0; i < n; ++i)
+            bulk_g2s(wstage + (size_t)i * P.w_stage, P.wtiles + ((size_t)cb0 * P.OB + i) * P.w_stage, P.w_stage,
+                     &wfull[0]);
+        }
+      } else
       for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
         for (int cb = cb0; cb < cb1; ++cb)
           for (int ob = 0; ob < P.OB; ++ob) {
@@ -893,11 +936,49 @@ __global__ void __launch_bounds__(256) weight_tiles_bwd_kernel(Geo g, int ncols,
 
 }  // namespace bd
 
+// Fused kernels: CTA = (slice of the column / lane blocks, chunk of the tiles).  Slices of equal size finish
+// together: among the smallest slice counts pick the one that wastes the least (padding blocks of the last
+// slice x SMs left without a CTA; cfg2: 9 blocks -> 3 x 3, not 5 + 4).  Then the shared-memory plan: two
+// grad_out tile buffers first (the MMA issuer then runs GEMM-1 of the next tile while the weight-gradient MMAs
+// of the previous one are still waiting for its scatter pass), and the slice's Wm^T images resident when they
+// fit (loaded once instead of re-streamed from L2 for every tile).
+//   real = bytes of one grad_out tile buffer, zero = shared zero images, other = everything but the grad_out
+//   buffers and the Wm^T stages
+static void choose_slices(bd::Params* P, int max_cb, size_t real, size_t zero, size_t other) {
+  const size_t cap = 227 * 1024;
+  const bool allow_res = !getenv("DCN_BWD_NO_RESIDENT");
+  const int ns_min = (P->cblocks + max_cb - 1) / max_cb;
+  double best = 1e30;
+  for (int ns = ns_min; ns <= ns_min + 2 && ns <= P->cblocks; ++ns) {
+    const int cbp = (P->cblocks + ns - 1) / ns;
+    const int ns_eff = (P->cblocks + cbp - 1) / cbp;
+    const double waste = (double)ns_eff * cbp / P->cblocks * 148.0 / (ns_eff * (148 / ns_eff));
+    if (waste < best - 1e-9) {
+      best = waste;
+      P->nslices = ns_eff;
+      P->cb_per_slice = cbp;
+    }
+  }
+  const size_t n_res = (size_t)P->cb_per_slice * P->OB;
+  P->w_resident = 0;
+  P->g_nbuf = 1;
+  for (int gn = 2; gn >= 1; --gn)
+    for (int res = allow_res ? 1 : 0; res >= 0; --res) {
+      const size_t n_w = res ? n_res : 2;
+      if (gn * real + zero + n_w * P->w_stage + other <= cap) {
+        P->g_nbuf = gn;
+        P->w_resident = res ? (int)n_res : 0;
+        return;
+      }
+    }
+}
+
 // ---------------------------------------------------------------------------- host side
 static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow_fuse = true) {
   const size_t nimg = operand == DCN_OPERAND_BF16 ? 1 : 2;
   if (!make_tiling(g, &P->t)) return false;
   P->fuse_w = 0;
+  P->w_resident = 0;
   P->g_nbuf = 1;
   P->gw = nullptr;
   P->nslices = P->nchunks = 1;
@@ -931,7 +1012,6 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
       if (P->Rt * ncols <= bd::plan_max_of(4) && real + zero + rest <= 227 * 1024) {
         P->fuse_w = 1;
         P->g_imgs = 2;
-        P->g_nbuf = (2 * real + zero + rest <= 227 * 1024) ? 2 : 1;
         P->ncols = ncols;
         P->cblocks = (g.K + ncols - 1) / ncols;
         P->plan_cap = P->Rt * ncols;
@@ -940,20 +1020,7 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
         P->tmem_cols = 512;
         int max_cb = 6;  // 512 TMEM columns - 2 gA buffers
         if (const char* e = getenv("DCN_BWD_SLICE_CB")) max_cb = atoi(e) < 1 ? 1 : (atoi(e) > 6 ? 6 : atoi(e));
-        // slices of equal size finish together: among the smallest slice counts pick the one that wastes
-        // the least (padding blocks of the last slice x SMs left without a CTA); cfg2: 9 blocks -> 3 x 3, not 5 + 4
-        const int ns_min = (P->cblocks + max_cb - 1) / max_cb;
-        double best = 1e30;
-        for (int ns = ns_min; ns <= ns_min + 2 && ns <= P->cblocks; ++ns) {
-          const int cbp = (P->cblocks + ns - 1) / ns;
-          const int ns_eff = (P->cblocks + cbp - 1) / cbp;
-          const double waste = (double)ns_eff * cbp / P->cblocks * 148.0 / (ns_eff * (148 / ns_eff));
-          if (waste < best - 1e-9) {
-            best = waste;
-            P->nslices = ns_eff;
-            P->cb_per_slice = cbp;
-          }
-        }
+        choose_slices(P, max_cb, real, zero, rest - 2 * (size_t)P->w_stage);
         return true;
       }
     }
@@ -991,7 +1058,6 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
     if (taps * ncols <= bd::plan_max_of(4) && real + rest <= 227 * 1024 && max_cb >= 1) {
       P->fuse_w = 1;
       P->o_cols = o_cols;
-      P->g_nbuf = (2 * real + rest <= 227 * 1024) ? 2 : 1;
       P->ncols = ncols;
       P->pix_blocks = (g.HW + ncols - 1) / ncols;
       P->num_tiles = g.B * P->pix_blocks;
@@ -1000,18 +1066,7 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
       P->g_img = (uint32_t)ncols * 128;
       P->w_stage = (uint32_t)nimg * 128 * 128;
       P->tmem_cols = 512;
-      const int ns_min = (P->cblocks + max_cb - 1) / max_cb;
-      double best = 1e30;
-      for (int ns = ns_min; ns <= ns_min + 2 && ns <= P->cblocks; ++ns) {
-        const int cbp = (P->cblocks + ns - 1) / ns;
-        const int ns_eff = (P->cblocks + cbp - 1) / cbp;
-        const double waste = (double)ns_eff * cbp / P->cblocks * 148.0 / (ns_eff * (148 / ns_eff));
-        if (waste < best - 1e-9) {
-          best = waste;
-          P->nslices = ns_eff;
-          P->cb_per_slice = cbp;
-        }
-      }
+      choose_slices(P, max_cb, real, 0, rest - 2 * (size_t)P->w_stage);
       return true;
     }
   }
@@ -1176,7 +1231,8 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
   P.scale_ix = g.variant == DCN_VARIANT_DCNV1 ? 1.f : g.sx * 2.0f / g.Dy;
   if (const char* e = getenv("DCN_BWD_GBUF"))
     if (atoi(e) == 1) P.g_nbuf = 1;
-  const size_t smem = ((size_t)P.g_nbuf * P.OB + (P.g_imgs - P.OB)) * nimg * P.g_img + 2 * (size_t)P.w_stage +
+  const size_t smem = ((size_t)P.g_nbuf * P.OB + (P.g_imgs - P.OB)) * nimg * P.g_img +
+                      (size_t)(P.w_resident ? P.w_resident : 2) * P.w_stage +
                       (P.fuse_w ? 2 * nimg * (size_t)(128 * 128) : 0) +
                       2 * (size_t)P.plan_cap * sizeof(bd::ScatEntry) + 256 + 1024;
   int dev = 0, sms = 148;
