@@ -99,7 +99,9 @@ struct Params {
   // fused kernels give every CTA a FIXED slice of column blocks for all its tiles: when the slice's Wm^T
   // images (cb_per_slice * OB stages) fit in shared memory they are loaded ONCE and stay resident instead of
   // being re-streamed from L2 for every tile through the 2-stage ring
-  int w_resident;        // 0 = 2-stage ring, else the number of resident stages
+  int w_resident;        // 0 = ring of w_ring stages, else the number of resident stages
+  int w_ring;            // 2, or 1 when only that leaves room for the second grad_out buffer (the loads of the
+                         // next block then serialise with its MMAs, but both hide behind the previous scatter pass)
 };
 
 struct RowInfo {
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
   uint8_t* wstage = gtile + g_zero_off + (size_t)(P.g_imgs - P.OB) * NIMG * P.g_img;
   // fused: 2 buffers of the sample operand S, each [hi | lo][128 tile rows x 64 columns], MN-major
   // (the 64 columns of a block are contiguous in a row, so a lane stores 8 columns with one STS.128)
-  uint8_t* sbuf = wstage + (size_t)(P.w_resident ? P.w_resident : 2) * P.w_stage;
+  uint8_t* sbuf = wstage + (size_t)(P.w_resident ? P.w_resident : P.w_ring) * P.w_stage;
   const uint32_t s_img = 128u * 128u, s_buf = FUSE ? NIMG * s_img : 0u;
   ScatEntry* plan = reinterpret_cast<ScatEntry*>(sbuf + 2 * (size_t)s_buf);
   uint64_t* bars = reinterpret_cast<uint64_t*>(plan + 2 * P.plan_cap);
@@ -211,6 +213,13 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
   uint64_t* sempty = bars + 18;  // [2]
   uint64_t* dfull = bars + 20;   // [1] weight-gradient accumulators final
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  {
+    // the host sizes the allocation with little alignment slack when shared memory is tight: fail loudly
+    // rather than run past the end
+    uint32_t dyn;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    if (smem_u32(tmem_slot + 1) - smem_u32(smem_raw) > dyn) __trap();
+  }
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ncols = P.ncols;
@@ -685,8 +694,10 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
             }
             if (!P.w_resident) {
               umma_commit(&wempty[s]);
-              s ^= 1;
-              if (s == 0) phase ^= 1;
+              if (++s == P.w_ring) {
+                s = 0;
+                phase ^= 1;
+              }
             }
           }
           umma_commit(&tfull[acc]);
@@ -734,8 +745,10 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
             mbar_arrive_expect_tx(&wfull[s], P.w_stage);
             bulk_g2s(wstage + (size_t)s * P.w_stage, P.wtiles + (size_t)(cb * P.OB + ob) * P.w_stage,
                      P.w_stage, &wfull[s]);
-            s ^= 1;
-            if (s == 0) phase ^= 1;
+            if (++s == P.w_ring) {
+              s = 0;
+              phase ^= 1;
+            }
           }
       }
     } else if (lane == 1) {
@@ -960,17 +973,21 @@ static void choose_slices(bd::Params* P, int max_cb, size_t real, size_t zero, s
     }
   }
   const size_t n_res = (size_t)P->cb_per_slice * P->OB;
-  P->w_resident = 0;
-  P->g_nbuf = 1;
-  for (int gn = 2; gn >= 1; --gn)
-    for (int res = allow_res ? 1 : 0; res >= 0; --res) {
-      const size_t n_w = res ? n_res : 2;
-      if (gn * real + zero + n_w * P->w_stage + other <= cap) {
-        P->g_nbuf = gn;
-        P->w_resident = res ? (int)n_res : 0;
-        return;
-      }
+  // plans in order of preference: {grad_out buffers, resident?, ring stages}.  The 1-stage ring is taken only
+  // to make room for the second grad_out buffer; its budget counts 256 instead of 1024 bytes of alignment slack
+  // (the dynamic shared-memory window starts 1 KB-aligned in practice; the kernel traps if it would overrun).
+  const int plans[5][3] = {{2, 1, 2}, {2, 0, 2}, {2, 0, 1}, {1, 1, 2}, {1, 0, 2}};
+  for (const auto& pl : plans) {
+    if (pl[1] && !allow_res) continue;
+    const size_t n_w = pl[1] ? n_res : (size_t)pl[2];
+    const size_t need = pl[0] * real + zero + n_w * P->w_stage + other;
+    if (need <= cap || (pl[2] == 1 && need - 768 <= cap && !getenv("DCN_BWD_NO_RING1"))) {
+      P->g_nbuf = pl[0];
+      P->w_resident = pl[1] ? (int)n_res : 0;
+      P->w_ring = pl[2];
+      return;
     }
+  }
 }
 
 // ---------------------------------------------------------------------------- host side
@@ -979,6 +996,7 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
   if (!make_tiling(g, &P->t)) return false;
   P->fuse_w = 0;
   P->w_resident = 0;
+  P->w_ring = 2;
   P->g_nbuf = 1;
   P->gw = nullptr;
   P->nslices = P->nchunks = 1;
@@ -1231,10 +1249,11 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
   P.scale_ix = g.variant == DCN_VARIANT_DCNV1 ? 1.f : g.sx * 2.0f / g.Dy;
   if (const char* e = getenv("DCN_BWD_GBUF"))
     if (atoi(e) == 1) P.g_nbuf = 1;
-  const size_t smem = ((size_t)P.g_nbuf * P.OB + (P.g_imgs - P.OB)) * nimg * P.g_img +
-                      (size_t)(P.w_resident ? P.w_resident : 2) * P.w_stage +
-                      (P.fuse_w ? 2 * nimg * (size_t)(128 * 128) : 0) +
-                      2 * (size_t)P.plan_cap * sizeof(bd::ScatEntry) + 256 + 1024;
+  size_t smem = ((size_t)P.g_nbuf * P.OB + (P.g_imgs - P.OB)) * nimg * P.g_img +
+                (size_t)(P.w_resident ? P.w_resident : P.w_ring) * P.w_stage +
+                (P.fuse_w ? 2 * nimg * (size_t)(128 * 128) : 0) +
+                2 * (size_t)P.plan_cap * sizeof(bd::ScatEntry) + 256 + 1024;
+  if (smem > 227 * 1024) smem = 227 * 1024;  // tight plan (choose_slices): less alignment slack, checked in the kernel
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
