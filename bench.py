@@ -75,6 +75,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--force-simt", action="store_true")
+    ap.add_argument("--stock-bn", action="store_true",
+                    help="detector workload: the framework's BatchNorm2d + ReLU instead of the engine's fused post-op")
     return ap.parse_args()
 
 
@@ -256,7 +258,7 @@ def run_detector(args):
     B = b1 - b0
     torch.manual_seed(0)                                   # replicated weights
     cls = dcn.TorchDeformConv2d if args.variant == "torch" else dcn.TorchDeformConv2dJittorSemantics
-    model = EDNetDetection(dcn_cls=cls).to(dev)
+    model = EDNetDetection(dcn_cls=cls, fused_bn_relu=not args.stock_bn).to(dev)
     with torch.no_grad():                                  # live offsets (the reference starts at zero)
         for m in model.modules():
             if isinstance(m, dcn.TorchDeformConv2d):
@@ -324,6 +326,8 @@ def run_detector(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": DETECTOR_DESC, "variant": args.variant, "global_batch": args.global_batch,
                        "batch_per_gpu": B, "parallelism": f"dp{world}",
+                       "post_op": ("framework BatchNorm2d + ReLU (cuDNN)" if args.stock_bn else
+                                   "relu(bn(x)) on the engine (dcn_bn_relu_forward / _backward)"),
                        "allreduce": "dcn_allreduce_sum_f32 (NCCL, one flat bucket of %d floats)" % bucket.numel
                        if world > 1 else "none",
                        "l2": "per-step activations (%.0f MB for conv2's input alone) exceed the 126 MB L2" %

@@ -158,6 +158,25 @@ DCN_API int dcn_backward(const DcnShape* s, const void* x, const void* offset, c
 DCN_API int dcn_debug_corners(const DcnShape* s, const void* offset, int32_t* y0, int32_t* x0,
                       float* w4, void* stream);
 
+/* ---- post-op: BatchNorm2d + ReLU ------------------------------------------
+ * Replaces `relu(bn(x))` after every DeformConv2d layer of the reference's detector (modules
+ * train.py:146-159 / 311-322, call sites train.py:167-170 / 329-332): nn.BatchNorm2d semantics
+ * (biased batch variance normalises, unbiased variance updates running_var, momentum as in torch)
+ * with the ReLU fused on both sides.  NCHW float32, HW = H*W.  Every channel is split over many
+ * CTAs (the framework kernels run one CTA per channel).
+ *   gamma, beta   [C] or NULL (= 1, 0)      running_mean/var [C], updated in training mode, read in
+ *   saved         4*C floats, written by the forward pass and handed to the backward pass       eval mode
+ *   workspace     dcn_bn_workspace_bytes(C) bytes of caller-owned scratch                          */
+DCN_API size_t dcn_bn_workspace_bytes(int32_t C);
+DCN_API int dcn_bn_relu_forward(int32_t B, int32_t C, int32_t HW, int32_t training, const void* x,
+                        const void* gamma, const void* beta, void* running_mean, void* running_var,
+                        float momentum, float eps, void* y, void* saved, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* grad_x may be NULL (first layer); grad_gamma / grad_beta [C] or NULL. */
+DCN_API int dcn_bn_relu_backward(int32_t B, int32_t C, int32_t HW, int32_t training, const void* x,
+                         const void* grad_y, const void* saved, void* grad_x, void* grad_gamma,
+                         void* grad_beta, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- data-parallel helpers (one process per GPU; NCCL over NVLink) --------------------
  * NCCL is dlopen'ed on first use; the core library has no link-time dependency on it.   */
 DCN_API int dcn_comm_unique_id(void* out128_host);                     /* 128-byte ncclUniqueId  */

@@ -25,7 +25,7 @@ EXPORTS = (
     "dcn_path_name", "dcn_launch_count", "dcn_launch_count_reset", "dcn_profile_begin",
     "dcn_profile_end", "dcn_forward", "dcn_backward",
     "dcn_debug_corners", "dcn_comm_unique_id", "dcn_comm_init", "dcn_allreduce_sum_f32",
-    "dcn_comm_destroy",
+    "dcn_comm_destroy", "dcn_bn_workspace_bytes", "dcn_bn_relu_forward", "dcn_bn_relu_backward",
 )
 
 
@@ -74,6 +74,11 @@ def load():
     lib.dcn_comm_init.argtypes = [ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(vp)]
     lib.dcn_allreduce_sum_f32.argtypes = [vp, vp, sz, ctypes.c_float, vp]
     lib.dcn_comm_destroy.argtypes = [vp]
+    i32, f32 = ctypes.c_int32, ctypes.c_float
+    lib.dcn_bn_workspace_bytes.restype = sz
+    lib.dcn_bn_workspace_bytes.argtypes = [i32]
+    lib.dcn_bn_relu_forward.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, sz, vp]
+    lib.dcn_bn_relu_backward.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     _lib = lib
     return lib
 

@@ -100,6 +100,21 @@ static size_t simt_workspace(const Geo& g, int operand, int phase) {
   return b;
 }
 
+size_t bn_workspace_bytes(int C);
+int bn_relu_forward(int B, int C, int HW, int training, const float* x, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps, float* y, float* saved,
+                    void* workspace, cudaStream_t st);
+int bn_relu_backward(int B, int C, int HW, int training, const float* x, const float* grad_y, const float* saved,
+                     float* grad_x, float* grad_gamma, float* grad_beta, void* workspace, cudaStream_t st);
+
+static int bn_shape_ok(int B, int C, int HW) {
+  if (B <= 0 || C <= 0 || HW <= 0 || (long long)B * C * HW > (1LL << 40) || (long long)B * HW > 0x7fffffffLL) {
+    set_error("bad batch-norm shape B=%d C=%d HW=%d", B, C, HW);
+    return DCN_ERR_BAD_SHAPE;
+  }
+  return DCN_OK;
+}
+
 static bool use_umma(const DcnShape* s, const Geo& g, int phase) {
   if (s->flags & DCN_FLAG_FORCE_SIMT) return false;
   return umma_supported(g, s->operand, phase);
@@ -286,6 +301,45 @@ int dcn_debug_corners(const DcnShape* s, const void* offset, int32_t* y0, int32_
       (rc = check_ptr(x0, "x0")) || (rc = check_ptr(w4, "w4")))
     return rc;
   return launch_corners(g, (const float*)offset, y0, x0, w4, (cudaStream_t)stream);
+}
+
+size_t dcn_bn_workspace_bytes(int32_t C) { return C > 0 ? bn_workspace_bytes(C) : 0; }
+
+int dcn_bn_relu_forward(int32_t B, int32_t C, int32_t HW, int32_t training, const void* x, const void* gamma,
+                        const void* beta, void* running_mean, void* running_var, float momentum, float eps,
+                        void* y, void* saved, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = bn_shape_ok(B, C, HW);
+  if (rc) return rc;
+  if ((rc = check_ptr(x, "x")) || (rc = check_ptr(y, "y")) || (rc = check_ptr(saved, "saved")) ||
+      (rc = check_ptr(workspace, "workspace")))
+    return rc;
+  if (!training && (!running_mean || !running_var)) {
+    set_error("eval-mode batch norm needs running_mean and running_var");
+    return DCN_ERR_NULL_POINTER;
+  }
+  if (workspace_bytes < bn_workspace_bytes(C)) {
+    set_error("batch-norm workspace: have %zu bytes, need %zu", workspace_bytes, bn_workspace_bytes(C));
+    return DCN_ERR_WORKSPACE;
+  }
+  return bn_relu_forward(B, C, HW, training, (const float*)x, (const float*)gamma, (const float*)beta,
+                         (float*)running_mean, (float*)running_var, momentum, eps, (float*)y, (float*)saved,
+                         workspace, (cudaStream_t)stream);
+}
+
+int dcn_bn_relu_backward(int32_t B, int32_t C, int32_t HW, int32_t training, const void* x, const void* grad_y,
+                         const void* saved, void* grad_x, void* grad_gamma, void* grad_beta, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  int rc = bn_shape_ok(B, C, HW);
+  if (rc) return rc;
+  if ((rc = check_ptr(x, "x")) || (rc = check_ptr(grad_y, "grad_y")) || (rc = check_ptr(saved, "saved")) ||
+      (rc = check_ptr(workspace, "workspace")))
+    return rc;
+  if (workspace_bytes < bn_workspace_bytes(C)) {
+    set_error("batch-norm workspace: have %zu bytes, need %zu", workspace_bytes, bn_workspace_bytes(C));
+    return DCN_ERR_WORKSPACE;
+  }
+  return bn_relu_backward(B, C, HW, training, (const float*)x, (const float*)grad_y, (const float*)saved,
+                          (float*)grad_x, (float*)grad_gamma, (float*)grad_beta, workspace, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -7,30 +7,35 @@ that its checkpoints (train.py:293, test.py:17-22) load unchanged.
 import torch
 import torch.nn as nn
 
-from .torch_module import TorchDeformConv2d
+from .torch_module import BatchNormReLU2d, TorchDeformConv2d
 
 # (name suffix, in, out) of the stride-2 DCN stages, train.py:149-158
 _DCN_STAGES = ((2, 16, 32), (3, 32, 64), (4, 64, 128), (5, 128, 256))
 
 
 class EDNetDetection(nn.Module):
-    def __init__(self, num_classes=10, groups=2, dcn_cls=TorchDeformConv2d):
+    def __init__(self, num_classes=10, groups=2, dcn_cls=TorchDeformConv2d, fused_bn_relu=True):
         super().__init__()
+        # fused_bn_relu: relu(bn(x)) as ONE engine op (BatchNormReLU2d, same state-dict keys as nn.BatchNorm2d);
+        # False keeps the framework's BatchNorm2d + ReLU as the reference has them
+        self.fused_bn_relu = fused_bn_relu
+        bn_cls = BatchNormReLU2d if fused_bn_relu else nn.BatchNorm2d
         del groups  # dead argument in the reference too (train.py:143,145)
         self.conv1 = nn.Conv2d(1, 16, 3, 1, 1)
-        self.bn1 = nn.BatchNorm2d(16)
+        self.bn1 = bn_cls(16)
         self.relu = nn.ReLU(inplace=True)
         for idx, cin, cout in _DCN_STAGES:
             setattr(self, f"conv{idx}", dcn_cls(cin, cout, 3, 2, 1))
-            setattr(self, f"bn{idx}", nn.BatchNorm2d(cout))
+            setattr(self, f"bn{idx}", bn_cls(cout))
         self.gap = nn.AdaptiveAvgPool2d(1)
         self.fc_cls = nn.Linear(256, num_classes)
         self.fc_bbox = nn.Linear(256, 4)
 
     def forward(self, x):
-        x = self.relu(self.bn1(self.conv1(x)))
+        act = (lambda t: t) if self.fused_bn_relu else self.relu
+        x = act(self.bn1(self.conv1(x)))
         for idx, _, _ in _DCN_STAGES:
-            x = self.relu(getattr(self, f"bn{idx}")(getattr(self, f"conv{idx}")(x)))
+            x = act(getattr(self, f"bn{idx}")(getattr(self, f"conv{idx}")(x)))
         feat = self.gap(x).flatten(1)
         return self.fc_cls(feat), torch.sigmoid(self.fc_bbox(feat))
 

@@ -224,3 +224,67 @@ def deform_conv2d_v1(input, offset, weight, bias=None, stride=1, padding=0):
     coordinate generator.  Differentiable in input, offset, weight and bias."""
     kernel_size = (int(weight.shape[2]), int(weight.shape[3]))
     return deform_conv2d(input, offset, weight, bias, kernel_size, stride, padding, variant=VARIANT_DCNV1)
+
+
+# ---- post-op: BatchNorm2d + ReLU (SURVEY 8f.2; train.py:167-170) -------------------------------------
+class BatchNormReLUFunction(torch.autograd.Function):
+    """relu(batch_norm(x)) on the engine's own kernels (csrc/dcn_bn.cu).  running_mean / running_var are
+    updated in place in training mode, exactly as nn.BatchNorm2d does."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps):
+        lib = _lib.load()
+        home = x.device
+        dev = _compute_device(x)
+        xd = _dev_ready(_to_device(x, dev))
+        B, C = xd.shape[0], xd.shape[1]
+        HW = xd.numel() // (B * C)
+        wd, bd = _dev_ready(_to_device(weight, dev)), _dev_ready(_to_device(bias, dev))
+        rm, rv = _to_device(running_mean, dev), _to_device(running_var, dev)
+        y = torch.empty_like(xd)
+        saved = torch.empty(4 * C, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            need = lib.dcn_bn_workspace_bytes(C)
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            rc = lib.dcn_bn_relu_forward(B, C, HW, 1 if training else 0, _ptr(xd), _ptr(wd), _ptr(bd), _ptr(rm),
+                                         _ptr(rv), float(momentum), float(eps), _ptr(y), _ptr(saved), _ptr(ws),
+                                         ws.numel(), ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "dcn_bn_relu_forward")
+        if training and running_mean is not None and rm is not running_mean:
+            running_mean.copy_(rm)       # host-resident module: write the updated statistics back
+            running_var.copy_(rv)
+        ctx.save_for_backward(xd, saved)
+        ctx.training, ctx.home = bool(training), home
+        ctx.has_affine = (weight is not None, bias is not None)
+        return y if home == dev else y.to(home)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        lib = _lib.load()
+        xd, saved = ctx.saved_tensors
+        dev = xd.device
+        B, C = xd.shape[0], xd.shape[1]
+        HW = xd.numel() // (B * C)
+        gy = _dev_ready(_to_device(grad_y, dev))
+        gx = torch.empty_like(xd) if ctx.needs_input_grad[0] else None
+        gg = torch.empty(C, dtype=torch.float32, device=dev) if ctx.has_affine[0] else None
+        gb = torch.empty(C, dtype=torch.float32, device=dev) if ctx.has_affine[1] else None
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            ws = torch.empty(lib.dcn_bn_workspace_bytes(C), dtype=torch.uint8, device=dev)
+            rc = lib.dcn_bn_relu_backward(B, C, HW, 1 if ctx.training else 0, _ptr(xd), _ptr(gy), _ptr(saved),
+                                          _ptr(gx), _ptr(gg), _ptr(gb), _ptr(ws), ws.numel(),
+                                          ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "dcn_bn_relu_backward")
+        home = ctx.home
+
+        def back(t):
+            return t if t is None or home == dev else t.to(home)
+
+        return back(gx), back(gg), back(gb), None, None, None, None, None
+
+
+def batch_norm_relu(x, weight, bias, running_mean, running_var, training, momentum=0.1, eps=1e-5):
+    """relu(F.batch_norm(x, running_mean, running_var, weight, bias, training, momentum, eps)) for NCHW float32."""
+    return BatchNormReLUFunction.apply(x, weight, bias, running_mean, running_var, training, momentum, eps)

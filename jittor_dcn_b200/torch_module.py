@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import deform_conv2d
+from .functional import batch_norm_relu, deform_conv2d
 
 
 class TorchDeformConv2d(nn.Module):
@@ -60,3 +60,27 @@ class TorchDeformConv2dJittorSemantics(TorchDeformConv2d):
     """PyTorch-hosted module with the Jittor operator's semantics (deform_conv.py:56-81):
     normalisation by the OUTPUT extent and (n, c)-ordered columns."""
     variant = _lib.VARIANT_JITTOR
+
+
+class BatchNormReLU2d(nn.BatchNorm2d):
+    """`relu(bn(x))` of the reference's detector (train.py:167-170, 329-332) as one module: the parameters,
+    buffers and state-dict keys of ``nn.BatchNorm2d`` (``weight``, ``bias``, ``running_mean``, ``running_var``,
+    ``num_batches_tracked``), evaluated by the engine's batch-norm kernels with the ReLU fused.
+    The framework's kernels run one CTA per channel and take most of the detector step on B200."""
+
+    def forward(self, x):
+        if x.dim() != 4 or x.dtype != torch.float32:
+            raise ValueError("BatchNormReLU2d expects a float32 NCHW tensor")
+        use_batch_stats = self.training or not self.track_running_stats
+        if use_batch_stats and x.numel() // x.shape[1] == 1:
+            # same refusal as nn.BatchNorm2d (torch.nn.functional._verify_batch_size)
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {x.size()}")
+        momentum = 0.0 if self.momentum is None else self.momentum
+        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+            if self.momentum is None:
+                momentum = 1.0 / float(self.num_batches_tracked)
+        return batch_norm_relu(x, self.weight, self.bias,
+                               self.running_mean if self.track_running_stats else None,
+                               self.running_var if self.track_running_stats else None,
+                               use_batch_stats, momentum, self.eps)
