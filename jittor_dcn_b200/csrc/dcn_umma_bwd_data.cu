@@ -134,7 +134,7 @@ __device__ __forceinline__ void plan_prepare(const Params& P, int tile, int cb, 
   uint32_t p, n, h, w;
   int b;
   if (VARIANT == DCN_VARIANT_TORCH) {
-    const int il = e / P.ncols, cc = e - il * P.ncols, j = cb * P.ncols + cc;
+    const int il = e >> (P.ncols == 128 ? 7 : 6), cc = e & (P.ncols - 1), j = cb * P.ncols + cc;  // ncols = 64 | 128
     const RowInfo ri = decode(P, tile * P.Rt + il);
     if (!ri.valid || j >= g.K) return;
     uint32_t cbase, q;
@@ -144,10 +144,10 @@ __device__ __forceinline__ void plan_prepare(const Params& P, int tile, int cb, 
     b = ri.b;
   } else {
     // entry (tap slot tl of lane block cb, pixel column cc)
-    const int tl = e / P.ncols, cc = e - tl * P.ncols;
+    const int tl = e >> (P.ncols == 128 ? 7 : 6), cc = e & (P.ncols - 1);
     b = tile / P.pix_blocks;
     p = (uint32_t)((tile - b * P.pix_blocks) * P.ncols + cc);
-    n = (uint32_t)((cb * 128) / g.C + tl);
+    n = P.t.divC.div((uint32_t)(cb * 128)) + (uint32_t)tl;
     if ((int)p >= g.HW || (int)n >= g.N) return;
   }
   P.t.divWo.divmod(p, h, w);

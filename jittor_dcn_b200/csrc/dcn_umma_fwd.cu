@@ -74,6 +74,11 @@ struct FwdParams {
   // instances) in shared memory as [o][i][r] and ONE tensor-map store writes the 16-byte runs.
   int tma_out, tpg, box_r, n_ost;  // n_ost = 1 or 2 staging buffers
   uint32_t stage_out_bytes;         // of ONE staging buffer
+  // Pixel-row layouts, forward: the K blocks of a tile are (tap, 64-channel slab) pairs, stored tap-major.
+  // With kperm_slabs = C / 64 > 1 they are WALKED slab-major (step i -> tap i % N of slab i / N): consecutive
+  // steps then gather the same 64 channels around the same pixels (only the tap's offset differs), so the
+  // corner lines of one step are L1 hits of the next.  The accumulation order over K is irrelevant.
+  int kperm_slabs;
 };
 
 // One plan entry in the making: the index math is done and the two offset loads are in
@@ -94,7 +99,9 @@ __device__ __forceinline__ void plan_prepare(const Geo& g, const Tiling& t, cons
     // Rt <= 4: entries are instance-interleaved (e = kk * Rt + il) so that the entries a warp reads
     // together sit next to each other in shared memory, i.e. in different banks; Rt = 8 keeps the
     // instance-major order (e = il * 64 + kk), which measured faster there
-    const int kk = t.Rt <= 4 ? e / t.Rt : (e & 63), il = t.Rt <= 4 ? e - kk * t.Rt : (e >> 6), j = kb * 64 + kk;
+    // (Rt is a power of two)
+    const int sh = t.Rt == 4 ? 2 : 1;
+    const int kk = t.Rt <= 4 ? (e >> sh) : (e & 63), il = t.Rt <= 4 ? (e & (t.Rt - 1)) : (e >> 6), j = kb * 64 + kk;
     const TileRowInfo ri = decode_inst(t, tile * t.Rt + il);
     if (!ri.valid || j >= g.K) return;
     uint32_t cb, q, pp, nn;
@@ -108,7 +115,7 @@ __device__ __forceinline__ void plan_prepare(const Geo& g, const Tiling& t, cons
     const int tl = e >> 7, m = e & 127;
     b = tile / t.pix_blocks;
     p = (tile - b * t.pix_blocks) * 128 + m;
-    n = (kb * 64) / g.C + tl;
+    n = (int)t.divC.div((uint32_t)(kb * 64)) + tl;
     if (p >= g.HW || n >= g.N) return;
   }
   uint32_t h, w;
@@ -215,6 +222,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
   const bool pairs = MODE == MODE_FWD && P.tpg == 2;
   auto next_tile = [&](int tile) {
     return pairs ? ((tile & 1) ? tile + 2 * (int)gridDim.x - 1 : tile + 1) : tile + tile_step;
+  };
+  // step of the K loop -> K block (see FwdParams::kperm_slabs)
+  auto kb_of = [&](int i) {
+    if (MODE != MODE_FWD || P.kperm_slabs <= 1) return i;
+    uint32_t slab, tap;
+    t.divN.divmod((uint32_t)i, slab, tap);
+    return (int)(tap * (uint32_t)P.kperm_slabs + slab);
   };
 
   if (tid == 0) {
@@ -506,7 +520,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
           mbar_wait_relaxed(&empty[s], phase ^ 1);
           uint8_t* dst = stage_base + (size_t)s * P.stage_bytes + NIMG * kATile;
           mbar_arrive_expect_tx(&full[s], NIMG * P.b_tile);
-          bulk_g2s(dst, P.wtiles + (size_t)kb * NIMG * P.b_tile, NIMG * P.b_tile, &full[s]);
+          bulk_g2s(dst, P.wtiles + (size_t)kb_of(kb) * NIMG * P.b_tile, NIMG * P.b_tile, &full[s]);
           if (++s == P.stages) {
             s = 0;
             phase ^= 1;
@@ -525,7 +539,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
       for (int u = 0; u < kPlanPerThread; ++u)
         if (pt + u * kPlanThreads < n_ent)
-          plan_prepare<VARIANT>(g, t, P.off, tile0, kb0, pt + u * kPlanThreads, pw[u]);
+          plan_prepare<VARIANT>(g, t, P.off, tile0, kb_of(kb0), pt + u * kPlanThreads, pw[u]);
     }
     for (int tile = tile0; tile < t.num_tiles; tile = next_tile(tile)) {
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -547,7 +561,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
           for (int u = 0; u < kPlanPerThread; ++u)
             if (pt + u * kPlanThreads < n_ent)
-              plan_prepare<VARIANT>(g, t, P.off, ntile, nkb, pt + u * kPlanThreads, pw[u]);
+              plan_prepare<VARIANT>(g, t, P.off, ntile, kb_of(nkb), pt + u * kPlanThreads, pw[u]);
         }
         pbuf ^= 1;
         if (pbuf == 0) pphase ^= 1;
@@ -598,6 +612,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     struct Pos {
       int tile, kb, s, pbuf;
       uint32_t phase, pphase;
+      int kbm;  // the K block this step works on: kb_of(kb)
     };
     auto advance = [&](Pos& q) {
       if (++q.kb == kb1) {
@@ -610,6 +625,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       }
       q.pbuf ^= 1;
       if (q.pbuf == 0) q.pphase ^= 1;
+      q.kbm = kb_of(q.kb);
     };
     const XT* img[kIt];  // load side: image base (+ channel group) of each item's rows
     auto set_images = [&](int tile) {
@@ -623,10 +639,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
     };
     // Jittor layout: channel offset / tap slot of this thread's V columns inside K block kb
     auto jit_cols = [&](int kb, int& c, int& tl, bool& ok) {
+      // (multiply-high division: this runs twice per gather item, a hardware-less `/` cost 12 % of the
+      // bf16 forward kernel's issue slots)
       const int j = kb * 64 + grp * V;
-      const int n = j / g.C;
+      const int n = (int)t.divC.div((uint32_t)j);
       c = j - n * g.C;
-      tl = n - (kb * 64) / g.C;
+      tl = n - (int)t.divC.div((uint32_t)(kb * 64));
       ok = j < g.K;
     };
     uint4 v[2][4];  // [buffer][corner], 16 raw bytes each
@@ -635,7 +653,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       int jc = 0, tl = 0;
       bool ok = true;
       if (VARIANT != DCN_VARIANT_TORCH) {
-        jit_cols(q.kb, jc, tl, ok);
+        jit_cols(q.kbm, jc, tl, ok);
         pl += tl * 128;
       }
       const int4 off = *reinterpret_cast<const int4*>(pl[ent_idx[it]].off);
@@ -660,7 +678,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       return fmaf(__uint_as_float(a3), w.w,
                   fmaf(__uint_as_float(a2), w.z, fmaf(__uint_as_float(a1), w.y, __uint_as_float(a0) * w.x)));
     };
-    Pos cur{tile0, kb0, 0, 0, 0u, 0u};
+    Pos cur{tile0, kb0, 0, 0, 0u, 0u, kb_of(kb0)};
     if (cur.tile < t.num_tiles) {
       set_images(cur.tile);
       mbar_wait(&pfull[cur.pbuf], cur.pphase);
@@ -674,7 +692,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
       bool col_ok = true;
       if (VARIANT != DCN_VARIANT_TORCH) {
         int jc, tl;
-        jit_cols(cur.kb, jc, tl, col_ok);
+        jit_cols(cur.kbm, jc, tl, col_ok);
         pl += tl * 128;
       }
       uint8_t* a_hi = stage_base + (size_t)cur.s * P.stage_bytes;
@@ -828,6 +846,7 @@ static void common_params(const Geo& g, FwdParams& P) {
   P.n_ost = 1;
   P.box_r = 0;
   P.stage_out_bytes = 0;
+  P.kperm_slabs = 0;
 }
 
 template <int MODE>
@@ -909,6 +928,9 @@ int umma_forward_any(const Geo& g, int operand, const void* x, const float* off,
     return DCN_ERR_UNSUPPORTED;
   }
   P.tmem_cols = pow2_cols(2 * g.O);
+  if (g.variant != DCN_VARIANT_TORCH && g.C % 64 == 0 && g.C > 64 && P.t.KB == g.N * (g.C / 64) &&
+      !getenv("DCN_FWD_NO_KPERM"))
+    P.kperm_slabs = g.C / 64;
   const size_t smem = (size_t)P.stages * P.stage_bytes + fixed;
   const int sms = num_sms();
   const int groups = (P.t.num_tiles + P.tpg - 1) / P.tpg;  // CTAs walk groups of tpg tiles
