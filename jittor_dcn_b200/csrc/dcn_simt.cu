@@ -404,7 +404,8 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(Geo g, int b_per_block, 
                                                         float* __restrict__ gb) {
   const int o = blockIdx.x, b0 = blockIdx.y * b_per_block, b1 = min(g.B, b0 + b_per_block);
   float s = 0.f;
-  const bool vec = sizeof(T) == 4 && (g.HW & 3) == 0;
+  // 4 elements per load: one float4, or 4 bfloat16 in 8 bytes
+  const bool vec = (g.HW & 3) == 0;
   // the (batch element, pixel) pairs of this block's slice are walked as ONE flat index space, so that small
   // planes (8 x 8 pixels in the detector's last layer) keep all 256 threads busy
   const int per_b = vec ? (g.HW >> 2) : g.HW, total = (b1 - b0) * per_b;
@@ -412,9 +413,13 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(Geo g, int b_per_block, 
   const T* base = gout + ((size_t)b0 * g.O + o) * g.HW;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int b = i / per_b, r = i - b * per_b;
-    if (vec) {
+    if (vec && sizeof(T) == 4) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)b * b_stride) + r);
       s += (v.x + v.y) + (v.z + v.w);
+    } else if (vec) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(base + (size_t)b * b_stride) + r);
+      s += (__uint_as_float(v.x << 16) + __uint_as_float(v.x & 0xffff0000u)) +
+           (__uint_as_float(v.y << 16) + __uint_as_float(v.y & 0xffff0000u));
     } else {
       s += (float)base[(size_t)b * b_stride + r];
     }
