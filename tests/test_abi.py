@@ -119,3 +119,63 @@ def test_detector_harness_keeps_reference_parameter_names():
     for k in sd:
         assert tuple(sd[k].shape) == tuple(ref[k].shape), k
     assert sum(p.numel() for p in m.parameters()) == 435862
+
+
+def test_wide_layers_dispatch_to_output_channel_groups_without_a_gpu():
+    """O > 256 (ResNet-50 C5, BASELINE configs[3]) stays on the tensor path for the pixel-row layouts; the Torch
+    layout follows gcd(Ho*Wo, C); bf16 storage never turns a shape away (generic kernels on widened copies)."""
+    lib = dcn.load()
+
+    def path(shape_args, variant, operand, phase):
+        s = dcn.make_shape(*shape_args, 3, 1, 1, variant, operand)
+        return lib.dcn_path_name(ctypes.byref(s), phase), lib.dcn_workspace_bytes(ctypes.byref(s), phase)
+
+    c5 = (128, 512, 512, 14, 14)
+    for operand in (dcn.OPERAND_FP32, dcn.OPERAND_BF16):
+        for phase in (0, 1):
+            for variant in (dcn.VARIANT_JITTOR, dcn.VARIANT_DCNV1):
+                name, ws = path(c5, variant, operand, phase)
+                assert name == b"umma" and ws > 0
+            name, ws = path(c5, dcn.VARIANT_TORCH, operand, phase)       # gcd(196, 512) = 4 channels per point
+            assert name == b"simt" and ws > 0
+    # groups are sized by the largest one: the workspace of O = 512 equals that of its 256-channel group for
+    # everything but the per-group weight / grad_out images, so it can never be smaller
+    for phase in (0, 1):
+        assert path(c5, dcn.VARIANT_JITTOR, dcn.OPERAND_FP32, phase)[1] >= \
+            path((128, 512, 256, 14, 14), dcn.VARIANT_JITTOR, dcn.OPERAND_FP32, phase)[1]
+    # O must split into multiples of 16
+    assert path((1, 64, 264, 8, 8), dcn.VARIANT_JITTOR, dcn.OPERAND_FP32, 0)[0] == b"simt"
+    assert path((1, 64, 768, 8, 8), dcn.VARIANT_JITTOR, dcn.OPERAND_FP32, 0)[0] == b"umma"
+
+
+def test_bn_relu_abi_rejects_bad_arguments_without_a_gpu():
+    lib = dcn.load()
+    buf = ctypes.create_string_buffer(1 << 16)
+    base = (ctypes.addressof(buf) + 255) // 256 * 256
+    ok = ctypes.c_void_p(base)
+    need = lib.dcn_bn_workspace_bytes(32)
+    assert need >= 2 * 32 * 8 + 2 * 32 * 4 and lib.dcn_bn_workspace_bytes(0) == 0
+    f = ctypes.c_float
+    assert lib.dcn_bn_relu_forward(0, 32, 64, 1, ok, ok, ok, ok, ok, f(0.1), f(1e-5), ok, ok, ok, need, None) == -1
+    assert lib.dcn_bn_relu_forward(4, 32, 64, 1, None, ok, ok, ok, ok, f(0.1), f(1e-5), ok, ok, ok, need, None) == -2
+    assert lib.dcn_bn_relu_forward(4, 32, 64, 1, ok, ok, ok, ok, ok, f(0.1), f(1e-5), ok, ok, ok, 8, None) == -4
+    # eval mode reads the running statistics: they must be there
+    assert lib.dcn_bn_relu_forward(4, 32, 64, 0, ok, ok, ok, None, None, f(0.1), f(1e-5), ok, ok, ok, need, None) == -2
+    assert lib.dcn_bn_relu_backward(4, 32, 64, 1, ok, None, ok, ok, ok, ok, ok, need, None) == -2
+    assert lib.dcn_bn_relu_backward(4, 32, 64, 1, ok, ctypes.c_void_p(base + 4), ok, ok, ok, ok, ok, need, None) == -3
+
+
+def test_bn_relu_module_keeps_the_batchnorm_interface():
+    """Same parameters, buffers, state-dict keys and defaults as tnn.BatchNorm2d (train.py:146-159), so that the
+    reference's checkpoints load unchanged; like it, training mode refuses one value per channel."""
+    import torch
+    ref = torch.nn.BatchNorm2d(16)
+    ours = dcn.BatchNormReLU2d(16)
+    assert list(ours.state_dict()) == list(ref.state_dict())
+    assert (ours.eps, ours.momentum, ours.affine, ours.track_running_stats) == \
+        (ref.eps, ref.momentum, ref.affine, ref.track_running_stats)
+    ours.load_state_dict(ref.state_dict())
+    with pytest.raises(ValueError):
+        ours(torch.zeros(1, 16, 1, 1))
+    with pytest.raises(ValueError):
+        ours(torch.zeros(2, 16, 4))
