@@ -677,10 +677,13 @@ def main():
         avg_s = prof[top][1] / prof[top][0] * 1e-3
         hbm_floor = work[role]["bytes"] / (pk["hbm"] * 1e9)
         tc_floor = work[role]["flops"] / (pk["bf16_sustained"] * 1e12)
-        traffic = None
+        traffic, limiter = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(f"{args.workload}:{args.variant}:{top}")
+            tj = json.load(open(tpath))
+            traffic = tj.get(f"{args.workload}:{args.variant}:{top}")
+            # what the counters of the committed ncu capture say actually bounds this kernel
+            limiter = tj.get("_limiter", {}).get(f"{args.workload}:{args.variant}:{top}")
         if hbm_floor >= tc_floor:
             ach = work[role]["bytes"] / avg_s / 1e9
             roofline = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
@@ -689,7 +692,7 @@ def main():
             ach = work[role]["flops"] / avg_s / 1e12
             roofline = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                         "frac": ach / pk["bf16_sustained"], "traffic": traffic}
-        roofline.update({"kernel": top, "avg_ms": avg_s * 1e3, "peak_source": pk["source"],
+        roofline.update({"kernel": top, "avg_ms": avg_s * 1e3, "peak_source": pk["source"], "measured_limiter": limiter,
                          "algorithmic_bytes": work[role]["bytes"], "algorithmic_flops": work[role]["flops"]})
 
     # ---- e2e: module API, host input buffers ----------------------------------------------

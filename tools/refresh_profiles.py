@@ -41,7 +41,8 @@ with open(os.path.join(P, f"{tag}_final_ncu.txt"), "w") as f:
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(io.StringIO(raw)))
 h, units = rr[0], rr[1]
-traffic = {}
+old = json.load(open(os.path.join(P, "traffic.json"))) if os.path.exists(os.path.join(P, "traffic.json")) else {}
+traffic = {"_limiter": old.get("_limiter", {})}
 for r in rr[2:]:
     d = dict(zip(h, r))
     def gb(key):
