@@ -25,7 +25,11 @@ class EDNetDetection(nn.Module):
         self.bn1 = bn_cls(16)
         self.relu = nn.ReLU(inplace=True)
         for idx, cin, cout in _DCN_STAGES:
-            setattr(self, f"conv{idx}", dcn_cls(cin, cout, 3, 2, 1))
+            layer = dcn_cls(cin, cout, 3, 2, 1)
+            # the backward pass reuses the forward pass's staged copy of x (one transpose of x per layer and step
+            # instead of two; the scratch buffer then lives from forward to backward)
+            layer.keep_staged_input = True
+            setattr(self, f"conv{idx}", layer)
             setattr(self, f"bn{idx}", bn_cls(cout))
         self.gap = nn.AdaptiveAvgPool2d(1)
         self.fc_cls = nn.Linear(256, num_classes)

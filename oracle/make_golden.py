@@ -28,6 +28,7 @@ import sys
 
 import numpy as np
 import torch
+import torch.nn as tnn
 
 from . import ref_loader, torch_chain
 
@@ -187,6 +188,48 @@ def make_detector_golden():
     _save("detector_eval", x=x.numpy(), cls=cls_logits.numpy(), bbox=bbox.numpy(), **arrays)
 
 
+def make_detector_train_golden():
+    """One TRAINING step's forward + backward of the unmodified reference detector (train.py:142-175 in train
+    mode, i.e. BatchNorm with batch statistics; loss recipe of train.py:195-199, 242-248): loss, heads,
+    BatchNorm running statistics after the step and the parameter gradients.  Initial weights = the state dict
+    stored in detector_eval.npz.  The four large DCN weight gradients are stored as their norm and their
+    projection on a fixed random direction (keeps the fixture small)."""
+    torch.manual_seed(97)
+    cls = ref_loader.load_reference_classes()["TorchEDNetDetection"]
+    m = cls()
+    ev = dict(np.load(os.path.join(OUT, "detector_eval.npz")))
+    m.load_state_dict({k[3:]: torch.as_tensor(v) for k, v in ev.items() if k.startswith("sd.")})
+    m.train()
+    B = 6
+    x = torch.zeros(B, 1, 128, 128)
+    pos = torch.randint(0, 101, (B, 2))
+    for i in range(B):
+        px, py = int(pos[i, 0]), int(pos[i, 1])
+        x[i, 0, py:py + 28, px:px + 28] = torch.rand(28, 28)
+    labels = torch.randint(0, 10, (B,))
+    boxes = torch.stack([pos[:, 0], pos[:, 1], pos[:, 0] + 28, pos[:, 1] + 28], 1).float() / 128.0
+    cls_out, bbox_out = m(x)
+    cls_loss = tnn.CrossEntropyLoss()(cls_out, labels)
+    diff = torch.abs(bbox_out - boxes)                                   # train.py:195-199, beta = 1
+    bbox_loss = torch.where(diff < 1.0, 0.5 * diff * diff / 1.0, diff - 0.5).mean()
+    total = cls_loss + 5.0 * bbox_loss                                   # train.py:247
+    total.backward()
+    arrays = {"x": x.numpy(), "labels": labels.numpy(), "boxes": boxes.numpy(), "loss": np.float32(total.item()),
+              "cls": cls_out.detach().numpy(), "bbox": bbox_out.detach().numpy()}
+    for k, v in m.state_dict().items():
+        if "running_" in k or "num_batches" in k:
+            arrays["buf." + k] = v.numpy()
+    g = torch.Generator().manual_seed(5)
+    for k, p_ in m.named_parameters():
+        gr = p_.grad
+        if gr.numel() > 20000:
+            d = torch.randn(gr.shape, generator=g)
+            arrays["gproj." + k] = np.array([float(gr.norm()), float((gr * d).sum()), float(d.norm())], np.float64)
+        else:
+            arrays["grad." + k] = gr.numpy()
+    _save("detector_train_step", **arrays)
+
+
 DCNV1 = {
     #  name             B  C   O   H   W   k       s  p       sigma
     "dcnv1_a_s1":      (2, 4,  6,  9,  11, 3,      1, 1,      1.5),
@@ -244,6 +287,7 @@ def main():
     make_layers(rng)
     make_module_golden()
     make_detector_golden()
+    make_detector_train_golden()
     make_wobble()
     make_dcnv1(np.random.default_rng(4242))
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as fh:
@@ -251,7 +295,7 @@ def main():
                  f"torch {torch.__version__}, numpy {np.__version__}\n"
                  "reference: x-y20/jittor-dcn train.py:70-175 loaded verbatim via ast "
                  "(oracle/ref_loader.py)\n"
-                 "stencil_*, wobble_*, layer_*, module_*, detector_*: outputs of the unmodified "
+                 "stencil_*, wobble_*, layer_*, module_*, detector_* (eval forward, one training step): outputs of the unmodified "
                  "reference\n"
                  "jittor_*: torch transliteration of deform_conv.py:30-81 "
                  "(oracle/torch_chain.py) - parity unpinned\n"

@@ -453,3 +453,52 @@ def test_wide_layer_staged_backward_and_flags():
         assert rel_err(out.cpu().numpy(), ref_out.cpu().numpy()) < FWD_TOL
         for a, b, nm in zip(got, ref, ("gx", "goff", "gw", "gb")):
             assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < GRAD_TOL, nm
+
+
+# ---- one TRAINING step of the reference's detector (BatchNorm with batch statistics) ------------
+@pytest.mark.parametrize("fused_bn_relu", [True, False])
+def test_detector_training_step_matches_reference(fused_bn_relu):
+    """Forward + backward of one training step (train.py:242-248: CE + 5 * smooth-L1) of the unmodified reference
+    detector in train mode (tests/golden/detector_train_step.npz, oracle/make_golden.py) against the harness
+    detector: its four DCN layers on the engine and — fused_bn_relu — relu(bn(x)) on the engine as well.
+    Tolerances (max-abs error over max-abs value): loss 1e-4, heads 1e-3, BatchNorm running statistics 1e-4,
+    gradients 2e-2.  The gradient bound is looser than the single-layer 1e-3 because the step's gradient is not a
+    continuous function of round-off: a 1e-6 difference in an offset moves a few samples across a pixel boundary
+    (the kink of the bilinear interpolation, where the offset gradient jumps) and flips a few ReLUs, and with a
+    batch of 6 those O(1) terms are a measurable part of the sums (observed: 5.6e-3 on bn1.bias, the parameter
+    that sees all four DCN layers, with either BatchNorm implementation).  An indexing error shows up as O(1)."""
+    from jittor_dcn_b200.detector import EDNetDetection, detection_loss
+    g, ev = golden("detector_train_step"), golden("detector_eval")
+    m = EDNetDetection(fused_bn_relu=fused_bn_relu).cuda().train()
+    m.load_state_dict({k[3:]: torch.as_tensor(v) for k, v in ev.items() if k.startswith("sd.")})
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False        # the reference's convolutions are float32 (CPU)
+    try:
+        cls, bbox = m(_cuda(g["x"]))
+        loss = detection_loss(cls, bbox, _cuda(g["labels"]), _cuda(g["boxes"]))
+        loss.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    assert rel_err(cls.detach().cpu().numpy(), g["cls"]) < 1e-3
+    assert rel_err(bbox.detach().cpu().numpy(), g["bbox"]) < 1e-3
+    for k, v in m.state_dict().items():
+        if "running_" in k:
+            assert rel_err(v.cpu().numpy(), g["buf." + k]) < 1e-4, k
+        elif "num_batches" in k:
+            assert int(v) == int(g["buf." + k]), k
+    gen = torch.Generator().manual_seed(5)          # the projection directions of make_detector_train_golden
+    for k, p in m.named_parameters():
+        gr = p.grad.detach().cpu()
+        if gr.numel() > 20000:
+            d = torch.randn(gr.shape, generator=gen)
+            norm, proj, dnorm = (float(t) for t in g["gproj." + k])
+            assert abs(float(gr.norm()) - norm) < 2e-2 * norm, k
+            assert abs(float((gr * d).sum()) - proj) < 2e-2 * norm * dnorm, k
+        elif float(np.abs(g["grad." + k]).max()) < 1e-3:
+            # biases in front of a BatchNorm have zero gradient (the batch mean removes them): what both sides hold
+            # is the round-off of a sum over up to 1e5 terms — 1e-4 on the CPU for conv1.bias, whose neighbours
+            # are ~1e-1
+            assert float(gr.abs().max()) < 1e-3, k
+        else:
+            assert rel_err(gr.numpy(), g["grad." + k]) < 2e-2, k
