@@ -502,3 +502,18 @@ def test_detector_training_step_matches_reference(fused_bn_relu):
             assert float(gr.abs().max()) < 1e-3, k
         else:
             assert rel_err(gr.numpy(), g["grad." + k]) < 2e-2, k
+
+
+def test_jittor_binding_host_helpers():
+    """The numpy-in / numpy-out helpers behind the Jittor `DeformConv2d` (jittor_dcn_b200/deform_conv.py: Vars live
+    on the host because the reference pins Jittor to the CPU, train.py:301) against the transliteration goldens.
+    Jittor itself is not installable here; this covers everything of that binding except the jt.Function shell."""
+    from jittor_dcn_b200.deform_conv import _engine_backward_host, _engine_forward_host
+    g = golden("jittor_a_s1")
+    k, s, p = _ksp(g["cfg"])
+    bias = g["bias"] if "bias" in g else None
+    out = _engine_forward_host(g["x"], g["off"], g["weight"], bias, k, s, p)
+    assert isinstance(out, np.ndarray) and rel_err(out, g["out"]) < FWD_TOL
+    gx, goff, gw, gb = _engine_backward_host(g["x"], g["off"], g["weight"], g["gout"], bias is not None, k, s, p)
+    assert rel_err(gx, g["gx"]) < GRAD_TOL and rel_err(goff, g["goff"]) < GRAD_TOL and rel_err(gw, g["gw"]) < GRAD_TOL
+    assert (gb is None) == (bias is None)
