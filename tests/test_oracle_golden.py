@@ -126,3 +126,30 @@ def test_dcnv1_oracle_matches_torchvision(name):
     assert rel_err(goff, g["goff"]) < 5e-6
     assert rel_err(gw, g["gw"]) < 5e-6
     assert rel_err(gb, g["gb"]) < 5e-6
+
+
+def test_harness_detector_with_the_chain_port_reproduces_the_reference_training_step():
+    """The harness detector topology (jittor_dcn_b200/detector.py) with its DCN layers replaced by the CPU port of
+    the reference's op chain (oracle/torch_chain.py) and the framework's BatchNorm2d + ReLU is the reference
+    detector restated: one training step (train mode, loss of train.py:242-248) must reproduce the golden made by
+    the UNMODIFIED reference (oracle/make_golden.py:make_detector_train_golden) — same torch build, same kernels.
+    Pins the harness topology / loss recipe and the port that bench.py times as the CPU baseline."""
+    import torch
+    from jittor_dcn_b200.detector import EDNetDetection, detection_loss
+    from oracle import torch_chain
+    g, ev = golden("detector_train_step"), golden("detector_eval")
+    torch.manual_seed(0)
+    m = EDNetDetection(dcn_cls=torch_chain.ChainLayer, fused_bn_relu=False).train()
+    m.load_state_dict({k[3:]: torch.as_tensor(v) for k, v in ev.items() if k.startswith("sd.")})
+    cls, bbox = m(torch.as_tensor(g["x"]))
+    loss = detection_loss(cls, bbox, torch.as_tensor(g["labels"]), torch.as_tensor(g["boxes"]))
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    assert rel_err(cls.detach().numpy(), g["cls"]) < 1e-5
+    assert rel_err(bbox.detach().numpy(), g["bbox"]) < 1e-5
+    for k, v in m.state_dict().items():
+        if "running_" in k:
+            assert rel_err(v.numpy(), g["buf." + k]) < 1e-6, k
+    for k, p in m.named_parameters():
+        if "grad." + k in g and float(np.abs(g["grad." + k]).max()) > 1e-3:
+            assert rel_err(p.grad.numpy(), g["grad." + k]) < 1e-4, k
