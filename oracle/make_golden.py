@@ -121,8 +121,21 @@ LAYERS = {
 }
 
 
-def make_layers(rng):
-    for name, (B, C, O, H, W, k, s, p, sigma, has_bias) in LAYERS.items():
+# Reference goldens that ROUTE TO THE TENSOR PATH (dcn_path_name == "umma" for both phases and all three coordinate
+# modes; tests/test_gpu_parity.py asserts the routing): every Torch-layout tiling class (Gt x Rt = 64x2, 32x4, 16x8),
+# two channel chunks per sampling point, partial last tiles, a stride-2 layer, live offsets.
+UMMA_LAYERS = {
+    #  name          B  C    O   H   W   k  s  p  sigma bias     Torch-layout tiling
+    "umma_a_64x2":  (3, 64,  64, 16, 16, 3, 1, 1, 1.5, True),   # G = 64: Gt 64, Rt 2, 6 full tiles
+    "umma_b_32x4":  (3, 32,  48, 12, 8,  3, 1, 1, 2.0, True),   # G = 32: Gt 32, Rt 4, R = 3: 9 instances, partial tile
+    "umma_c_16x8":  (2, 64,  32, 12, 12, 3, 1, 1, 1.0, True),   # G = 16: Gt 16, Rt 8, Cs = 4, R = 9: partial tile
+    "umma_d_chunk": (1, 128, 64, 16, 16, 3, 1, 1, 2.5, False),  # G = 128: two 64-channel chunks per sampling point
+    "umma_e_s2":    (2, 32,  64, 32, 32, 3, 2, 1, 2.0, True),   # stride 2 (detector conv3 shape at 32 x 32)
+}
+
+
+def make_layers(rng, layers=None):
+    for name, (B, C, O, H, W, k, s, p, sigma, has_bias) in (layers or LAYERS).items():
         kh, kw = torch_chain._pair(k)
         sh, sw = torch_chain._pair(s)
         ph, pw = torch_chain._pair(p)
@@ -148,7 +161,7 @@ def make_layers(rng):
         jar.update(out=out.numpy(), gx=grads[0].numpy(), goff=grads[1].numpy(), gw=grads[2].numpy())
         if has_bias:
             jar["gb"] = grads[3].numpy()
-        _save(name.replace("layer_", "jittor_"), **jar)
+        _save(name.replace("layer_", "jittor_").replace("umma_", "jittor_umma_"), **jar)
 
 
 def make_module_golden():
@@ -282,6 +295,9 @@ def main():
     assert ref_loader.available(), "needs /root/reference (build container only)"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    make_layers(np.random.default_rng(20261019), UMMA_LAYERS)   # own generator: added in round 2
+    if "--only-umma" in sys.argv:
+        return 0
     rng = np.random.default_rng(20261018)
     make_stencils(rng)
     make_layers(rng)
@@ -295,8 +311,11 @@ def main():
                  f"torch {torch.__version__}, numpy {np.__version__}\n"
                  "reference: x-y20/jittor-dcn train.py:70-175 loaded verbatim via ast "
                  "(oracle/ref_loader.py)\n"
-                 "stencil_*, wobble_*, layer_*, module_*, detector_* (eval forward, one training step): outputs of the unmodified "
-                 "reference\n"
+                 "stencil_*, wobble_*, layer_*, umma_*, module_*, detector_* (eval forward, one training step): outputs of "
+                 "the unmodified reference\n"
+                 "umma_*: layer fixtures whose shapes run on the tcgen05 path (dcn_path_name == umma, forward and "
+                 "backward, all coordinate modes): " + ", ".join(UMMA_LAYERS) + "\n"
+                 "layer_*: layer_d_det0 runs on the tcgen05 path, the other eight on the generic kernels\n"
                  "jittor_*: torch transliteration of deform_conv.py:30-81 "
                  "(oracle/torch_chain.py) - parity unpinned\n"
                  "dcnv1_*: outputs of torchvision.ops.deform_conv2d (CPU) for DCN_VARIANT_DCNV1\n")

@@ -89,11 +89,20 @@ def test_corners_bit_exact_random_offsets(shape, variant):
     assert np.array_equal(a.view(np.uint32)[~both_nan], b.view(np.uint32)[~both_nan])
 
 
+def _paths(g, variant):
+    B, C, O, H, W, kh, kw, sh, sw, ph, pw = (int(v) for v in g["cfg"])
+    shp = dcn.make_shape(B, C, O, H, W, (kh, kw), (sh, sw), (ph, pw), variant)
+    return [dcn._lib.path_name(shp, ph_) for ph_ in (dcn._lib.PHASE_FORWARD, dcn._lib.PHASE_BACKWARD)]
+
+
 @pytest.mark.parametrize("flags", FLAG_SETS)
-@pytest.mark.parametrize("name", golden_names("layer_"))
+@pytest.mark.parametrize("name", golden_names("layer_") + golden_names("umma_"))
 def test_layer_against_reference_golden(name, flags):
-    """Forward and all four gradients against the unmodified reference's own outputs."""
+    """Forward and all four gradients against the unmodified reference's own outputs.  The umma_* fixtures are the
+    ones whose shapes run on the tcgen05 kernels (both phases); the routing itself is asserted."""
     g = golden(name)
+    if name.startswith("umma_") and flags == 0:
+        assert _paths(g, dcn.VARIANT_TORCH) == ["umma", "umma"]
     out, gx, goff, gw, gb = _engine(g, dcn.VARIANT_TORCH, flags)
     assert rel_err(out.cpu().numpy(), g["out"]) < FWD_TOL
     assert rel_err(gx.cpu().numpy(), g["gx"]) < GRAD_TOL
@@ -110,6 +119,8 @@ def test_layer_jittor_variant_against_transliteration(name, flags):
     s = shape_from_cfg(g["cfg"], orc.VARIANT_JITTOR)
     if min(orc.out_hw(s)) == 1:
         pytest.skip("H_out or W_out == 1: the reference divides by zero (deform_conv.py:37-38)")
+    if name.startswith("jittor_umma_") and flags == 0:
+        assert _paths(g, dcn.VARIANT_JITTOR) == ["umma", "umma"]
     out, gx, goff, gw, gb = _engine(g, dcn.VARIANT_JITTOR, flags)
     assert rel_err(out.cpu().numpy(), g["out"]) < FWD_TOL
     assert rel_err(gx.cpu().numpy(), g["gx"]) < GRAD_TOL
