@@ -2,6 +2,7 @@
 // dispatch to a kernel family.  No torch types, no allocation, no device synchronisation.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <map>
@@ -28,6 +29,30 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
   return DCN_ERR_CUDA;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static int env_set(const char* name) { return getenv(name) != nullptr; }
+
+const Knobs& knobs() {
+  // C++11 magic static: initialised once, thread-safe
+  static const Knobs k = [] {
+    Knobs v;
+    v.fwd_no_tma_out = env_set("DCN_FWD_NO_TMA_OUT");
+    v.fwd_stages = env_int("DCN_FWD_STAGES", 3);
+    v.fwd_no_kperm = env_set("DCN_FWD_NO_KPERM");
+    v.bwd_no_resident = env_set("DCN_BWD_NO_RESIDENT");
+    v.bwd_no_ring1 = env_set("DCN_BWD_NO_RING1");
+    v.bwd_slice_cb = env_int("DCN_BWD_SLICE_CB", 6);
+    v.bwd_no_fuse = env_int("DCN_BWD_NO_FUSE", 0);
+    v.bwd_gbuf1 = env_int("DCN_BWD_GBUF", 0) == 1;
+    v.bwd_data_simt = env_int("DCN_BWD_DATA_SIMT", 0);
+    return v;
+  }();
+  return k;
 }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }

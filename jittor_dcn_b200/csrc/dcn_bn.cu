@@ -48,7 +48,9 @@ __device__ __forceinline__ void block_reduce2(double& a, double& b) {
 // Block (c, s): batch elements [s * bpb, (s + 1) * bpb) of channel c, walked as one flat index space so that
 // small planes (8 x 8 in the detector's last layer) keep all threads busy.  fp32 partial sums of at most 64
 // elements are flushed into double accumulators.
-//   MODE 0: sums[c] += {sum x, sum x^2}
+//   MODE 0: sums[c] += {sum (x - pivot), sum (x - pivot)^2} with pivot = the channel's first element x[0, c, 0]:
+//           shifted sums, so that the variance S2/n - (S1/n)^2 does not cancel when |mean| >> std
+//           (a channel at mean 1e3, std 1e-2 loses every digit of E[x^2] - E[x]^2 in fp32)
 //   MODE 1: sums[c] += {sum dyr, sum dyr * (x - mean[c])}   with dyr = dy * [fmaf(x, scale, shift) > 0]
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(int B, int C, int HW, int bpb,
@@ -68,6 +70,8 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(int B, int C, int H
     sc = scale[c];
     sh = shift[c];
     mu = mean[c];
+  } else {
+    mu = __ldg(x + (size_t)c * HW);  // pivot
   }
   double A = 0.0, Q = 0.0;
   float a = 0.f, q = 0.f;
@@ -77,8 +81,9 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(int B, int C, int H
     if (VEC) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)b * b_stride) + r);
       if (MODE == 0) {
-        a += (v.x + v.y) + (v.z + v.w);
-        q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
+        a += (d0 + d1) + (d2 + d3);
+        q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
       } else {
         const float4 g = __ldg(reinterpret_cast<const float4*>(db + (size_t)b * b_stride) + r);
         const float g0 = fmaf(v.x, sc, sh) > 0.f ? g.x : 0.f, g1 = fmaf(v.y, sc, sh) > 0.f ? g.y : 0.f;
@@ -89,8 +94,8 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(int B, int C, int H
     } else {
       const float v = __ldg(xb + (size_t)b * b_stride + r);
       if (MODE == 0) {
-        a += v;
-        q += v * v;
+        a += v - mu;
+        q += (v - mu) * (v - mu);
       } else {
         const float g = fmaf(v, sc, sh) > 0.f ? __ldg(db + (size_t)b * b_stride + r) : 0.f;
         a += g;
@@ -115,16 +120,18 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(int B, int C, int H
 
 // per channel: batch statistics -> affine map of the forward pass, saved statistics, running statistics
 // (nn.BatchNorm2d: biased variance normalises, unbiased variance updates running_var)
-__global__ void bn_finalize_kernel(int C, double count, const double* __restrict__ sums,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+__global__ void bn_finalize_kernel(int C, int HW, const float* __restrict__ x, double count,
+                                   const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ save_mean,
                                    float* __restrict__ save_invstd, float* __restrict__ scale,
                                    float* __restrict__ shift) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double m = sums[2 * c] / count;
-  double var = sums[2 * c + 1] / count - m * m;
+  // shifted sums about the pivot x[0, c, 0] (bn_reduce_kernel MODE 0)
+  const double dm = sums[2 * c] / count;
+  const double m = (double)x[(size_t)c * HW] + dm;
+  double var = sums[2 * c + 1] / count - dm * dm;
   if (var < 0.0) var = 0.0;
   const float mean = (float)m, invstd = 1.0f / sqrtf((float)var + eps);
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
@@ -278,7 +285,7 @@ int bn_relu_forward(int B, int C, int HW, int training, const float* x, const fl
                                                                       nullptr, sums);
       DCN_KERNEL_CHECK("bn_stats_kernel");
     }
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, (double)B * HW, sums, gamma, beta, eps, momentum,
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, HW, x, (double)B * HW, sums, gamma, beta, eps, momentum,
                                                       running_mean, running_var, save_mean, save_invstd, scale,
                                                       shift);
     DCN_KERNEL_CHECK("bn_finalize_kernel");

@@ -199,6 +199,21 @@ struct KernelScope {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Tuning knobs for A/B measurements (INTEGRATION.md "Tuning knobs").  The environment is read ONCE, on the first
+// call into the library; afterwards the dispatch path touches no process-global state.  Defaults = production.
+struct Knobs {
+  int fwd_no_tma_out;   // DCN_FWD_NO_TMA_OUT   forward epilogue: direct stores instead of the staged tensor-map store
+  int fwd_stages;       // DCN_FWD_STAGES       forward pipeline depth wanted (2..4, default 3)
+  int fwd_no_kperm;     // DCN_FWD_NO_KPERM     pixel-row layouts: walk the K blocks tap-major
+  int bwd_no_resident;  // DCN_BWD_NO_RESIDENT  fused backward: always stream the Wm^T images through the ring
+  int bwd_no_ring1;     // DCN_BWD_NO_RING1     fused backward: never take the 1-stage ring plan
+  int bwd_slice_cb;     // DCN_BWD_SLICE_CB     fused backward (Torch layout): max column blocks per slice (1..6)
+  int bwd_no_fuse;      // DCN_BWD_NO_FUSE      weight gradient as its own pass
+  int bwd_gbuf1;        // DCN_BWD_GBUF=1       one grad_out tile buffer
+  int bwd_data_simt;    // DCN_BWD_DATA_SIMT    fp32 data gradient on the generic kernels
+};
+const Knobs& knobs();
+
 // ---- kernel families (each returns a DcnStatus) --------------------------------------
 // plan: Tap per (b, q); stored in q-order [b][p][n] (Torch) or tap-major [b][n][p] (Jittor)
 int launch_plan(const Geo& g, const float* off, Tap* plan, cudaStream_t st);

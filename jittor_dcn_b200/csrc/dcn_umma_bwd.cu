@@ -33,8 +33,7 @@ size_t umma_bwd_data_gtile_bytes(const Geo& g, int operand);
 static size_t plan_bytes(const Geo& g) { return align_up(sizeof(Tap) * (size_t)g.B * g.P, 1024); }
 
 static bool use_umma_data(const Geo& g, int operand) {
-  if (const char* e = getenv("DCN_BWD_DATA_SIMT"))
-    if (atoi(e)) return false;
+  if (knobs().bwd_data_simt) return false;
   return umma_bwd_data_supported(g, operand);
 }
 

@@ -959,7 +959,7 @@ __global__ void __launch_bounds__(256) weight_tiles_bwd_kernel(Geo g, int ncols,
 //   buffers and the Wm^T stages
 static void choose_slices(bd::Params* P, int max_cb, size_t real, size_t zero, size_t other) {
   const size_t cap = 227 * 1024;
-  const bool allow_res = !getenv("DCN_BWD_NO_RESIDENT");
+  const bool allow_res = !knobs().bwd_no_resident;
   const int ns_min = (P->cblocks + max_cb - 1) / max_cb;
   double best = 1e30;
   for (int ns = ns_min; ns <= ns_min + 2 && ns <= P->cblocks; ++ns) {
@@ -981,7 +981,7 @@ static void choose_slices(bd::Params* P, int max_cb, size_t real, size_t zero, s
     if (pl[1] && !allow_res) continue;
     const size_t n_w = pl[1] ? n_res : (size_t)pl[2];
     const size_t need = pl[0] * real + zero + n_w * P->w_stage + other;
-    if (need <= cap || (pl[2] == 1 && need - 768 <= cap && !getenv("DCN_BWD_NO_RING1"))) {
+    if (need <= cap || (pl[2] == 1 && need - 768 <= cap && !knobs().bwd_no_ring1)) {
       P->g_nbuf = pl[0];
       P->w_resident = pl[1] ? (int)n_res : 0;
       P->w_ring = pl[2];
@@ -1037,7 +1037,7 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
         P->w_stage = (uint32_t)nimg * ncols * 128;
         P->tmem_cols = 512;
         int max_cb = 6;  // 512 TMEM columns - 2 gA buffers
-        if (const char* e = getenv("DCN_BWD_SLICE_CB")) max_cb = atoi(e) < 1 ? 1 : (atoi(e) > 6 ? 6 : atoi(e));
+        max_cb = knobs().bwd_slice_cb < 1 ? 1 : (knobs().bwd_slice_cb > 6 ? 6 : knobs().bwd_slice_cb);
         choose_slices(P, max_cb, real, zero, rest - 2 * (size_t)P->w_stage);
         return true;
       }
@@ -1109,9 +1109,7 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
 }
 
 static bool fuse_allowed() {
-  if (const char* e = getenv("DCN_BWD_NO_FUSE"))
-    if (atoi(e)) return false;
-  return true;
+  return !knobs().bwd_no_fuse;
 }
 
 bool umma_bwd_data_supported(const Geo& g, int operand) {
@@ -1247,8 +1245,7 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
   // (autograd of train.py:111-113 -> GridSampler.h:27-36; dcn_simt.cu:offset_scale_kernel)
   P.scale_iy = g.variant == DCN_VARIANT_DCNV1 ? 1.f : g.sy * 2.0f / g.Dx;
   P.scale_ix = g.variant == DCN_VARIANT_DCNV1 ? 1.f : g.sx * 2.0f / g.Dy;
-  if (const char* e = getenv("DCN_BWD_GBUF"))
-    if (atoi(e) == 1) P.g_nbuf = 1;
+  if (knobs().bwd_gbuf1) P.g_nbuf = 1;
   size_t smem = ((size_t)P.g_nbuf * P.OB + (P.g_imgs - P.OB)) * nimg * P.g_img +
                 (size_t)(P.w_resident ? P.w_resident : P.w_ring) * P.w_stage +
                 (P.fuse_w ? 2 * nimg * (size_t)(128 * 128) : 0) +

@@ -901,7 +901,7 @@ int umma_forward_any(const Geo& g, int operand, const void* x, const float* off,
   memset(&tmap, 0, sizeof(tmap));
   // (Rt = 2 only: with Rt >= 4 the direct stores already write 16-byte runs, and the staged path
   // measured slower there)
-  if (g.variant == DCN_VARIANT_TORCH && P.t.Rt == 2 && !getenv("DCN_FWD_NO_TMA_OUT")) {
+  if (g.variant == DCN_VARIANT_TORCH && P.t.Rt == 2 && !knobs().fwd_no_tma_out) {
     const int box_r = P.t.Rt < 4 ? 4 : P.t.Rt;
     const size_t bytes = sizeof(float) * (size_t)g.O * P.t.Gt * box_r;
     if (P.t.R % box_r == 0 && bytes <= 64 * 1024 && g.O <= 256 &&
@@ -918,8 +918,7 @@ int umma_forward_any(const Geo& g, int operand, const void* x, const float* off,
   int stages = (int)((227 * 1024 - fixed) / P.stage_bytes);
   // A few stages are enough to overlap the (fast) MMAs with the (slow) gather; every KB of
   // shared memory not taken stays L1 for the gather's footprint (L1 + smem share 256 KB).
-  int want = 3;
-  if (const char* e = getenv("DCN_FWD_STAGES")) want = atoi(e);
+  int want = knobs().fwd_stages;
   if (want < 2) want = 2;
   if (want > kMaxStages) want = kMaxStages;
   P.stages = stages > want ? want : stages;
@@ -929,7 +928,7 @@ int umma_forward_any(const Geo& g, int operand, const void* x, const float* off,
   }
   P.tmem_cols = pow2_cols(2 * g.O);
   if (g.variant != DCN_VARIANT_TORCH && g.C % 64 == 0 && g.C > 64 && P.t.KB == g.N * (g.C / 64) &&
-      !getenv("DCN_FWD_NO_KPERM"))
+      !knobs().fwd_no_kperm)
     P.kperm_slabs = g.C / 64;
   const size_t smem = (size_t)P.stages * P.stage_bytes + fixed;
   const int sms = num_sms();

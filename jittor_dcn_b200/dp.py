@@ -74,9 +74,14 @@ class DcnComm:
         self.world, self.device, self.lib = world, device, lib
 
     def allreduce_mean_(self, flat):
+        """flat <- mean over ranks (equal shards; see allreduce_gradients for uneven ones)."""
+        return self.allreduce_sum_(flat, 1.0 / self.world)
+
+    def allreduce_sum_(self, flat, scale=1.0):
+        """flat <- scale * sum over ranks, in place, on the current stream (capturable in a CUDA graph)."""
         stream = torch.cuda.current_stream(self.device)
         _lib.check(self.lib.dcn_allreduce_sum_f32(self.handle, ctypes.c_void_p(flat.data_ptr()),
-                                                  flat.numel(), 1.0 / self.world,
+                                                  flat.numel(), float(scale),
                                                   ctypes.c_void_p(stream.cuda_stream)),
                    "dcn_allreduce_sum_f32")
         return flat
@@ -87,14 +92,29 @@ class DcnComm:
             self.handle = ctypes.c_void_p()
 
 
-def allreduce_gradients(bucket, comm=None, group=None):
-    """Average the gradients of `bucket.params` over all ranks with ONE collective."""
+def shard_weight(global_batch, rank, world):
+    """Weight of rank `rank`'s gradients in the global-batch gradient: B_local / B_global.  Every rank's loss is
+    the MEAN over its own shard, so the global-batch mean is sum_r (B_r / B) * grad_r; only for equal shards is
+    that the plain average 1 / world."""
+    b, e = shard_range(global_batch, rank, world)
+    return (e - b) / float(global_batch)
+
+
+def allreduce_gradients(bucket, comm=None, group=None, weight=None):
+    """Combine the gradients of `bucket.params` over all ranks with ONE collective.
+
+    weight = None: plain average (equal shards).  weight = shard_weight(B, rank, world): each rank's
+    per-shard-mean gradients are scaled by B_local / B_global before the sum, which reproduces the single-process
+    gradient of the global-batch mean loss for ANY split (uneven shards, B % world != 0).
+    BatchNorm batch statistics stay per rank, as in the reference (no SyncBN, train.py:146-159)."""
     flat = bucket.pack()
+    if weight is not None:
+        flat.mul_(float(weight))
     if comm is not None:
-        comm.allreduce_mean_(flat)
+        comm.allreduce_sum_(flat, 1.0 if weight is not None else 1.0 / comm.world)
     else:
-        world = dist.get_world_size(group)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.mul_(1.0 / world)
+        if weight is None:
+            flat.mul_(1.0 / dist.get_world_size(group))
     bucket.unpack()
     return flat

@@ -12,16 +12,32 @@ from ._lib import (FLAG_ACCUM_GRAD_X, FLAG_FORCE_SIMT, FLAG_NO_GRAD_X, FLAG_XT_S
                    PHASE_BACKWARD, PHASE_FORWARD, VARIANT_DCNV1, VARIANT_JITTOR, VARIANT_TORCH)
 
 _workspaces = {}
+_captured = []   # scratch buffers whose addresses are baked into CUDA graphs: alive until clear_workspaces()
 
 
 def _workspace(device, stream_id, nbytes):
-    """Caller-owned scratch, one growing buffer per (device, stream)."""
+    """Caller-owned scratch, one growing buffer per (device, stream).
+
+    While the stream is being captured into a CUDA graph the call gets a PRIVATE buffer that is never freed or
+    handed out again (a replay reads and writes the captured address; the shared cache may be re-allocated by a
+    later, larger eager call).  clear_workspaces() drops everything — only once such graphs are gone."""
+    if torch.cuda.is_current_stream_capturing():
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _captured.append(ws)
+        return ws
     key = (device.index, stream_id)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+def clear_workspaces():
+    """Release the cached scratch buffers (all devices / streams) and the ones captured CUDA graphs point at.
+    Call only when no such graph will be replayed again."""
+    _workspaces.clear()
+    del _captured[:]
 
 
 def _dev_ready(t, dtype=torch.float32):
@@ -111,10 +127,22 @@ def dcn_forward(x, offset, weight, bias, kernel_size=3, stride=1, padding=1, var
 
 def dcn_backward(x, offset, weight, grad_out, has_bias, kernel_size=3, stride=1, padding=1,
                  variant=VARIANT_TORCH, operand=OPERAND_FP32, flags=0, need_grad_x=True, ws=None,
-                 xt_staged=False):
+                 xt_staged=False, grad_x=None):
     """-> grad_x (or None), grad_offset, grad_weight, grad_bias (or None); all float32.
-    ws / xt_staged: the buffer from staged_workspace() that the matching dcn_forward used."""
+    ws / xt_staged: the buffer from staged_workspace() that the matching dcn_forward used.
+    grad_x: an existing float32 gradient of x's shape to ACCUMULATE into (DCN_FLAG_ACCUM_GRAD_X; e.g. the
+    term the companion offset conv contributes); without it the flag is refused — the library would add into
+    whatever the freshly allocated output buffer happens to hold."""
     lib = _lib.load()
+    if grad_x is not None:
+        if not need_grad_x:
+            raise ValueError("grad_x given but need_grad_x is False")
+        if grad_x.dtype != torch.float32 or tuple(grad_x.shape) != tuple(x.shape) or not grad_x.is_contiguous() \
+                or grad_x.data_ptr() % 16:
+            raise ValueError("grad_x must be a dense, 16-byte aligned float32 tensor of x's shape")
+        flags |= FLAG_ACCUM_GRAD_X
+    elif flags & FLAG_ACCUM_GRAD_X:
+        raise ValueError("FLAG_ACCUM_GRAD_X needs the tensor to accumulate into: pass grad_x=")
     if not need_grad_x:
         flags |= FLAG_NO_GRAD_X
     if xt_staged and ws is not None:
@@ -126,7 +154,7 @@ def dcn_backward(x, offset, weight, grad_out, has_bias, kernel_size=3, stride=1,
     x, weight, grad_out = _dev_ready(x, act), _dev_ready(weight, act), _dev_ready(grad_out, act)
     offset = _dev_ready(offset)
     dev = x.device
-    gx = torch.empty(x.shape, dtype=torch.float32, device=dev) if need_grad_x else None
+    gx = grad_x if grad_x is not None else (torch.empty(x.shape, dtype=torch.float32, device=dev) if need_grad_x else None)
     goff = torch.empty((shp.B, 2 * N, Ho, Wo), dtype=torch.float32, device=dev)
     gw = torch.empty(weight.shape, dtype=torch.float32, device=dev)
     gb = torch.empty((shp.O,), dtype=torch.float32, device=dev) if has_bias else None
@@ -189,6 +217,7 @@ class DeformConvFunction(torch.autograd.Function):
     def backward(ctx, grad_out):
         xd, od, wd = ctx.saved_tensors
         kernel_size, stride, padding, variant, operand, flags = ctx.cfg[:6]
+        flags &= ~FLAG_ACCUM_GRAD_X     # autograd sums gradient terms itself; the output buffer here is fresh
         dev = xd.device
         gx, goff, gw, gb = dcn_backward(xd, od, wd, _to_device(grad_out, dev), ctx.has_bias,
                                         kernel_size, stride, padding, variant, operand, flags,

@@ -46,7 +46,7 @@ def test_bucket_roundtrip():
         assert torch.equal(p.grad, 2.0 * w)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, batch=8):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -55,14 +55,15 @@ def _worker(rank, world, port, out):
         model = torch.nn.Sequential(torch.nn.Conv2d(2, 3, 3, padding=1), torch.nn.Flatten(),
                                     torch.nn.Linear(3 * 6 * 6, 4))
         gen = torch.Generator().manual_seed(123)  # same global batch on every rank
-        x = torch.randn(8, 2, 6, 6, generator=gen)
-        y = torch.randn(8, 4, generator=gen)
-        b, e = dp.shard_range(8, rank, world)
-        # mean over the GLOBAL batch = mean over ranks of the per-shard mean (equal shards)
+        x = torch.randn(batch, 2, 6, 6, generator=gen)
+        y = torch.randn(batch, 4, generator=gen)
+        b, e = dp.shard_range(batch, rank, world)
+        # mean over the GLOBAL batch = sum over ranks of (B_r / B) * per-shard mean; equal shards: plain average
         loss = ((model(x[b:e]) - y[b:e]) ** 2).mean()
         loss.backward()
         bucket = dp.GradBucket(model.parameters())
-        dp.allreduce_gradients(bucket)            # ONE collective
+        weight = None if batch % world == 0 else dp.shard_weight(batch, rank, world)
+        dp.allreduce_gradients(bucket, weight=weight)   # ONE collective
         if rank == 0:
             ref = torch.nn.Sequential(torch.nn.Conv2d(2, 3, 3, padding=1), torch.nn.Flatten(),
                                       torch.nn.Linear(3 * 6 * 6, 4))
@@ -74,11 +75,12 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_two_rank_allreduce_equals_full_batch_gradients():
+@pytest.mark.parametrize("batch", [8, 7])   # 7: uneven shards (4 + 3), weighted by B_local / B_global
+def test_two_rank_allreduce_equals_full_batch_gradients(batch):
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out, batch)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:

@@ -128,3 +128,28 @@ def test_detector_fused_matches_framework_bn():
         assert rel_err(p.grad.cpu().numpy(), q.grad.cpu().numpy()) < 2e-3, n
     for (n, p), (_, q) in zip(a.named_buffers(), b.named_buffers()):
         assert rel_err(p.float().cpu().numpy(), q.float().cpu().numpy()) < 1e-4, n
+
+
+def test_batch_variance_with_mean_far_above_std():
+    """A channel at mean 1e3, std 1e-2 (ADVICE r1): E[x^2] - E[x]^2 in float32 loses every digit of the variance;
+    the kernels accumulate sums shifted by a per-channel pivot instead.  Reference: float64 two-pass statistics.
+    x itself carries a relative spacing of 6e-8 * 1e3 = 6e-5 around the mean, i.e. 0.6 % of std: the normalised
+    output is compared where that input quantisation is the same for both sides (same float32 x)."""
+    torch.manual_seed(11)
+    B, C, H, W = 8, 6, 32, 32
+    mean = torch.tensor([1e3, -1e3, 50.0, 0.0, 1e3, 3.0]).view(1, C, 1, 1)
+    std = torch.tensor([1e-2, 1e-2, 1e-3, 1.0, 5.0, 1e-4]).view(1, C, 1, 1)
+    x = (torch.randn(B, C, H, W, dtype=torch.float64) * std + mean).float()
+    ours = dcn.BatchNormReLU2d(C).cuda()
+    y = ours(x.cuda())
+    xd = x.double()
+    m = xd.mean(dim=(0, 2, 3))
+    v = xd.var(dim=(0, 2, 3), unbiased=False)
+    ref = torch.relu((xd - m.view(1, C, 1, 1)) / torch.sqrt(v.view(1, C, 1, 1) + ours.eps))
+    assert rel_err(y.cpu().numpy(), ref.numpy()) < 1e-3
+    # running_var = 0.9 * 1 + 0.1 * unbiased batch variance
+    n = B * H * W
+    exp_rv = 0.9 + 0.1 * v * n / (n - 1)
+    assert float(((ours.running_var.cpu().double() - exp_rv).abs() / exp_rv).max()) < 1e-5
+    exp_rm = 0.1 * m
+    assert float((ours.running_mean.cpu().double() - exp_rm).abs().max()) < 1e-4

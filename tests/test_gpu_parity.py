@@ -528,3 +528,24 @@ def test_jittor_binding_host_helpers():
     gx, goff, gw, gb = _engine_backward_host(g["x"], g["off"], g["weight"], g["gout"], bias is not None, k, s, p)
     assert rel_err(gx, g["gx"]) < GRAD_TOL and rel_err(goff, g["goff"]) < GRAD_TOL and rel_err(gw, g["gw"]) < GRAD_TOL
     assert (gb is None) == (bias is None)
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS)
+@pytest.mark.parametrize("variant", [dcn.VARIANT_TORCH, dcn.VARIANT_JITTOR])
+def test_backward_accumulates_into_a_given_grad_x(variant, flags):
+    """DCN_FLAG_ACCUM_GRAD_X: grad_x= is added to, bit-compatible with a separate add; the bare flag
+    without a tensor to accumulate into is refused by the wrapper."""
+    rng = np.random.default_rng(21)
+    B, C, O, H, W = 2, 64, 64, 16, 16
+    x, off, w, gout = (_cuda(a.astype(np.float32)) for a in (
+        rng.standard_normal((B, C, H, W)), rng.standard_normal((B, 18, H, W)) * 1.5,
+        rng.standard_normal((O, C, 3, 3)) * 0.05, rng.standard_normal((B, O, H, W))))
+    base = _cuda(rng.standard_normal((B, C, H, W)).astype(np.float32))
+    gx_plain, goff0, gw0, _ = dcn.dcn_backward(x, off, w, gout, False, 3, 1, 1, variant, flags=flags)
+    acc = base.clone()
+    gx, goff1, gw1, _ = dcn.dcn_backward(x, off, w, gout, False, 3, 1, 1, variant, flags=flags, grad_x=acc)
+    assert gx is acc
+    assert rel_err(acc.cpu().numpy(), (base + gx_plain).cpu().numpy()) < 1e-5
+    assert rel_err(goff1.cpu().numpy(), goff0.cpu().numpy()) < 1e-5 and rel_err(gw1.cpu().numpy(), gw0.cpu().numpy()) < 1e-5
+    with pytest.raises(ValueError):
+        dcn.dcn_backward(x, off, w, gout, False, 3, 1, 1, variant, flags=flags | dcn.FLAG_ACCUM_GRAD_X)
