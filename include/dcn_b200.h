@@ -87,11 +87,12 @@ enum {
                                       tcgen05 path supports the shape (A/B testing) */
   DCN_FLAG_NO_GRAD_X = 1 << 2,     /* dcn_backward: skip grad_x (first layer of a net) */
   DCN_FLAG_RELU_OUT = 1 << 3,      /* reserved for the fused epilogue */
-  DCN_FLAG_XT_STAGED = 1 << 4      /* dcn_backward: the workspace is the very buffer the preceding
-                                      dcn_forward of the same shape / operand was given (sized for the
-                                      backward phase) and nothing has written to it since, so its head
-                                      still holds the staged copy of x: skip re-staging.  Only
-                                      meaningful when both phases run on the tensor path
+  DCN_FLAG_XT_STAGED = 1 << 4      /* the workspace is the very buffer a preceding call of this library for the
+                                      same shape / operand was given (dcn_offset_conv_forward, dcn_forward or
+                                      dcn_layer_forward; sized for the largest phase used) and nothing has written
+                                      to it since, so its head still holds the staged copy of x: skip re-staging.
+                                      Honoured by dcn_forward, dcn_backward, dcn_offset_conv_forward and
+                                      dcn_layer_backward.  Only meaningful on the tensor path
                                       (dcn_path_name == "umma"); ignored otherwise */
 };
 
@@ -108,8 +109,14 @@ typedef struct DcnShape {
   int32_t flags;       /* DCN_FLAG_* */
 } DcnShape;
 
-/* phases for dcn_workspace_bytes */
-enum { DCN_PHASE_FORWARD = 0, DCN_PHASE_BACKWARD = 1, DCN_PHASE_CORNERS = 2 };
+/* phases for dcn_workspace_bytes / dcn_path_name */
+enum {
+  DCN_PHASE_FORWARD = 0, DCN_PHASE_BACKWARD = 1, DCN_PHASE_CORNERS = 2,
+  /* whole layer = companion offset convolution + DCN span (dcn_layer_forward / dcn_layer_backward); dcn_path_name
+   * answers "umma" when the layer calls are available for the shape, "unsupported" otherwise (the caller then keeps
+   * the offset conv on its framework and uses dcn_forward / dcn_backward) */
+  DCN_PHASE_LAYER_FORWARD = 3, DCN_PHASE_LAYER_BACKWARD = 4
+};
 
 /* ---- introspection ---------------------------------------------------------------- */
 DCN_API int dcn_version(void);
@@ -152,6 +159,28 @@ DCN_API int dcn_backward(const DcnShape* s, const void* x, const void* offset, c
                  const void* grad_out, void* grad_x, void* grad_offset, void* grad_weight,
                  void* grad_bias, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the whole layer: companion offset convolution + DCN span ------------------------------------
+ * The offset conv (deform_conv.py:16-21,58 / train.py:80-85,98: C -> 2N channels, same kernel / stride / padding) runs
+ * as a "plain" mode of the same tcgen05 kernels: a regular convolution is the DCNv1 sampling with all offsets zero,
+ * i.e. ONE exact pixel per (pixel, tap) instead of four weighted corners.  x is staged once for offset conv, DCN
+ * forward and the whole backward; in the backward pass grad_offset never leaves the workspace and the offset conv's
+ * data gradient accumulates into the same channels-last grad_x buffer as the DCN data gradient (one transposition
+ * at the end).  fp32 operands; shapes: dcn_path_name(s, DCN_PHASE_LAYER_*) == "umma".
+ *   offset_weight [2N,C,kh,kw]   offset_bias [2N] or NULL   offset [B,2N,Ho,Wo] (written by the forward pass and
+ *   handed back to the backward pass: it is the saved activation)
+ * dcn_offset_conv_forward alone computes `offset` (stages x unless DCN_FLAG_XT_STAGED); a following
+ * dcn_forward with DCN_FLAG_XT_STAGED on the same workspace reuses the staged copy. */
+DCN_API int dcn_offset_conv_forward(const DcnShape* s, const void* x, const void* offset_weight, const void* offset_bias,
+                            void* offset, void* workspace, size_t workspace_bytes, void* stream);
+DCN_API int dcn_layer_forward(const DcnShape* s, const void* x, const void* offset_weight, const void* offset_bias,
+                      const void* weight, const void* bias, void* offset, void* out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* grad_x may be NULL with DCN_FLAG_NO_GRAD_X; grad_offset_bias / grad_bias may be NULL. */
+DCN_API int dcn_layer_backward(const DcnShape* s, const void* x, const void* offset, const void* offset_weight,
+                       const void* weight, const void* grad_out, void* grad_x, void* grad_offset_weight,
+                       void* grad_offset_bias, void* grad_weight, void* grad_bias, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Sampling geometry only (bit-exactness probe): for every (b, n, h, w)
  *   y0,x0 [B,N,Ho,Wo] int32   floor'ed row / column of the north-west corner
  *   w4    [B,N,Ho,Wo,4] f32   corner weights nw, ne, sw, se (unmasked)                     */
@@ -184,6 +213,24 @@ DCN_API int dcn_comm_init(int rank, int world, const void* unique_id128_host, vo
 /* buf[i] = scale * sum_over_ranks(buf[i]), in place, float32 */
 DCN_API int dcn_allreduce_sum_f32(void* comm, void* buf, size_t count, float scale, void* stream);
 DCN_API int dcn_comm_destroy(void* comm);
+
+/* ---- the same all-reduce as ONE kernel over NVLink peer memory (csrc/dcn_p2p.cu) ----------------------------
+ * For the gradient bucket of SURVEY.md 8(e) (1.74 MB: pure latency) every rank publishes its bucket in a buffer the
+ * peers have mapped through CUDA IPC and sums all `world` copies itself, in rank order (bit-identical results on
+ * every rank).  No NCCL, no host synchronisation; the exchange is sequenced by an epoch counter in device memory
+ * that the kernel advances itself, so the call can be captured in a CUDA graph and replayed.
+ *   dcn_p2p_create        allocates the published buffers (room for max_floats) on the current device
+ *   dcn_p2p_local_handle  writes dcn_p2p_handle_bytes() bytes (a cudaIpcMemHandle_t) to host memory; the caller
+ *                         gathers the handles of all ranks (any host-side transport), rank order, and passes the
+ *                         concatenation to dcn_p2p_connect
+ *   dcn_p2p_allreduce_sum_f32  buf[i] = scale * sum_ranks buf[i], in place; buf 16-byte aligned and readable /
+ *                         writable up to the next multiple of 4 floats; every rank must call with the same count */
+DCN_API size_t dcn_p2p_handle_bytes(void);
+DCN_API int dcn_p2p_create(int rank, int world, size_t max_floats, void** comm);
+DCN_API int dcn_p2p_local_handle(void* comm, void* out_handle_host);
+DCN_API int dcn_p2p_connect(void* comm, const void* all_handles_host);
+DCN_API int dcn_p2p_allreduce_sum_f32(void* comm, void* buf, size_t count, float scale, void* stream);
+DCN_API int dcn_p2p_destroy(void* comm);
 
 #ifdef __cplusplus
 }

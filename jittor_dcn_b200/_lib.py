@@ -18,6 +18,7 @@ FLAG_FORCE_SIMT = 1 << 1
 FLAG_NO_GRAD_X = 1 << 2
 FLAG_XT_STAGED = 1 << 4
 PHASE_FORWARD, PHASE_BACKWARD, PHASE_CORNERS = 0, 1, 2
+PHASE_LAYER_FORWARD, PHASE_LAYER_BACKWARD = 3, 4   # offset conv + DCN span (dcn_layer_*)
 
 # every symbol include/dcn_b200.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = (
@@ -26,6 +27,9 @@ EXPORTS = (
     "dcn_profile_end", "dcn_forward", "dcn_backward",
     "dcn_debug_corners", "dcn_comm_unique_id", "dcn_comm_init", "dcn_allreduce_sum_f32",
     "dcn_comm_destroy", "dcn_bn_workspace_bytes", "dcn_bn_relu_forward", "dcn_bn_relu_backward",
+    "dcn_offset_conv_forward", "dcn_layer_forward", "dcn_layer_backward",
+    "dcn_p2p_handle_bytes", "dcn_p2p_create", "dcn_p2p_local_handle", "dcn_p2p_connect",
+    "dcn_p2p_allreduce_sum_f32", "dcn_p2p_destroy",
 )
 
 
@@ -70,10 +74,19 @@ def load():
     lib.dcn_forward.argtypes = [shp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.dcn_backward.argtypes = [shp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.dcn_debug_corners.argtypes = [shp, vp, vp, vp, vp, vp]
+    lib.dcn_offset_conv_forward.argtypes = [shp, vp, vp, vp, vp, vp, sz, vp]
+    lib.dcn_layer_forward.argtypes = [shp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.dcn_layer_backward.argtypes = [shp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.dcn_comm_unique_id.argtypes = [vp]
     lib.dcn_comm_init.argtypes = [ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(vp)]
     lib.dcn_allreduce_sum_f32.argtypes = [vp, vp, sz, ctypes.c_float, vp]
     lib.dcn_comm_destroy.argtypes = [vp]
+    lib.dcn_p2p_handle_bytes.restype = sz
+    lib.dcn_p2p_create.argtypes = [ctypes.c_int, ctypes.c_int, sz, ctypes.POINTER(vp)]
+    lib.dcn_p2p_local_handle.argtypes = [vp, vp]
+    lib.dcn_p2p_connect.argtypes = [vp, vp]
+    lib.dcn_p2p_allreduce_sum_f32.argtypes = [vp, vp, sz, ctypes.c_float, vp]
+    lib.dcn_p2p_destroy.argtypes = [vp]
     i32, f32 = ctypes.c_int32, ctypes.c_float
     lib.dcn_bn_workspace_bytes.restype = sz
     lib.dcn_bn_workspace_bytes.argtypes = [i32]

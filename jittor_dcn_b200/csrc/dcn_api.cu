@@ -145,6 +145,21 @@ static bool use_umma(const DcnShape* s, const Geo& g, int phase) {
   return umma_supported(g, s->operand, phase);
 }
 
+// whole-layer calls (offset conv + DCN span): fp32 operands on the tensor path only
+static bool layer_ok(const DcnShape* s, const Geo& g, int phase) {
+  if ((s->flags & DCN_FLAG_FORCE_SIMT) || s->operand != DCN_OPERAND_FP32) return false;
+  if (!umma_supported(g, DCN_OPERAND_FP32, DCN_PHASE_FORWARD) || !umma_offset_conv_fwd_supported(g)) return false;
+  if (phase == DCN_PHASE_LAYER_FORWARD) return true;
+  return umma_layer_bwd_supported(g);
+}
+
+static size_t layer_workspace(const Geo& g, int operand, int phase) {
+  const size_t f1 = umma_offset_conv_fwd_workspace(g), f2 = umma_workspace_bytes(g, operand, DCN_PHASE_FORWARD);
+  const size_t f = f1 > f2 ? f1 : f2;
+  if (phase == DCN_PHASE_LAYER_FORWARD) return f;
+  return umma_layer_bwd_workspace(g);
+}
+
 }  // namespace dcn
 
 using namespace dcn;
@@ -182,6 +197,8 @@ size_t dcn_workspace_bytes(const DcnShape* s, int phase) {
   Geo g;
   if (geo_or_error(s, &g)) return 0;
   if (phase == DCN_PHASE_CORNERS) return 0;
+  if (phase == DCN_PHASE_LAYER_FORWARD || phase == DCN_PHASE_LAYER_BACKWARD)
+    return layer_ok(s, g, phase) ? layer_workspace(g, s->operand, phase) : 0;
   if (use_umma(s, g, phase)) return umma_workspace_bytes(g, s->operand, phase);
   return simt_workspace(g, s->operand, phase);
 }
@@ -189,6 +206,8 @@ size_t dcn_workspace_bytes(const DcnShape* s, int phase) {
 const char* dcn_path_name(const DcnShape* s, int phase) {
   Geo g;
   if (geo_or_error(s, &g)) return "invalid";
+  if (phase == DCN_PHASE_LAYER_FORWARD || phase == DCN_PHASE_LAYER_BACKWARD)
+    return layer_ok(s, g, phase) ? "umma" : "unsupported";
   return use_umma(s, g, phase) ? "umma" : "simt";
 }
 
@@ -315,6 +334,80 @@ int dcn_backward(const DcnShape* s, const void* x, const void* offset, const voi
   return simt_backward(g, s->flags, (const float*)x, plan, (const float*)weight,
                        (const float*)grad_out, (float*)grad_x, (float*)grad_offset,
                        (float*)grad_weight, (float*)grad_bias, st);
+}
+
+int dcn_offset_conv_forward(const DcnShape* s, const void* x, const void* offset_weight, const void* offset_bias,
+                            void* offset, void* workspace, size_t workspace_bytes, void* stream) {
+  Geo g;
+  int rc = geo_or_error(s, &g);
+  if (rc) return rc;
+  if ((rc = check_ptr(x, "x")) || (rc = check_ptr(offset_weight, "offset_weight")) ||
+      (rc = check_ptr(offset_bias, "offset_bias", false)) || (rc = check_ptr(offset, "offset")) ||
+      (rc = check_ptr(workspace, "workspace")))
+    return rc;
+  if (!layer_ok(s, g, DCN_PHASE_LAYER_FORWARD)) {
+    set_error("offset conv on the engine: shape / operand / flags not supported (dcn_path_name(s, DCN_PHASE_LAYER_FORWARD))");
+    return DCN_ERR_UNSUPPORTED;
+  }
+  const size_t need = umma_offset_conv_fwd_workspace(g);
+  if (workspace_bytes < need) {
+    set_error("offset conv workspace: have %zu bytes, need %zu", workspace_bytes, need);
+    return DCN_ERR_WORKSPACE;
+  }
+  return umma_offset_conv_forward(g, x, (const float*)offset_weight, (const float*)offset_bias, (float*)offset,
+                                  workspace, (cudaStream_t)stream, !(s->flags & DCN_FLAG_XT_STAGED));
+}
+
+int dcn_layer_forward(const DcnShape* s, const void* x, const void* offset_weight, const void* offset_bias,
+                      const void* weight, const void* bias, void* offset, void* out, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  Geo g;
+  int rc = geo_or_error(s, &g);
+  if (rc) return rc;
+  if ((rc = check_ptr(weight, "weight")) || (rc = check_ptr(bias, "bias", false)) || (rc = check_ptr(out, "out")))
+    return rc;
+  if (!layer_ok(s, g, DCN_PHASE_LAYER_FORWARD)) {
+    set_error("layer forward: shape / operand / flags not supported (dcn_path_name(s, DCN_PHASE_LAYER_FORWARD))");
+    return DCN_ERR_UNSUPPORTED;
+  }
+  const size_t need = layer_workspace(g, s->operand, DCN_PHASE_LAYER_FORWARD);
+  if (workspace_bytes < need) {
+    set_error("layer forward workspace: have %zu bytes, need %zu", workspace_bytes, need);
+    return DCN_ERR_WORKSPACE;
+  }
+  if ((rc = dcn_offset_conv_forward(s, x, offset_weight, offset_bias, offset, workspace, workspace_bytes, stream)))
+    return rc;
+  return umma_forward(g, s->operand, s->flags | DCN_FLAG_XT_STAGED, x, (const float*)offset, weight,
+                      (const float*)bias, out, workspace, (cudaStream_t)stream);
+}
+
+int dcn_layer_backward(const DcnShape* s, const void* x, const void* offset, const void* offset_weight,
+                       const void* weight, const void* grad_out, void* grad_x, void* grad_offset_weight,
+                       void* grad_offset_bias, void* grad_weight, void* grad_bias, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  Geo g;
+  int rc = geo_or_error(s, &g);
+  if (rc) return rc;
+  const bool want_gx = !(s->flags & DCN_FLAG_NO_GRAD_X);
+  if ((rc = check_ptr(x, "x")) || (rc = check_ptr(offset, "offset")) ||
+      (rc = check_ptr(offset_weight, "offset_weight")) || (rc = check_ptr(weight, "weight")) ||
+      (rc = check_ptr(grad_out, "grad_out")) || (rc = check_ptr(grad_x, "grad_x", want_gx)) ||
+      (rc = check_ptr(grad_offset_weight, "grad_offset_weight")) ||
+      (rc = check_ptr(grad_offset_bias, "grad_offset_bias", false)) || (rc = check_ptr(grad_weight, "grad_weight")) ||
+      (rc = check_ptr(grad_bias, "grad_bias", false)) || (rc = check_ptr(workspace, "workspace")))
+    return rc;
+  if (!layer_ok(s, g, DCN_PHASE_LAYER_BACKWARD)) {
+    set_error("layer backward: shape / operand / flags not supported (dcn_path_name(s, DCN_PHASE_LAYER_BACKWARD))");
+    return DCN_ERR_UNSUPPORTED;
+  }
+  const size_t need = layer_workspace(g, s->operand, DCN_PHASE_LAYER_BACKWARD);
+  if (workspace_bytes < need) {
+    set_error("layer backward workspace: have %zu bytes, need %zu", workspace_bytes, need);
+    return DCN_ERR_WORKSPACE;
+  }
+  return umma_layer_backward(g, s->flags, x, (const float*)offset, (const float*)offset_weight, weight, grad_out,
+                             (float*)grad_x, (float*)grad_offset_weight, (float*)grad_offset_bias,
+                             (float*)grad_weight, (float*)grad_bias, workspace, need, (cudaStream_t)stream);
 }
 
 int dcn_debug_corners(const DcnShape* s, const void* offset, int32_t* y0, int32_t* x0, float* w4,

@@ -31,6 +31,14 @@ struct Geo {
   //   reference: row <- channel n ("x" offset: the sample is transposed), column <- channel N + n
   //   DCNv1    : row <- channel 2n (dy),                                   column <- channel 2n + 1 (dx)
   int row_mul, row_add, col_mul, col_add;
+  // PLAIN problems (the companion offset convolution, deform_conv.py:16-21,58 / train.py:80-85,98, on the tensor
+  // kernels): a regular convolution = DCNv1 coordinates with all offsets zero, i.e. ONE exact pixel per (pixel, tap)
+  // instead of four weighted corners; no offset tensor is read.  plain_geo() builds such a Geo; o_valid = 2N real
+  // output channels inside the padded O the forward accumulators need.
+  int plain, o_valid;
+  // channel permutation of the staged copy the plain problem shares with its Torch-layout DCN layer (0 = none):
+  // staged channel c' holds image channel (c' % perm_G) * perm_Cs + c' / perm_G  (dcn_umma_prep.cu)
+  int perm_G, perm_Cs;
 };
 
 __host__ __device__ __forceinline__ int off_row_ch(const Geo& g, int n) { return n * g.row_mul + g.row_add; }
@@ -42,7 +50,9 @@ __host__ __device__ __forceinline__ int off_col_ch(const Geo& g, int n) { return
 //   DCNv1: column (c, n) of the (c, tap)-ordered weight, i.e. element c*N + n.
 __host__ __device__ __forceinline__ size_t wt_index(const Geo& g, int o, int j) {
   if (g.variant == DCN_VARIANT_DCNV1) {
-    const int n = j / g.C, c = j - n * g.C;
+    const int n = j / g.C;
+    int c = j - n * g.C;
+    if (g.perm_G) c = (c % g.perm_G) * g.perm_Cs + c / g.perm_G;
     return (size_t)o * g.K + (size_t)c * g.N + n;
   }
   return (size_t)o * g.K + j;
@@ -64,6 +74,9 @@ __host__ inline int make_geo(const DcnShape* s, Geo* g) {
     return DCN_ERR_BAD_SHAPE;
   g->B = s->B; g->C = s->C; g->O = s->O; g->H = s->H; g->W = s->W;
   g->Oimg = s->O;
+  g->plain = 0;
+  g->o_valid = s->O;
+  g->perm_G = g->perm_Cs = 0;
   g->N = s->kh * s->kw;
   g->Ho = (s->H + 2 * s->ph - s->kh) / s->sh + 1;
   g->Wo = (s->W + 2 * s->pw - s->kw) / s->sw + 1;

@@ -29,6 +29,8 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
                       const void* gout, float* goff, float* gw, uint8_t* wtiles, uint8_t* gtiles,
                       cudaStream_t st);
 size_t umma_bwd_data_gtile_bytes(const Geo& g, int operand);
+bool o_groups(const Geo& g, int* size);
+Geo o_group_geo(const Geo& g, int o0, int size);
 
 static size_t plan_bytes(const Geo& g) { return align_up(sizeof(Tap) * (size_t)g.B * g.P, 1024); }
 
@@ -43,6 +45,40 @@ bool umma_bwd_supported(const Geo& g, int operand) {
   return operand == DCN_OPERAND_FP32 || umma_bwd_data_supported(g, operand);
 }
 
+// ---- companion offset convolution (PLAIN problem) inside the layer's backward pass ---------------------------------
+static bool plain_bwd_ok(const Geo& g) {
+  Tiling t;
+  if (!make_tiling(g, &t)) return false;
+  const Geo gp = plain_geo(g, t, false);
+  return umma_bwd_data_supported(gp, DCN_OPERAND_FP32) && umma_bwd_data_fuses_wgrad(gp, DCN_OPERAND_FP32);
+}
+
+// Whole-layer backward (DCN span + offset conv) on the tensor path: fp32 operands, one output-channel group or more,
+// data gradient on the tcgen05 kernel (so that the channels-last grad_x accumulator exists for both passes).
+bool umma_layer_bwd_supported(const Geo& g) {
+  int gsize;
+  if (!o_groups(g, &gsize)) return false;
+  const Geo g0 = o_group_geo(g, 0, gsize);
+  return umma_bwd_supported(g0, DCN_OPERAND_FP32) && use_umma_data(g0, DCN_OPERAND_FP32) && plain_bwd_ok(g);
+}
+
+static size_t goff_bytes(const Geo& g) { return align_up(sizeof(float) * (size_t)g.B * 2 * g.N * g.HW, 1024); }
+
+// [xt][rest as umma_bwd_workspace, its tile regions sized for the larger of the two passes][grad_offset]
+size_t umma_layer_bwd_workspace(const Geo& g) {
+  int gsize;
+  if (!o_groups(g, &gsize)) return 0;
+  const Geo g0 = o_group_geo(g, 0, gsize);
+  Tiling t;
+  if (!make_tiling(g, &t)) return 0;
+  const Geo gp = plain_geo(g, t, false);
+  const size_t tiles_dcn = umma_bwd_data_wtile_bytes(g0, DCN_OPERAND_FP32) + umma_bwd_data_gtile_bytes(g0, DCN_OPERAND_FP32);
+  const size_t tiles_pln = umma_bwd_data_wtile_bytes(gp, DCN_OPERAND_FP32) + umma_bwd_data_gtile_bytes(gp, DCN_OPERAND_FP32);
+  const size_t a = umma_xt_bytes(g, DCN_OPERAND_FP32) + (tiles_dcn > tiles_pln ? tiles_dcn : tiles_pln);
+  const size_t c = umma_wgrad_gtile_bytes(g0, DCN_OPERAND_FP32);
+  return umma_xt_bytes(g, DCN_OPERAND_FP32) + (a > c ? a : c) + goff_bytes(g);
+}
+
 size_t umma_bwd_workspace(const Geo& g, int operand) {
   // [xt] then either [gxt | Wm^T tiles | grad_out tiles] (tensor-path data gradient) or [sampling plan]
   // (generic); the unfused weight-gradient pass runs last and re-uses that region for its own staged
@@ -55,14 +91,14 @@ size_t umma_bwd_workspace(const Geo& g, int operand) {
   return umma_xt_bytes(g, operand) + (m > c ? m : c);
 }
 
-bool o_groups(const Geo& g, int* size);
-Geo o_group_geo(const Geo& g, int o0, int size);
-
 // g is the whole layer; the kernels run per output-channel group (dcn_umma_host.cu) — one group unless
 // O > 256.  grad_x (via gxt) and grad_offset accumulate over the groups.
+// woff != nullptr: whole-layer backward — the companion offset convolution's backward runs as a PLAIN pass between the
+// DCN data gradient and the final transposition: grad_offset (goff) is its grad_out, its data gradient accumulates
+// into the SAME channels-last grad_x buffer, gwoff / gboff receive its parameter gradients.
 int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, const float* off, const void* wtv,
                       const void* goutv, float* gx, float* goff, float* gw, float* gb, void* workspace,
-                      cudaStream_t st) {
+                      cudaStream_t st, const float* woff, float* gwoff, float* gboff) {
   int gsize;
   if (!o_groups(g, &gsize)) {
     set_error("umma backward: O = %d cannot be split into groups", g.O);
@@ -101,11 +137,25 @@ int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, cons
                                   (const uint8_t*)goutv + (size_t)o0 * g.HW * esz, goff, gwc, wtiles, gtiles, st)))
         return rc;
     }
+    if (woff) {
+      const Geo gp = plain_geo(g, t, false);
+      uint8_t* wtiles2 = rest + umma_xt_bytes(g, DCN_OPERAND_FP32);
+      uint8_t* gtiles2 = wtiles2 + umma_bwd_data_wtile_bytes(gp, DCN_OPERAND_FP32);
+      DCN_CUDA_TRY(cudaMemsetAsync(gwoff, 0, sizeof(float) * (size_t)gp.O * g.K, st));
+      if ((rc = umma_bwd_data_any(gp, DCN_OPERAND_FP32, xt, want_gx ? gxt : nullptr, nullptr, woff, goff, nullptr, gwoff,
+                                  wtiles2, gtiles2, st)))
+        return rc;
+      if ((rc = launch_bias_grad(gp, goff, DCN_OPERAND_FP32, gboff, st))) return rc;
+    }
     if (want_gx && (rc = launch_nhwc_to_nchw_add(g, t, gxt, gx, (flags & DCN_FLAG_ACCUM_GRAD_X) ? 1 : 0, st)))
       return rc;
     if ((rc = launch_bias_grad(g, goutv, operand, gb, st))) return rc;
     if (all_fused) return DCN_OK;
   } else {
+    if (woff) {
+      set_error("layer backward: the data gradient of this shape does not run on the tensor path");
+      return DCN_ERR_UNSUPPORTED;
+    }
     all_fused = false;
     Tap* plan = (Tap*)rest;
     if ((rc = launch_plan(g, off, plan, st))) return rc;
@@ -124,6 +174,19 @@ int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, cons
       return rc;
   }
   return DCN_OK;
+}
+
+}  // namespace dcn
+
+namespace dcn {
+
+// Whole-layer backward: see umma_backward_any.  The internal grad_offset buffer sits at the tail of the workspace.
+int umma_layer_backward(const Geo& g, int flags, const void* x, const float* off, const float* woff, const void* wt,
+                        const void* gout, float* gx, float* gwoff, float* gboff, float* gw, float* gb,
+                        void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  float* goff = (float*)((uint8_t*)workspace + workspace_bytes - goff_bytes(g));
+  return umma_backward_any(g, DCN_OPERAND_FP32, flags, x, off, wt, gout, gx, goff, gw, gb, workspace, st, woff, gwoff,
+                           gboff);
 }
 
 }  // namespace dcn

@@ -124,7 +124,7 @@ struct PlanWork {
   int h, w, n, chan_base, gidx, valid;
 };
 
-template <int VARIANT>
+template <int VARIANT, bool PLAIN = false>
 __device__ __forceinline__ void plan_prepare(const Params& P, int tile, int cb, int e, PlanWork& pw) {
   const Geo& g = P.g;
   pw.valid = 0;
@@ -154,11 +154,30 @@ __device__ __forceinline__ void plan_prepare(const Params& P, int tile, int cb, 
   pw.h = (int)h;
   pw.w = (int)w;
   pw.n = (int)n;
-  pw.gidx = (b * 2 * g.N + off_row_ch(g, (int)n)) * g.HW + (int)p;  // target of g_iy
-  const float* ob = P.off + (size_t)b * 2 * g.N * g.HW;
-  pw.ox = __ldg(ob + (size_t)off_row_ch(g, (int)n) * g.HW + p);
-  pw.oy = __ldg(ob + (size_t)off_col_ch(g, (int)n) * g.HW + p);
+  if (PLAIN) {
+    pw.gidx = 0;  // live entry; a plain problem has no offsets and no coordinate gradient
+  } else {
+    pw.gidx = (b * 2 * g.N + off_row_ch(g, (int)n)) * g.HW + (int)p;  // target of g_iy
+    const float* ob = P.off + (size_t)b * 2 * g.N * g.HW;
+    pw.ox = __ldg(ob + (size_t)off_row_ch(g, (int)n) * g.HW + p);
+    pw.oy = __ldg(ob + (size_t)off_col_ch(g, (int)n) * g.HW + p);
+  }
   pw.valid = 1;
+}
+
+// PLAIN: the one pixel a (pixel, tap) pair reads / its gradient goes to (dcn_umma_common.cuh:plain_base)
+__device__ __forceinline__ ScatEntry plan_finish_plain(const Geo& g, const PlanWork& pw) {
+  ScatEntry e;
+  int base = xt_null_base(g);
+  e.fx = e.fy = 0.f;
+  e.gidx = -1;
+  if (pw.valid) {
+    bool inside;
+    base = plain_base(g, pw.h, pw.w, pw.n, inside);
+    if (inside) e.gidx = 0;
+  }
+  e.base = 4u * (uint32_t)(base + pw.chan_base);
+  return e;
 }
 
 __device__ __forceinline__ ScatEntry plan_finish(const Geo& g, const PlanWork& pw) {
@@ -182,7 +201,10 @@ __device__ __forceinline__ ScatEntry plan_finish(const Geo& g, const PlanWork& p
 
 // RW = lanes that share one sampling point (32, or 16 when only 16 channels do)
 // BF  = bf16 operand mode: x / weight / grad_out are bfloat16, one image per operand, one MMA per K step
-template <int VARIANT, int RW, bool FUSE, bool BF, int PW>
+// PLAIN = backward of a regular convolution (the companion offset conv, Geo::plain): one exact pixel per column
+//         instead of four weighted corners — one red.global per column, the "sample" of the fused weight gradient
+//         is the pixel itself, no coordinate gradient
+template <int VARIANT, int RW, bool FUSE, bool BF, int PW, bool PLAIN = false>
 __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __grid_constant__ Params P) {
   constexpr int NIMG = BF ? 1 : 2;
   typedef typename std::conditional<BF, __nv_bfloat16, float>::type XT;
@@ -341,6 +363,12 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
             constexpr int XS = BF ? 1 : 0;
             const char* xp = ximg + (e4.x >> XS);
             const float v0 = (float)__ldg(reinterpret_cast<const XT*>(xp));
+            if (PLAIN) {
+              if (gimg && (int)e4.w >= 0) atomicAdd(reinterpret_cast<float*>(gimg + e4.x), gs);
+              part_g[8 * nb + u] = part_g[8 * NB + 8 * nb + u] = 0.f;
+              if (FUSE) smp8[u] = v0;   // dead entries read the all-zero frame-only block
+              continue;
+            }
             const float v1 = (float)__ldg(reinterpret_cast<const XT*>(xp + dx1));
             const float v2 = (float)__ldg(reinterpret_cast<const XT*>(xp + dx2));
             const float v3 = (float)__ldg(reinterpret_cast<const XT*>(xp + dx2 + dx1));
@@ -373,6 +401,7 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
             if (!BF) *reinterpret_cast<uint4*>(s_row + s_img + so) = lo;
           }
           }  // sub-batch
+          if (PLAIN) return;
           // butterfly reduce-scatter over the RW lanes that share the sampling points:
           // afterwards lane gl (< 16*NB) holds the total of value index gl
           if (!WIDE && RW == 32) {
@@ -428,6 +457,21 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
             constexpr int XS = BF ? 1 : 0;
             const char* xp = xpair + (e4.x >> XS);
             float2 v0, v1, v2, v3;
+            if (PLAIN) {
+              if (BF) {
+                const uint32_t r0 = __ldg(reinterpret_cast<const uint32_t*>(xp));
+                v0 = make_float2(__uint_as_float(r0 << 16), __uint_as_float(r0 & 0xffff0000u));
+              } else {
+                v0 = __ldg(reinterpret_cast<const float2*>(xp));
+              }
+              if (gpair && (int)e4.w >= 0) atomicAdd(reinterpret_cast<float2*>(gpair + e4.x), make_float2(ga[u], gb[u]));
+              part_g[u] = part_g[4 + u] = 0.f;
+              if (FUSE) {
+                sa[u] = v0.x;   // dead entries read the all-zero frame-only block
+                sb2[u] = v0.y;
+              }
+              continue;
+            }
             if (BF) {
               const uint32_t r0 = __ldg(reinterpret_cast<const uint32_t*>(xp));
               const uint32_t r1 = __ldg(reinterpret_cast<const uint32_t*>(xp + dx1));
@@ -478,6 +522,7 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
             *reinterpret_cast<uint2*>(ra + 128 + sob) = hi;
             if (!BF) *reinterpret_cast<uint2*>(ra + 128 + s_img + sob) = lo;
           }
+          if (PLAIN) return;
           // reduce-scatter of the 8 values over the 16 lanes of equal parity (lane bits 4..1)
 #pragma unroll
           for (int k = 0; k < 8; ++k) part_g[k] += __shfl_xor_sync(0xffffffffu, part_g[k], 16);
@@ -786,7 +831,7 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
     if (tile0 < P.num_tiles) {
 #pragma unroll
       for (int u = 0; u < kPlanPerThread; ++u)
-        if (pt + u * kPlanThreads < n_ent) plan_prepare<VARIANT>(P, tile0, cb0, pt + u * kPlanThreads, pw[u]);
+        if (pt + u * kPlanThreads < n_ent) plan_prepare<VARIANT, PLAIN>(P, tile0, cb0, pt + u * kPlanThreads, pw[u]);
     }
     for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
       for (int cb = cb0; cb < cb1; ++cb) {
@@ -794,7 +839,8 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
         mbar_wait_relaxed(&pempty[pb], pphase ^ 1, 64);
 #pragma unroll
         for (int u = 0; u < kPlanPerThread; ++u)
-          if (pt + u * kPlanThreads < n_ent) pl[pt + u * kPlanThreads] = plan_finish(g, pw[u]);
+          if (pt + u * kPlanThreads < n_ent)
+            pl[pt + u * kPlanThreads] = PLAIN ? plan_finish_plain(g, pw[u]) : plan_finish(g, pw[u]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&pfull[pb]);
         int ntile = tile, ncb = cb + 1;
@@ -805,7 +851,7 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
         if (ntile < P.num_tiles) {
 #pragma unroll
           for (int u = 0; u < kPlanPerThread; ++u)
-            if (pt + u * kPlanThreads < n_ent) plan_prepare<VARIANT>(P, ntile, ncb, pt + u * kPlanThreads, pw[u]);
+            if (pt + u * kPlanThreads < n_ent) plan_prepare<VARIANT, PLAIN>(P, ntile, ncb, pt + u * kPlanThreads, pw[u]);
         }
         pb ^= 1;
         if (pb == 0) pphase ^= 1;
@@ -1262,7 +1308,7 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
     grid = P.nslices * P.nchunks;
   }
   const bool narrow = g.variant == DCN_VARIANT_TORCH ? P.Gt == 16 : g.C == 16;  // 16 channels per sampling point
-  KernelScope scope("umma_bwd_data_kernel", st);
+  KernelScope scope(g.plain ? "umma_offset_conv_bwd_kernel" : "umma_bwd_data_kernel", st);
 #define DCN_LAUNCH_BD(V, RW, F, PW)                                                                       \
   do {                                                                                                    \
     if (bf) {                                                                                             \
@@ -1278,6 +1324,29 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
   // <= 128 plan entries per block (2 per plan thread): 2 plan warps are enough (20 warps, 96 registers for
   // the scatter loop); with more sampling points per block the plan would become the bottleneck: 4 warps
   const bool slim = P.plan_cap <= 128;
+  if (g.plain) {
+    // regular convolution (the companion offset conv): pixel-row layout, fp32, weight gradient fused
+    if (g.variant == DCN_VARIANT_TORCH || bf || !P.fuse_w) {
+      set_error("plain (offset-conv) backward: pixel-row layout, fp32 operands, fused weight gradient only");
+      return DCN_ERR_UNSUPPORTED;
+    }
+#define DCN_LAUNCH_PLAIN(RW, PW)                                                                              \
+  do {                                                                                                        \
+    DCN_CUDA_TRY(cudaFuncSetAttribute(bd::bwd_data_kernel<DCN_VARIANT_JITTOR, RW, true, false, PW, true>,     \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+    bd::bwd_data_kernel<DCN_VARIANT_JITTOR, RW, true, false, PW, true><<<grid, bd::threads_of(PW), smem, st>>>(P); \
+  } while (0)
+    if (narrow) {
+      if (slim) DCN_LAUNCH_PLAIN(16, 2);
+      else DCN_LAUNCH_PLAIN(16, 4);
+    } else {
+      if (slim) DCN_LAUNCH_PLAIN(32, 2);
+      else DCN_LAUNCH_PLAIN(32, 4);
+    }
+#undef DCN_LAUNCH_PLAIN
+    DCN_KERNEL_CHECK("umma_bwd_data_kernel");
+    return DCN_OK;
+  }
 #define DCN_LAUNCH_BD2(V, RW, F)                       \
   do {                                                 \
     if (slim) DCN_LAUNCH_BD(V, RW, F, 2);              \

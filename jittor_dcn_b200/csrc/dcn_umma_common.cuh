@@ -139,6 +139,37 @@ __device__ __forceinline__ int xt_corner_base(const Geo& g, int y0, int x0, bool
   return inside ? ((y0 + 1) * (g.W + 2) + (x0 + 1)) * g.C : xt_null_base(g);
 }
 
+// PLAIN problems (regular convolution, Geo::plain — the companion offset conv): tap (ki, kj) of output pixel (h, w)
+// reads image pixel (h*sh - ph + ki, w*sw - pw + kj) = frame position (+1, +1).  Anything inside the framed copy is
+// either the pixel or the zero border (= zero padding; gradient that lands there is discarded); positions outside
+// the frame (padding > 1) use the frame-only block with weight 0.
+__device__ __forceinline__ int plain_base(const Geo& g, int h, int w, int n, bool& inside) {
+  const int ki = n / g.kw, kj = n - ki * g.kw;
+  const int fy = h * g.sh - g.ph + ki + 1, fx = w * g.sw - g.pw + kj + 1;
+  inside = (unsigned)fy <= (unsigned)(g.H + 2) && (unsigned)fx <= (unsigned)(g.W + 1);
+  return inside ? (fy * (g.W + 2) + fx) * g.C : xt_null_base(g);
+}
+
+// The plain Geo of a DCN layer's companion offset convolution (deform_conv.py:16-21 / train.py:80-85): same input,
+// kernel, stride and padding, 2N output channels, columns ordered (tap, staged channel) like the DCNv1 layout, weight
+// element (o, c, ki, kj) with c un-permuted when the staged copy follows the Torch layout's channel permutation.
+// pad_o: round O up to 16 accumulator columns (forward kernel); the real count stays in o_valid / Oimg.
+__host__ inline Geo plain_geo(const Geo& g, const Tiling& layer_tiling, bool pad_o) {
+  Geo p = g;
+  p.variant = DCN_VARIANT_DCNV1;
+  p.plain = 1;
+  p.o_valid = 2 * g.N;
+  p.Oimg = 2 * g.N;
+  p.O = pad_o ? (2 * g.N + 15) / 16 * 16 : 2 * g.N;
+  p.perm_G = p.perm_Cs = 0;
+  if (g.variant == DCN_VARIANT_TORCH) {
+    p.perm_G = layer_tiling.G;
+    p.perm_Cs = layer_tiling.Cs;
+  }
+  p.row_mul = 2; p.row_add = 0; p.col_mul = 2; p.col_add = 1;
+  return p;
+}
+
 // Plan entry as the forward gather warps consume it (32 bytes in shared memory): the four
 // corners' element offsets inside image b of the framed copy and their weights.
 struct __align__(16) PlanEntry {

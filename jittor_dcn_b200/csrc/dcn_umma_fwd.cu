@@ -88,7 +88,7 @@ struct PlanWork {
   int h, w, n, chan_base, valid;
 };
 
-template <int VARIANT>
+template <int VARIANT, bool PLAIN = false>
 __device__ __forceinline__ void plan_prepare(const Geo& g, const Tiling& t, const float* __restrict__ off,
                                              int tile, int kb, int e, PlanWork& pw) {
   pw.valid = 0;
@@ -123,10 +123,27 @@ __device__ __forceinline__ void plan_prepare(const Geo& g, const Tiling& t, cons
   pw.h = (int)h;
   pw.w = (int)w;
   pw.n = n;
-  const float* ob = off + (size_t)b * 2 * g.N * g.HW;
-  pw.ox = __ldg(ob + (size_t)off_row_ch(g, n) * g.HW + p);
-  pw.oy = __ldg(ob + (size_t)off_col_ch(g, n) * g.HW + p);
+  if (!PLAIN) {
+    const float* ob = off + (size_t)b * 2 * g.N * g.HW;
+    pw.ox = __ldg(ob + (size_t)off_row_ch(g, n) * g.HW + p);
+    pw.oy = __ldg(ob + (size_t)off_col_ch(g, n) * g.HW + p);
+  }
   pw.valid = 1;
+}
+
+__device__ __forceinline__ PlanEntry plan_finish_plain(const Geo& g, const PlanWork& pw) {
+  PlanEntry e;
+  int base = xt_null_base(g);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) e.w[k] = 0.f;
+  if (pw.valid) {
+    bool inside;
+    base = plain_base(g, pw.h, pw.w, pw.n, inside);
+    e.w[0] = inside ? 1.f : 0.f;
+  }
+  base += pw.chan_base;
+  e.off[0] = e.off[1] = e.off[2] = e.off[3] = base;
+  return e;
 }
 
 // coordinate chain (bit-exact, dcn_common.cuh:tap_of) -> branch-free gather entry: corners
@@ -170,7 +187,8 @@ __device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
 // BF = bf16 operand mode (DCN_OPERAND_BF16): x / weight / grad_out are bfloat16 in HBM, every
 // operand is ONE bf16 image and every K step ONE MMA; otherwise fp32 with the hi/lo split (two
 // images, three MMAs).  A gather item is one 16-byte load per corner: V = 4 fp32 or 8 bf16 channels.
-template <int VARIANT, int MODE, bool BF>
+// PLAIN = regular convolution on the same machinery (the companion offset conv): one exact pixel per entry.
+template <int VARIANT, int MODE, bool BF, bool PLAIN = false>
 __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_constant__ FwdParams P,
                                                                    const __grid_constant__ CUtensorMap tmap_out) {
   constexpr int V = BF ? 8 : 4;
@@ -342,6 +360,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
           if (valid) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
+              if (PLAIN && c0 + i >= g.o_valid) break;   // padded accumulator columns of a plain problem
               const float bv = P.bias ? __ldg(P.bias + c0 + i) : 0.f;
               P.out[out_off + (size_t)(c0 + i) * g.HW] = v[i] + bv;
             }
@@ -539,7 +558,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
       for (int u = 0; u < kPlanPerThread; ++u)
         if (pt + u * kPlanThreads < n_ent)
-          plan_prepare<VARIANT>(g, t, P.off, tile0, kb_of(kb0), pt + u * kPlanThreads, pw[u]);
+          plan_prepare<VARIANT, PLAIN>(g, t, P.off, tile0, kb_of(kb0), pt + u * kPlanThreads, pw[u]);
     }
     for (int tile = tile0; tile < t.num_tiles; tile = next_tile(tile)) {
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -548,7 +567,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         // finish this K block's entries (their offset loads were issued one block ago) ...
 #pragma unroll
         for (int u = 0; u < kPlanPerThread; ++u)
-          if (pt + u * kPlanThreads < n_ent) pl[pt + u * kPlanThreads] = plan_finish(g, pw[u]);
+          if (pt + u * kPlanThreads < n_ent)
+            pl[pt + u * kPlanThreads] = PLAIN ? plan_finish_plain(g, pw[u]) : plan_finish(g, pw[u]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&pfull[pbuf]);
         // ... and start the next block's
@@ -561,7 +581,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
           for (int u = 0; u < kPlanPerThread; ++u)
             if (pt + u * kPlanThreads < n_ent)
-              plan_prepare<VARIANT>(g, t, P.off, ntile, kb_of(nkb), pt + u * kPlanThreads, pw[u]);
+              plan_prepare<VARIANT, PLAIN>(g, t, P.off, ntile, kb_of(nkb), pt + u * kPlanThreads, pw[u]);
         }
         pbuf ^= 1;
         if (pbuf == 0) pphase ^= 1;
@@ -656,12 +676,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         jit_cols(q.kbm, jc, tl, ok);
         pl += tl * 128;
       }
-      const int4 off = *reinterpret_cast<const int4*>(pl[ent_idx[it]].off);
       const XT* base = img[it] + jc;
-      v[buf][0] = __ldg(reinterpret_cast<const uint4*>(base + off.x));
-      v[buf][1] = __ldg(reinterpret_cast<const uint4*>(base + off.y));
-      v[buf][2] = __ldg(reinterpret_cast<const uint4*>(base + off.z));
-      v[buf][3] = __ldg(reinterpret_cast<const uint4*>(base + off.w));
+      if (PLAIN) {
+        v[buf][0] = __ldg(reinterpret_cast<const uint4*>(base + pl[ent_idx[it]].off[0]));
+      } else {
+        const int4 off = *reinterpret_cast<const int4*>(pl[ent_idx[it]].off);
+        v[buf][0] = __ldg(reinterpret_cast<const uint4*>(base + off.x));
+        v[buf][1] = __ldg(reinterpret_cast<const uint4*>(base + off.y));
+        v[buf][2] = __ldg(reinterpret_cast<const uint4*>(base + off.z));
+        v[buf][3] = __ldg(reinterpret_cast<const uint4*>(base + off.w));
+      }
     };
     // blend one pair of channels held as the two bf16 halves of a word (bf16 mode)
     auto blend_bf = [](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, const float4& w) {
@@ -711,7 +735,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         float4 w = *reinterpret_cast<const float4*>(pl[ent_idx[it]].w);
         if (VARIANT != DCN_VARIANT_TORCH && !col_ok) w = make_float4(0.f, 0.f, 0.f, 0.f);
         const uint4* c4 = v[it & 1];
-        if (BF) {
+        if (PLAIN) {
+          // one exact pixel: the "blend" is a product with 1 (or with 0 for padding columns / positions off the frame)
+          float4 r;
+          r.x = __uint_as_float(c4[0].x) * w.x;
+          r.y = __uint_as_float(c4[0].y) * w.x;
+          r.z = __uint_as_float(c4[0].z) * w.x;
+          r.w = __uint_as_float(c4[0].w) * w.x;
+          uint2 hi, lo;
+          split4(r, hi, lo);
+          *reinterpret_cast<uint2*>(a_hi + st_off[it]) = hi;
+          *reinterpret_cast<uint2*>(a_lo + st_off[it]) = lo;
+        } else if (BF) {
           // 8 channels: blend in fp32, ONE bf16 rounding of the sample, one 16-byte store
           uint4 r;
           r.x = blend_bf(c4[0].x, c4[1].x, c4[2].x, c4[3].x, w);
@@ -852,6 +887,17 @@ static void common_params(const Geo& g, FwdParams& P) {
 template <int MODE>
 static int launch_gemm(const Geo& g, int operand, const FwdParams& P, const CUtensorMap& tmap, int grid,
                        size_t smem, cudaStream_t st) {
+  if (g.plain) {
+    // regular convolution: pixel-row tiling, fp32 operands only
+    if (g.variant == DCN_VARIANT_TORCH || operand != DCN_OPERAND_FP32) {
+      set_error("plain (offset-conv) problems run in the pixel-row layout with fp32 operands");
+      return DCN_ERR_UNSUPPORTED;
+    }
+    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<DCN_VARIANT_JITTOR, MODE, false, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_gemm_kernel<DCN_VARIANT_JITTOR, MODE, false, true><<<grid, kFwdThreads, smem, st>>>(P, tmap);
+    return DCN_OK;
+  }
 #define DCN_GEMM_CASE(V, BFV)                                                                              \
   do {                                                                                                     \
     DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<V, MODE, BFV>,                                      \
@@ -934,10 +980,39 @@ int umma_forward_any(const Geo& g, int operand, const void* x, const float* off,
   const int sms = num_sms();
   const int groups = (P.t.num_tiles + P.tpg - 1) / P.tpg;  // CTAs walk groups of tpg tiles
   const int grid = groups < sms ? groups : sms;
-  KernelScope scope("umma_fwd_kernel", st);
+  KernelScope scope(g.plain ? "umma_offset_conv_fwd_kernel" : "umma_fwd_kernel", st);
   if ((rc = launch_gemm<MODE_FWD>(g, operand, P, tmap, grid, smem, st))) return rc;
   DCN_KERNEL_CHECK("umma_fwd_kernel");
   return DCN_OK;
+}
+
+// ---- the companion offset convolution (deform_conv.py:16-21,58 / train.py:80-85,98) as a PLAIN problem -----------
+// g is the DCN layer; the staged copy of x at the head of the workspace is the layer's (channel-permuted for the
+// Torch layout), so offset conv, dcn_forward and dcn_backward share ONE staging pass.
+bool umma_offset_conv_fwd_supported(const Geo& g) {
+  Tiling t;
+  if (!make_tiling(g, &t)) return false;          // the layer's own staging layout
+  const Geo gp = plain_geo(g, t, true);
+  return umma_fwd_supported(gp, DCN_OPERAND_FP32);
+}
+
+size_t umma_offset_conv_fwd_workspace(const Geo& g) {
+  Tiling t;
+  if (!make_tiling(g, &t)) return 0;
+  return umma_fwd_workspace(plain_geo(g, t, true), DCN_OPERAND_FP32);
+}
+
+int umma_offset_conv_forward(const Geo& g, const void* x, const float* woff, const float* boff, float* offset_out,
+                             void* workspace, cudaStream_t st, bool stage_x) {
+  Tiling t;
+  if (!make_tiling(g, &t)) {
+    set_error("offset conv: layer shape not tileable");
+    return DCN_ERR_UNSUPPORTED;
+  }
+  int rc;
+  if (stage_x && (rc = launch_nchw_to_nhwc(g, t, x, workspace, DCN_OPERAND_FP32, st))) return rc;
+  const Geo gp = plain_geo(g, t, true);
+  return umma_forward_any(gp, DCN_OPERAND_FP32, x, nullptr, woff, boff, offset_out, workspace, st, false);
 }
 
 // grad_weight[O, K] (zeroed here) = sum over all rows of gout^T * S, S re-sampled by the same

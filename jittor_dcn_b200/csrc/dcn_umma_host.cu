@@ -20,7 +20,7 @@ bool umma_bwd_supported(const Geo& g, int operand);
 size_t umma_bwd_workspace(const Geo& g, int operand);
 int umma_backward_any(const Geo& g, int operand, int flags, const void* x, const float* off, const void* wt,
                       const void* gout, float* gx, float* goff, float* gw, float* gb, void* workspace,
-                      cudaStream_t st);
+                      cudaStream_t st, const float* woff, float* gwoff, float* gboff);
 
 bool o_groups(const Geo& g, int* size) {
   if (g.O <= 256) {
@@ -36,6 +36,7 @@ bool o_groups(const Geo& g, int* size) {
 Geo o_group_geo(const Geo& g, int o0, int size) {
   Geo c = g;
   c.O = g.O - o0 < size ? g.O - o0 : size;
+  c.o_valid = c.O;
   return c;
 }
 
@@ -58,7 +59,6 @@ size_t umma_workspace_bytes(const Geo& g, int operand, int phase) {
 
 int umma_forward(const Geo& g, int operand, int flags, const void* x, const float* off, const void* wt,
                  const float* bias, void* out, void* workspace, cudaStream_t st) {
-  (void)flags;
   int size;
   if (!o_groups(g, &size)) {
     set_error("umma forward: O = %d cannot be split into groups", g.O);
@@ -69,7 +69,7 @@ int umma_forward(const Geo& g, int operand, int flags, const void* x, const floa
     const Geo gc = o_group_geo(g, o0, size);
     const int rc = umma_forward_any(gc, operand, x, off, (const uint8_t*)wt + (size_t)o0 * g.K * esz,
                                     bias ? bias + o0 : nullptr, (float*)out + (size_t)o0 * g.HW, workspace, st,
-                                    o0 == 0);
+                                    o0 == 0 && !(flags & DCN_FLAG_XT_STAGED));
     if (rc) return rc;
   }
   return DCN_OK;
@@ -78,7 +78,8 @@ int umma_forward(const Geo& g, int operand, int flags, const void* x, const floa
 int umma_backward(const Geo& g, int operand, int flags, const void* x, const float* off, const void* wt,
                   const void* gout, float* gx, float* goff, float* gw, float* gb, void* workspace,
                   cudaStream_t st) {
-  return umma_backward_any(g, operand, flags, x, off, wt, gout, gx, goff, gw, gb, workspace, st);
+  return umma_backward_any(g, operand, flags, x, off, wt, gout, gx, goff, gw, gb, workspace, st, nullptr, nullptr,
+                           nullptr);
 }
 
 }  // namespace dcn

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) weight_tiles_fwd_kernel(Geo g, int KB, co
   const uint32_t tile_bytes = (uint32_t)g.O * 128;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int o = i / (KB * 64), jj = i - o * (KB * 64), kb = jj >> 6, kk = jj & 63;
-    const float v = jj < g.K ? (float)wt[wt_index(g, o, jj)] : 0.f;
+    const float v = (jj < g.K && o < g.o_valid) ? (float)wt[wt_index(g, o, jj)] : 0.f;
     __nv_bfloat16 hi, lo;
     ptx::split_bf16(v, hi, lo);
     uint8_t* base = tiles + (size_t)kb * NIMG * tile_bytes + ptx::kmajor_sw128_off(o, kk);

@@ -9,7 +9,8 @@ import torch
 
 from . import _lib
 from ._lib import (FLAG_ACCUM_GRAD_X, FLAG_FORCE_SIMT, FLAG_NO_GRAD_X, FLAG_XT_STAGED, OPERAND_BF16, OPERAND_FP32,
-                   PHASE_BACKWARD, PHASE_FORWARD, VARIANT_DCNV1, VARIANT_JITTOR, VARIANT_TORCH)
+                   PHASE_BACKWARD, PHASE_FORWARD, PHASE_LAYER_BACKWARD, PHASE_LAYER_FORWARD, VARIANT_DCNV1,
+                   VARIANT_JITTOR, VARIANT_TORCH)
 
 _workspaces = {}
 _captured = []   # scratch buffers whose addresses are baked into CUDA graphs: alive until clear_workspaces()
@@ -168,6 +169,139 @@ def dcn_backward(x, offset, weight, grad_out, has_bias, kernel_size=3, stride=1,
                               ctypes.c_void_p(stream.cuda_stream))
     _lib.check(rc, "dcn_backward")
     return gx, goff, gw, gb
+
+
+# ---- whole layer: companion offset conv + DCN span on the engine -----------------------------------
+def layer_supported(x_shape, out_channels, kernel_size=3, stride=1, padding=1, variant=VARIANT_TORCH,
+                    operand=OPERAND_FP32, flags=0):
+    """True when dcn_layer_forward / dcn_layer_backward cover the shape (both phases on the tensor path)."""
+    B, C, H, W = (int(v) for v in x_shape)
+    shp = _lib.make_shape(B, C, int(out_channels), H, W, kernel_size, stride, padding, variant, operand, flags)
+    return all(_lib.path_name(shp, ph) == "umma" for ph in (PHASE_LAYER_FORWARD, PHASE_LAYER_BACKWARD))
+
+
+def layer_workspace(x, weight, kernel_size=3, stride=1, padding=1, variant=VARIANT_TORCH, flags=0):
+    """One scratch buffer big enough for dcn_layer_forward AND dcn_layer_backward of this layer: handing the same
+    buffer to both lets the backward pass reuse the staged copy of x (DCN_FLAG_XT_STAGED)."""
+    lib = _lib.load()
+    shp = _shape_of(x, weight, kernel_size, stride, padding, variant, OPERAND_FP32, flags)
+    need = max(lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_LAYER_FORWARD),
+               lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_LAYER_BACKWARD))
+    return torch.empty(need, dtype=torch.uint8, device=x.device)
+
+
+def dcn_offset_conv_forward(x, offset_weight, offset_bias, out_channels, kernel_size=3, stride=1, padding=1,
+                            variant=VARIANT_TORCH, flags=0, ws=None, xt_staged=False):
+    """offset[B,2N,Ho,Wo] = the companion offset convolution on the engine (a plain mode of the tcgen05 forward
+    kernel).  `variant` / out_channels describe the DCN layer the offsets are for: the staged copy of x is laid out
+    for it, so a following dcn_forward(..., ws=ws, xt_staged=True) reuses it."""
+    lib = _lib.load()
+    B, C, H, W = x.shape
+    if xt_staged and ws is not None:
+        flags |= FLAG_XT_STAGED
+    shp = _lib.make_shape(B, C, int(out_channels), H, W, kernel_size, stride, padding, variant, OPERAND_FP32, flags)
+    Ho, Wo = _lib.output_hw(shp)
+    N = shp.kh * shp.kw
+    x, offset_weight, offset_bias = _dev_ready(x), _dev_ready(offset_weight), _dev_ready(offset_bias)
+    if tuple(offset_weight.shape) != (2 * N, C, shp.kh, shp.kw):
+        raise ValueError(f"offset_weight shape {tuple(offset_weight.shape)} != {(2 * N, C, shp.kh, shp.kw)}")
+    offset = torch.empty((B, 2 * N, Ho, Wo), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream(x.device)
+        need = lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_LAYER_FORWARD)
+        if ws is None:
+            ws = _workspace(x.device, stream.cuda_stream, need)
+        rc = lib.dcn_offset_conv_forward(ctypes.byref(shp), _ptr(x), _ptr(offset_weight), _ptr(offset_bias), _ptr(offset),
+                                         _ptr(ws), ws.numel(), ctypes.c_void_p(stream.cuda_stream))
+    _lib.check(rc, "dcn_offset_conv_forward")
+    return offset
+
+
+def dcn_layer_forward(x, offset_weight, offset_bias, weight, bias, kernel_size=3, stride=1, padding=1,
+                      variant=VARIANT_TORCH, flags=0, ws=None):
+    """-> (offset, out): offset conv + DCN forward, x staged once (no autograd)."""
+    lib = _lib.load()
+    shp = _shape_of(x, weight, kernel_size, stride, padding, variant, OPERAND_FP32, flags)
+    Ho, Wo = _lib.output_hw(shp)
+    N = shp.kh * shp.kw
+    x, weight, bias = _dev_ready(x), _dev_ready(weight), _dev_ready(bias)
+    offset_weight, offset_bias = _dev_ready(offset_weight), _dev_ready(offset_bias)
+    offset = torch.empty((shp.B, 2 * N, Ho, Wo), dtype=torch.float32, device=x.device)
+    out = torch.empty((shp.B, shp.O, Ho, Wo), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream(x.device)
+        need = lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_LAYER_FORWARD)
+        if ws is None:
+            ws = _workspace(x.device, stream.cuda_stream, need)
+        rc = lib.dcn_layer_forward(ctypes.byref(shp), _ptr(x), _ptr(offset_weight), _ptr(offset_bias), _ptr(weight),
+                                   _ptr(bias), _ptr(offset), _ptr(out), _ptr(ws), ws.numel(),
+                                   ctypes.c_void_p(stream.cuda_stream))
+    _lib.check(rc, "dcn_layer_forward")
+    return offset, out
+
+
+def dcn_layer_backward(x, offset, offset_weight, weight, grad_out, has_offset_bias=True, has_bias=True, kernel_size=3,
+                       stride=1, padding=1, variant=VARIANT_TORCH, flags=0, need_grad_x=True, ws=None, xt_staged=False):
+    """-> grad_x (or None), grad_offset_weight, grad_offset_bias (or None), grad_weight, grad_bias (or None).
+    grad_offset stays inside the workspace; the offset conv's data gradient is accumulated on chip-side buffers."""
+    lib = _lib.load()
+    if not need_grad_x:
+        flags |= FLAG_NO_GRAD_X
+    if xt_staged and ws is not None:
+        flags |= FLAG_XT_STAGED
+    shp = _shape_of(x, weight, kernel_size, stride, padding, variant, OPERAND_FP32, flags)
+    x, weight, grad_out = _dev_ready(x), _dev_ready(weight), _dev_ready(grad_out)
+    offset, offset_weight = _dev_ready(offset), _dev_ready(offset_weight)
+    dev = x.device
+    gx = torch.empty(x.shape, dtype=torch.float32, device=dev) if need_grad_x else None
+    gwoff = torch.empty(offset_weight.shape, dtype=torch.float32, device=dev)
+    gboff = torch.empty((offset_weight.shape[0],), dtype=torch.float32, device=dev) if has_offset_bias else None
+    gw = torch.empty(weight.shape, dtype=torch.float32, device=dev)
+    gb = torch.empty((shp.O,), dtype=torch.float32, device=dev) if has_bias else None
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        need = lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_LAYER_BACKWARD)
+        if ws is None:
+            ws = _workspace(dev, stream.cuda_stream, need)
+        rc = lib.dcn_layer_backward(ctypes.byref(shp), _ptr(x), _ptr(offset), _ptr(offset_weight), _ptr(weight),
+                                    _ptr(grad_out), _ptr(gx), _ptr(gwoff), _ptr(gboff), _ptr(gw), _ptr(gb), _ptr(ws),
+                                    ws.numel(), ctypes.c_void_p(stream.cuda_stream))
+    _lib.check(rc, "dcn_layer_backward")
+    return gx, gwoff, gboff, gw, gb
+
+
+class DeformLayerFunction(torch.autograd.Function):
+    """The whole reference module forward (offset conv + sampling + GEMM, deform_conv.py:56-81 / train.py:95-140)
+    and its autograd as ONE node on the engine: x is staged once per step, grad_offset never reaches HBM as a
+    framework tensor, and the two data-gradient terms are summed before the single transposition back to NCHW."""
+
+    @staticmethod
+    def forward(ctx, x, offset_weight, offset_bias, weight, bias, cfg):
+        kernel_size, stride, padding, variant, flags, keep_staged = cfg
+        ctx.ws = layer_workspace(x, weight, kernel_size, stride, padding, variant, flags) if keep_staged else None
+        offset, out = dcn_layer_forward(x, offset_weight, offset_bias, weight, bias, kernel_size, stride, padding,
+                                        variant, flags, ws=ctx.ws)
+        ctx.save_for_backward(x, offset, offset_weight, weight)
+        ctx.cfg = cfg
+        ctx.has = (offset_bias is not None, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, offset, offset_weight, weight = ctx.saved_tensors
+        kernel_size, stride, padding, variant, flags, _ = ctx.cfg
+        gx, gwoff, gboff, gw, gb = dcn_layer_backward(
+            x, offset, offset_weight, weight, grad_out, ctx.has[0], ctx.has[1], kernel_size, stride, padding, variant,
+            flags & ~FLAG_ACCUM_GRAD_X, need_grad_x=ctx.needs_input_grad[0], ws=ctx.ws, xt_staged=ctx.ws is not None)
+        ctx.ws = None
+        return gx, gwoff, gboff, gw, gb, None
+
+
+def deform_layer(x, offset_weight, offset_bias, weight, bias=None, kernel_size=3, stride=1, padding=1,
+                 variant=VARIANT_TORCH, flags=0, keep_staged=False):
+    """Differentiable whole layer on the engine (CUDA float32 tensors; check layer_supported() first)."""
+    cfg = (_lib._pair(kernel_size), _lib._pair(stride), _lib._pair(padding), variant, flags, bool(keep_staged))
+    return DeformLayerFunction.apply(x, offset_weight, offset_bias, weight, bias, cfg)
 
 
 def dcn_corners(offset, in_hw, kernel_size=3, stride=1, padding=1, variant=VARIANT_TORCH):

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import batch_norm_relu, deform_conv2d
+from .functional import batch_norm_relu, deform_conv2d, deform_layer, layer_supported
 
 
 class TorchDeformConv2d(nn.Module):
@@ -32,6 +32,10 @@ class TorchDeformConv2d(nn.Module):
         # that the backward pass reuses the staged channels-last copy of x (no second transpose);
         # costs device memory between the two passes, saves one full pass over x
         self.keep_staged_input = False
+        # True (default): when the shape allows it, the companion offset convolution runs on the engine as well
+        # (a plain mode of the tcgen05 kernels) and the whole layer is ONE autograd node; otherwise —
+        # or for CPU inputs, bf16 operands, unsupported channel counts — offset_conv stays a framework convolution
+        self.engine_offset_conv = True
 
         # companion offset conv: C -> 2N, same k/s/p (train.py:80-85)
         self.offset_conv = nn.Conv2d(in_channels, 2 * self.N, kernel_size=self.kernel_size,
@@ -45,7 +49,17 @@ class TorchDeformConv2d(nn.Module):
         nn.init.zeros_(self.offset_conv.weight)
         nn.init.zeros_(self.offset_conv.bias)
 
+    def _whole_layer_on_engine(self, x):
+        return (self.engine_offset_conv and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+                and self.operand == _lib.OPERAND_FP32 and self.weight.is_cuda
+                and layer_supported(x.shape, self.out_channels, self.kernel_size, self.stride, self.padding,
+                                    self.variant, self.operand, self.engine_flags))
+
     def forward(self, x):
+        if self._whole_layer_on_engine(x):
+            return deform_layer(x, self.offset_conv.weight, self.offset_conv.bias, self.weight, self.bias,
+                                self.kernel_size, self.stride, self.padding, self.variant, self.engine_flags,
+                                keep_staged=self.keep_staged_input and torch.is_grad_enabled())
         offset = self.offset_conv(x)
         return deform_conv2d(x, offset, self.weight, self.bias, self.kernel_size, self.stride,
                              self.padding, self.variant, self.operand, self.engine_flags,

@@ -184,6 +184,38 @@ def make_module_golden():
           gx=x.grad.numpy(), **arrays)
 
 
+# Whole-module fixtures whose shapes run the WHOLE layer on the engine (offset conv as a plain mode of the tcgen05
+# kernels + DCN span, dcn_layer_forward / dcn_layer_backward): outputs of the unmodified reference module.
+MODULE_UMMA = {
+    #  name               C    O   H   W   s
+    "module_umma_s1":    (64,  64, 16, 16, 1),
+    "module_umma_s2":    (32,  64, 32, 32, 2),    # detector conv3 channel counts, stride 2
+    "module_umma_c128":  (128, 32, 12, 12, 1),    # Torch layout: 16 channels per sampling point, Cs = 8
+    "module_umma_c16":   (16,  32, 32, 32, 2),    # detector conv2 channel counts
+}
+
+
+def make_module_umma_goldens():
+    cls = ref_loader.load_reference_classes(("TorchDeformConv2d",))["TorchDeformConv2d"]
+    for i, (name, (C, O, H, W, s_)) in enumerate(MODULE_UMMA.items()):
+        torch.manual_seed(777 + i)
+        m = cls(C, O, 3, s_, 1)
+        with torch.no_grad():
+            m.offset_conv.weight.normal_(0, 0.02)
+            m.offset_conv.bias.normal_(0, 1.0)
+            m.bias.normal_(0, 0.1)
+        x = torch.randn(2, C, H, W, requires_grad=True)
+        out = m(x)
+        gout = torch.randn_like(out)
+        out.backward(gout)
+        with torch.no_grad():
+            offset = m.offset_conv(x)
+        arrays = {"sd." + k: v.detach().numpy() for k, v in m.state_dict().items()}
+        arrays.update({"grad." + k: p.grad.numpy() for k, p in m.named_parameters()})
+        _save(name, cfg=np.array([C, O, H, W, s_], np.int32), x=x.detach().numpy(), out=out.detach().numpy(),
+              gout=gout.numpy(), gx=x.grad.numpy(), offset=offset.numpy(), **arrays)
+
+
 def make_detector_golden():
     """One forward of the reference's toy detector (train.py:142-175) in eval mode."""
     torch.manual_seed(4321)
@@ -295,7 +327,11 @@ def main():
     assert ref_loader.available(), "needs /root/reference (build container only)"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if "--only-module-umma" in sys.argv:
+        make_module_umma_goldens()
+        return 0
     make_layers(np.random.default_rng(20261019), UMMA_LAYERS)   # own generator: added in round 2
+    make_module_umma_goldens()
     if "--only-umma" in sys.argv:
         return 0
     rng = np.random.default_rng(20261018)
@@ -315,6 +351,8 @@ def main():
                  "the unmodified reference\n"
                  "umma_*: layer fixtures whose shapes run on the tcgen05 path (dcn_path_name == umma, forward and "
                  "backward, all coordinate modes): " + ", ".join(UMMA_LAYERS) + "\n"
+                 "module_umma_*: whole-module fixtures (live offset conv) whose shapes run offset conv + DCN span on "
+                 "the engine (dcn_layer_forward / dcn_layer_backward)\n"
                  "layer_*: layer_d_det0 runs on the tcgen05 path, the other eight on the generic kernels\n"
                  "jittor_*: torch transliteration of deform_conv.py:30-81 "
                  "(oracle/torch_chain.py) - parity unpinned\n"
