@@ -72,6 +72,10 @@ def parse_args():
                          "x / weight / grad_out with fp32 accumulation (BASELINE configs[3])")
     ap.add_argument("--offset-sigma", type=float, default=2.0,
                     help="std (pixels) of the synthetic live offsets (SURVEY 8d)")
+    ap.add_argument("--scope", default="span", choices=["span", "layer"],
+                    help="single-layer workloads: 'span' = dcn_forward + dcn_backward with offsets supplied "
+                         "(deform_conv.py:62-81 / train.py:102-140); 'layer' = the whole module on the engine, companion "
+                         "offset conv included (dcn_layer_forward + dcn_layer_backward, SURVEY 8f.1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--force-simt", action="store_true")
@@ -563,9 +567,10 @@ def main():
     wt = (torch.randn(O, C, k, k, device=dev, generator=gen) * (2.0 / (C * N)) ** 0.5).to(act)
     bias = torch.randn(O, device=dev, generator=gen) * 0.1
     gout = torch.randn(B, O, Ho, Wo, device=dev, generator=gen).to(act)
-    # flat gradient bucket: [grad_weight | grad_bias | offset_conv.weight.grad | offset_conv.bias.grad]
+    # flat gradient bucket: [grad_weight | grad_bias], plus [offset_conv.weight.grad | offset_conv.bias.grad] when the
+    # whole layer is timed (--scope layer); every slot is written by the step before the all-reduce
     n_w, n_b, n_ow, n_ob = O * C * N, O, 2 * N * C * N, 2 * N
-    bucket = torch.zeros(n_w + n_b + n_ow + n_ob, device=dev)
+    bucket = torch.zeros(n_w + n_b + (n_ow + n_ob if args.scope == "layer" else 0), device=dev)
 
     comm = None
     allreduce_kind = "none"
@@ -582,13 +587,31 @@ def main():
     from jittor_dcn_b200.functional import staged_workspace
     ws = staged_workspace(x, wt, k, s, p, variant, operand, flags)
 
+    layer_scope = args.scope == "layer"
+    if layer_scope:
+        from jittor_dcn_b200.functional import dcn_layer_backward, dcn_layer_forward, layer_supported, layer_workspace
+        if operand != dcn.OPERAND_FP32 or not layer_supported(x.shape, O, k, s, p, variant, operand, flags):
+            raise SystemExit("--scope layer: the whole-layer entry points do not cover this shape / operand mode")
+        w_off = torch.randn(2 * N, C, k, k, device=dev, generator=gen) * 0.01
+        b_off = torch.randn(2 * N, device=dev, generator=gen) * args.offset_sigma
+        ws = layer_workspace(x, wt, k, s, p, variant, flags)
+
     def step():
-        out = dcn.dcn_forward(x, off, wt, bias, k, s, p, variant, operand=operand, flags=flags, ws=ws)
-        gx, goff, gw, gb = dcn.dcn_backward(x, off, wt, gout, True, k, s, p, variant, operand=operand, flags=flags,
-                                            ws=ws, xt_staged=ws is not None)
+        if layer_scope:
+            off_l, out = dcn_layer_forward(x, w_off, b_off, wt, bias, k, s, p, variant, flags, ws=ws)
+            gx, gwo, gbo, gw, gb = dcn_layer_backward(x, off_l, w_off, wt, gout, True, True, k, s, p, variant, flags,
+                                                      ws=ws, xt_staged=True)
+            goff = None
+        else:
+            out = dcn.dcn_forward(x, off, wt, bias, k, s, p, variant, operand=operand, flags=flags, ws=ws)
+            gx, goff, gw, gb = dcn.dcn_backward(x, off, wt, gout, True, k, s, p, variant, operand=operand, flags=flags,
+                                                ws=ws, xt_staged=ws is not None)
         if comm is not None:
             bucket[:n_w].copy_(gw.view(-1))
             bucket[n_w:n_w + n_b].copy_(gb)
+            if layer_scope:
+                bucket[n_w + n_b:n_w + n_b + n_ow].copy_(gwo.view(-1))
+                bucket[n_w + n_b + n_ow:].copy_(gbo)
             comm.allreduce_mean_(bucket)
         return out, gx, goff
 
@@ -784,6 +807,10 @@ def main():
             "dtype": "bf16" if operand == dcn.OPERAND_BF16 else "f32",
             "data": "synthetic",
             "config": {"workload": args.workload + ": " + desc, "variant": args.variant, "operand": args.operand,
+                       "scope": ("whole layer on the engine: companion offset conv + DCN span, forward and backward "
+                                 "(dcn_layer_forward / dcn_layer_backward)" if layer_scope else
+                                 "DCN span with offsets supplied (dcn_forward + dcn_backward); the offset conv is not in "
+                                 "the timed region"),
                        "batch_per_gpu": B, "global_batch": world * B, "offset_sigma_px": args.offset_sigma,
                        "path_fwd": lib.dcn_path_name(ctypes.byref(shp), 0).decode(),
                        "path_bwd": lib.dcn_path_name(ctypes.byref(shp), 1).decode(),

@@ -703,6 +703,74 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
                   fmaf(__uint_as_float(a2), w.z, fmaf(__uint_as_float(a1), w.y, __uint_as_float(a0) * w.x)));
     };
     Pos cur{tile0, kb0, 0, 0, 0u, 0u, kb_of(kb0)};
+    if constexpr (PLAIN) {
+      // One exact pixel per item = ONE 16-byte load: with the one-item-deep pipeline below a thread had a single load
+      // in flight and the kernel ran at the L2 latency (2.45 ms for the cfg2 offset conv, 4x the L1 time of its
+      // gathers).  Here every thread issues ALL kIt loads of the NEXT K block before it converts the current one:
+      // kIt .. 2*kIt loads in flight per thread, two register sets used alternately (static indexing).
+      uint4 va[kIt], vb[kIt];
+      auto issue_all = [&](const Pos& q, uint4 (&dst)[kIt]) {
+        const PlanEntry* pl = plan + q.pbuf * P.plan_cap;
+        int jc, tl;
+        bool ok;
+        jit_cols(q.kbm, jc, tl, ok);
+        pl += tl * 128;
+#pragma unroll
+        for (int it = 0; it < kIt; ++it)
+          dst[it] = __ldg(reinterpret_cast<const uint4*>(img[it] + jc + pl[ent_idx[it]].off[0]));
+      };
+      auto convert = [&](const Pos& q, const uint4 (&src)[kIt]) {
+        const PlanEntry* pl = plan + q.pbuf * P.plan_cap;
+        int jc, tl;
+        bool col_ok;
+        jit_cols(q.kbm, jc, tl, col_ok);
+        pl += tl * 128;
+        uint8_t* a_hi = stage_base + (size_t)q.s * P.stage_bytes;
+        uint8_t* a_lo = a_hi + kATile;
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+          const float w = col_ok ? pl[ent_idx[it]].w[0] : 0.f;  // 1, or 0 for padding columns / positions off the frame
+          float4 r;
+          r.x = __uint_as_float(src[it].x) * w;
+          r.y = __uint_as_float(src[it].y) * w;
+          r.z = __uint_as_float(src[it].z) * w;
+          r.w = __uint_as_float(src[it].w) * w;
+          uint2 hi, lo;
+          split4(r, hi, lo);
+          *reinterpret_cast<uint2*>(a_hi + st_off[it]) = hi;
+          *reinterpret_cast<uint2*>(a_lo + st_off[it]) = lo;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&full[q.s]);
+          mbar_arrive(&pempty[q.pbuf]);
+        }
+      };
+      auto start = [&](const Pos& q, const Pos& prev, uint4 (&dst)[kIt]) {
+        if (q.tile != prev.tile) set_images(q.tile);
+        mbar_wait(&pfull[q.pbuf], q.pphase);
+        mbar_wait(&empty[q.s], q.phase ^ 1);
+        issue_all(q, dst);
+      };
+      if (cur.tile < t.num_tiles) {
+        set_images(cur.tile);
+        start(cur, cur, va);
+      }
+      while (cur.tile < t.num_tiles) {
+        Pos nxt = cur;
+        advance(nxt);
+        const bool nv = nxt.tile < t.num_tiles;
+        if (nv) start(nxt, cur, vb);
+        convert(cur, va);
+        if (!nv) break;
+        Pos nn = nxt;
+        advance(nn);
+        if (nn.tile < t.num_tiles) start(nn, nxt, va);
+        convert(nxt, vb);
+        cur = nn;
+      }
+    } else {
     if (cur.tile < t.num_tiles) {
       set_images(cur.tile);
       mbar_wait(&pfull[cur.pbuf], cur.pphase);
@@ -773,6 +841,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         mbar_arrive(&pempty[cur.pbuf]);
       }
       cur = nxt;
+    }
     }
   }
 

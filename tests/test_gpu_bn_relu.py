@@ -146,7 +146,7 @@ def test_batch_variance_with_mean_far_above_std():
     m = xd.mean(dim=(0, 2, 3))
     v = xd.var(dim=(0, 2, 3), unbiased=False)
     ref = torch.relu((xd - m.view(1, C, 1, 1)) / torch.sqrt(v.view(1, C, 1, 1) + ours.eps))
-    assert rel_err(y.cpu().numpy(), ref.numpy()) < 1e-3
+    assert rel_err(y.detach().cpu().numpy(), ref.numpy()) < 1e-3
     # running_var = 0.9 * 1 + 0.1 * unbiased batch variance
     n = B * H * W
     exp_rv = 0.9 + 0.1 * v * n / (n - 1)
