@@ -58,6 +58,25 @@ DETECTOR_DESC = ("detector: data-parallel DCN detector training step (train.py:1
                  "gradient all-reduce (BASELINE configs[4])")
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else that libraries write to file descriptor 1 (NCCL prints its
+    version banner there) is sent to stderr; the JSON line goes to the original descriptor."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -81,6 +100,11 @@ def parse_args():
     ap.add_argument("--force-simt", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
                     help="detector workload: launch the training step eagerly instead of replaying its CUDA graph")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="detector workload: exchange the gradient bucket with dcn_allreduce_sum_f32 (NCCL, eager "
+                         "launches) instead of the one-kernel peer-memory all-reduce inside the step's CUDA graph")
+    ap.add_argument("--no-detector-dp", action="store_true",
+                    help="default workload: skip the extra detector_dp measurement (BASELINE configs[4])")
     ap.add_argument("--stock-bn", action="store_true",
                     help="detector workload: the framework's BatchNorm2d + ReLU instead of the engine's fused post-op")
     return ap.parse_args()
@@ -236,29 +260,23 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
-def run_detector(args):
-    """BASELINE configs[4]: the reference's toy detector (4 DCN layers on the engine, the rest stock
-    torch CUDA ops) trained data-parallel: global batch sharded over the ranks (strong scaling),
-    Adam lr 1e-3 wd 1e-4, loss CE + 5*smoothL1 (train.py:187-199,247), ONE all-reduce of the flat
-    435,862-float gradient bucket through the C ABI."""
+def measure_detector(args, world, rank, local_rank, dev, steps, warmup, want_e2e=True, sample_clocks=True):
+    """BASELINE configs[4]: the reference's toy detector (4 DCN layers on the engine — offset conv included —, relu(bn(x))
+    on the engine, the rest stock torch CUDA ops) trained data-parallel: global batch sharded over the ranks (STRONG
+    scaling), Adam lr 1e-3 wd 1e-4, loss CE + 5*smoothL1 (train.py:187-199,247), ONE all-reduce of the flat
+    435,862-float gradient bucket.  The exchange is the engine's one-kernel peer-memory all-reduce (dcn_p2p_*), which a
+    CUDA graph can record, so the WHOLE step — forward, backward, exchange, Adam — is replayed as one graph at every
+    N.  The process group must already exist for world > 1.  Returns a dict (rank 0: complete; others: timing only)."""
     import torch
     import torch.distributed as dist
     import jittor_dcn_b200 as dcn
     from jittor_dcn_b200 import _lib, dp
     from jittor_dcn_b200.detector import EDNetDetection, detection_loss, synthetic_canvases
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
     lib = dcn.load()
     b0, b1 = dp.shard_range(args.global_batch, rank, world)
     B = b1 - b0
@@ -270,21 +288,29 @@ def run_detector(args):
             if isinstance(m, dcn.TorchDeformConv2d):
                 m.offset_conv.weight.normal_(0, 0.01)
                 m.offset_conv.bias.normal_(0, 1.0)
-    # (single process only: capturing the NCCL all-reduce of the data-parallel step hung on the 2-GPU box, so the
-    # multi-GPU step stays eagerly launched)
-    use_graph = not args.no_graph and world == 1
+    use_graph = not args.no_graph
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, capturable=use_graph)
     x, labels, boxes = synthetic_canvases(B, torch.Generator().manual_seed(100 + rank), dev)
     x_host = x.cpu().pin_memory()
     bucket = dp.GradBucket(model.parameters())
-    comm = dp.DcnComm(rank, world, dev) if world > 1 else None
+    comm, comm_kind = None, "none"
+    if world > 1:
+        if args.nccl_allreduce:
+            comm = dp.DcnComm(rank, world, dev)
+            comm_kind = "dcn_allreduce_sum_f32 (NCCL, one flat bucket of %d floats)" % bucket.numel
+            use_graph = False          # a captured NCCL collective hung on the 2-GPU box (round 1): eager launches
+        else:
+            comm = dp.DcnP2P(rank, world, dev, bucket.numel)
+            comm_kind = ("dcn_p2p_allreduce_sum_f32 (ONE kernel over NVLink peer memory, one flat bucket of %d "
+                         "floats; recorded in the step's CUDA graph)" % bucket.numel)
+    weight = dp.shard_weight(args.global_batch, rank, world) if world > 1 else None
     stream = torch.cuda.current_stream(dev)
 
     def train_step():
         loss = detection_loss(*model(x), labels, boxes)
         loss.backward()
         if comm is not None:
-            dp.allreduce_gradients(bucket, comm)
+            dp.allreduce_gradients(bucket, comm, weight=weight)
         opt.step()
         return loss
 
@@ -311,9 +337,10 @@ def run_detector(args):
     launches_per_step = int(lib.dcn_launch_count())
     prof = _lib.profile_end()
 
-    # The step is launch-bound at small per-GPU batches (batch 16: ~150 launches for ~1 ms of kernels), so the
-    # whole training step — forward, backward, the gradient all-reduce, Adam — is captured once into a CUDA graph
-    # and replayed; inputs live in static buffers.
+    # The step is launch-bound at small per-GPU batches (batch 16: ~150 launches for ~1 ms of kernels; 8 GPUs at
+    # global batch 1024: 6.2 ms eager for 2.6 ms of kernels), so the whole training step is captured once and replayed;
+    # inputs live in static buffers.  thread_local capture mode: torch's NCCL watchdog thread (the process group only
+    # serves barriers / rendez-vous here) must not invalidate the capture.
     graph, graph_note, static_loss = None, "eager launches", None
     if use_graph:
         try:
@@ -326,9 +353,10 @@ def run_detector(args):
             barrier()
             opt.zero_grad(set_to_none=True)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 static_loss = train_step()
-            graph_note = "whole training step replayed as one CUDA graph"
+            graph_note = "whole training step%s replayed as one CUDA graph" % (
+                " (gradient all-reduce included)" if comm is not None else "")
         except Exception as e:  # noqa: BLE001 - report and fall back to eager launches
             graph, graph_note = None, f"eager launches (graph capture failed: {type(e).__name__}: {e})"[:300]
             barrier()
@@ -342,59 +370,86 @@ def run_detector(args):
         graph.replay()
         return static_loss
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record(stream)
     barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    launches = launches_per_step * args.steps
+    ms = e0.elapsed_time(e1) / steps
     clocks = sampler.stop() if sampler else None
-    # e2e: canvases come from pinned host memory every step, the loss is read back
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        float(step(from_host=True))
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
+    e2e_s = None
+    if want_e2e:
+        # e2e: canvases come from pinned host memory every step, the loss is read back
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            float(step(from_host=True).detach())
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / steps
     if world > 1:
-        t = torch.tensor([ms, e2e_s], device=dev)
+        t = torch.tensor([ms, e2e_s or 0.0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
+        ms, e2e_s = float(t[0]), (float(t[1]) if want_e2e else None)
+    res = {
+        "ms_per_step": ms, "images_per_s": args.global_batch / (ms * 1e-3), "batch_per_gpu": B,
+        "launches_per_step": launches_per_step, "graph": graph is not None, "launch": graph_note,
+        "allreduce": comm_kind, "bucket_floats": bucket.numel, "e2e_s": e2e_s, "clocks": clocks,
+        "h2d_bytes_per_step": x_host.numel() * 4,
+        "kernels": {k: {"launches": v[0], "avg_ms": v[1] / max(v[0], 1)} for k, v in prof.items()},
+        "engine_ms_per_step": sum(v[1] for v in prof.values()),   # of the profiled eager step
+    }
+    del graph
+    if comm is not None:
+        barrier()
+        comm.close()
+    return res
+
+
+def run_detector(args):
+    """--workload detector: BASELINE configs[4] as its own bench line (see measure_detector)."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    r = measure_detector(args, world, rank, local_rank, dev, args.steps, args.warmup)
     if rank == 0:
-        ours = sum(v[1] for v in prof.values())   # the profiled eager step
         line = {
-            "metric": "DeformConv2d fwd+bwd images/sec", "value": args.global_batch / (ms * 1e-3), "unit": "images/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "metric": "DeformConv2d fwd+bwd images/sec", "value": r["images_per_s"], "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": DETECTOR_DESC, "variant": args.variant, "global_batch": args.global_batch,
-                       "batch_per_gpu": B, "parallelism": f"dp{world}",
-                       "launch": graph_note,
+                       "batch_per_gpu": r["batch_per_gpu"], "parallelism": f"dp{world}",
+                       "launch": r["launch"],
                        "post_op": ("framework BatchNorm2d + ReLU (cuDNN)" if args.stock_bn else
                                    "relu(bn(x)) on the engine (dcn_bn_relu_forward / _backward)"),
-                       "allreduce": "dcn_allreduce_sum_f32 (NCCL, one flat bucket of %d floats)" % bucket.numel
-                       if world > 1 else "none",
+                       "allreduce": r["allreduce"],
                        "l2": "per-step activations (%.0f MB for conv2's input alone) exceed the 126 MB L2" %
-                             (B * 16 * 128 * 128 * 4 / 1e6)},
-            "kernels": {k: {"launches": v[0], "avg_ms": v[1] / max(v[0], 1)} for k, v in prof.items()},
-            "dcn_engine_ms_per_step": ours, "roofline": None, "cpu_baseline": None,
-            "e2e": {"value": args.global_batch / e2e_s, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3,
+                             (r["batch_per_gpu"] * 16 * 128 * 128 * 4 / 1e6)},
+            "kernels": r["kernels"],
+            "dcn_engine_ms_per_step": r["engine_ms_per_step"], "roofline": None, "cpu_baseline": None,
+            "e2e": {"value": args.global_batch / r["e2e_s"], "unit": "images/s",
+                    "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": 4, "ms_per_step": r["e2e_s"] * 1e3,
                     "api": "EDNetDetection (4 x jittor_dcn_b200.TorchDeformConv2d) train step"},
-            "gpu_launches": launches, "clocks": clocks,
+            "gpu_launches": r["launches_per_step"] * args.steps, "clocks": r["clocks"],
         }
-        print(json.dumps(line), flush=True)
-    if comm is not None:
-        comm.close()
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -503,7 +558,7 @@ def run_stack(args):
                     "algorithmic_bytes": work[role]["bytes"], "algorithmic_flops": work[role]["flops"],
                     "note": "sum over the 13 layers' launches of this kernel in one step"}
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": "DeformConv2d fwd+bwd images/sec", "value": world * B / (ms_per_step * 1e-3),
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -514,7 +569,7 @@ def run_stack(args):
                        "l2": "layers interleaved; every layer's inputs are evicted by the others' traffic "
                              "(1.4 GB of operands per step)", "allreduce": "none", "parallelism": f"dp{world}"},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": None, "e2e": None,
-            "gpu_launches": launches, "clocks": clocks}), flush=True)
+            "gpu_launches": launches, "clocks": clocks})
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -522,6 +577,7 @@ def run_stack(args):
 
 def main():
     args = parse_args()
+    claim_stdout()
     if args.workload == "stack":
         if args.impl == "reference":
             raise SystemExit("--impl reference supports the single-layer workloads")
@@ -799,6 +855,28 @@ def main():
                "sample": f"median of {runs} fwd+bwd passes over a {micro_b}-sample micro-batch of the same layer "
                          f"(reference op chain restated with torch CPU ops, offsets supplied)"}
 
+    # ---- BASELINE configs[4] next to the headline, at this N: the data-parallel detector training step, global
+    # batch 1024 sharded over the ranks (STRONG scaling; the headline above is weak scaling of one layer)
+    detector_dp = None
+    l2_note = ("L2 flushed (512 MB write) between timed iterations" if needs_flush else
+               "inputs (x %.0f MB + gout %.0f MB) exceed the 126 MB L2; no flush needed"
+               % (x.numel() * x.element_size() / 1e6, gout.numel() * gout.element_size() / 1e6))
+    staging_note = ("backward reuses the forward pass's staged copy of x (DCN_FLAG_XT_STAGED, one scratch buffer for "
+                    "both phases)" if ws is not None else "re-staged per phase")
+    if args.workload == "cfg2" and not args.no_detector_dp:
+        del x, off, gout, ws, flush_buf
+        torch.cuda.empty_cache()
+        try:
+            r = measure_detector(args, world, rank, local_rank, dev, steps=10, warmup=3, want_e2e=False,
+                                 sample_clocks=False)
+            detector_dp = {"global_batch": args.global_batch, "batch_per_gpu": r["batch_per_gpu"],
+                           "ms_per_step": r["ms_per_step"], "images_per_s": r["images_per_s"], "scaling": "strong",
+                           "launches": r["launches_per_step"], "graph": r["graph"], "launch": r["launch"],
+                           "allreduce": r["allreduce"], "dcn_engine_ms_per_step": r["engine_ms_per_step"],
+                           "steps": 10, "warmup": 3}
+        except Exception as e:  # noqa: BLE001 - the headline line must still be printed
+            detector_dp = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if rank == 0:
         line = {
             "metric": "DeformConv2d fwd+bwd images/sec", "value": value, "unit": "images/s", "n_gpus": world,
@@ -814,16 +892,12 @@ def main():
                        "batch_per_gpu": B, "global_batch": world * B, "offset_sigma_px": args.offset_sigma,
                        "path_fwd": lib.dcn_path_name(ctypes.byref(shp), 0).decode(),
                        "path_bwd": lib.dcn_path_name(ctypes.byref(shp), 1).decode(),
-                       "l2": ("L2 flushed (512 MB write) between timed iterations" if needs_flush else
-                              "inputs (x %.0f MB + gout %.0f MB) exceed the 126 MB L2; no flush needed"
-                              % (x.numel() * x.element_size() / 1e6, gout.numel() * gout.element_size() / 1e6)),
-                       "staging": ("backward reuses the forward pass's staged copy of x (DCN_FLAG_XT_STAGED, one "
-                                   "scratch buffer for both phases)" if ws is not None else "re-staged per phase"),
+                       "l2": l2_note, "staging": staging_note,
                        "allreduce": allreduce_kind, "parallelism": f"dp{world}"},
             "roofline": roofline, "kernels": kernels, "fwd_only": fwd_only, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": launches, "clocks": clocks,
+            "detector_dp": detector_dp, "gpu_launches": launches, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if comm is not None:
         comm.close()
     if world > 1:

@@ -86,7 +86,13 @@ enum {
   DCN_FLAG_FORCE_SIMT = 1 << 1,    /* use the generic CUDA-core kernels even when the
                                       tcgen05 path supports the shape (A/B testing) */
   DCN_FLAG_NO_GRAD_X = 1 << 2,     /* dcn_backward: skip grad_x (first layer of a net) */
-  DCN_FLAG_RELU_OUT = 1 << 3,      /* reserved for the fused epilogue */
+  DCN_FLAG_RELU_OUT = 1 << 3,      /* fused post-op epilogue (train.py:167-170): dcn_forward / dcn_layer_forward
+                                      store max(acc + bias, 0).  With eval-mode BatchNorm folded into weight / bias
+                                      by the caller (scale_o = gamma_o / sqrt(var_o + eps); weight_o *= scale_o,
+                                      bias_o = (bias_o - mean_o) * scale_o + beta_o) this is relu(bn(conv(x))) in the
+                                      producing kernel.  The backward entry points take grad_out with respect to
+                                      the PRE-activation sum: the caller masks it with out > 0 (the Python autograd
+                                      nodes do); the flag itself is ignored there */
   DCN_FLAG_XT_STAGED = 1 << 4      /* the workspace is the very buffer a preceding call of this library for the
                                       same shape / operand was given (dcn_offset_conv_forward, dcn_forward or
                                       dcn_layer_forward; sized for the largest phase used) and nothing has written

@@ -16,6 +16,7 @@ OPERAND_BF16 = 1
 FLAG_ACCUM_GRAD_X = 1 << 0
 FLAG_FORCE_SIMT = 1 << 1
 FLAG_NO_GRAD_X = 1 << 2
+FLAG_RELU_OUT = 1 << 3     # forward epilogue stores max(acc + bias, 0)
 FLAG_XT_STAGED = 1 << 4
 PHASE_FORWARD, PHASE_BACKWARD, PHASE_CORNERS = 0, 1, 2
 PHASE_LAYER_FORWARD, PHASE_LAYER_BACKWARD = 3, 4   # offset conv + DCN span (dcn_layer_*)

@@ -39,6 +39,9 @@ struct Geo {
   // channel permutation of the staged copy the plain problem shares with its Torch-layout DCN layer (0 = none):
   // staged channel c' holds image channel (c' % perm_G) * perm_Cs + c' / perm_G  (dcn_umma_prep.cu)
   int perm_G, perm_Cs;
+  // DCN_FLAG_RELU_OUT: the forward epilogues store max(acc + bias, 0) (with eval-mode BatchNorm folded
+  // into weight / bias by the caller this is the whole relu(bn(conv(x))) post-op of train.py:167-170 in the epilogue)
+  int relu_out;
 };
 
 __host__ __device__ __forceinline__ int off_row_ch(const Geo& g, int n) { return n * g.row_mul + g.row_add; }
@@ -77,6 +80,7 @@ __host__ inline int make_geo(const DcnShape* s, Geo* g) {
   g->plain = 0;
   g->o_valid = s->O;
   g->perm_G = g->perm_Cs = 0;
+  g->relu_out = (s->flags & DCN_FLAG_RELU_OUT) ? 1 : 0;
   g->N = s->kh * s->kw;
   g->Ho = (s->H + 2 * s->ph - s->kh) / s->sh + 1;
   g->Wo = (s->W + 2 * s->pw - s->kw) / s->sw + 1;

@@ -176,13 +176,18 @@ __global__ void __launch_bounds__(256) fwd_kernel(Geo g, const float* __restrict
     const float bv = bias ? __ldg(bias + o) : 0.f;
     float* orow = out + ((size_t)b * g.O + o) * g.HW;
     const int r = r0 + tx * 4;
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = acc[i][j] + bv;
+      if (g.relu_out) v[i] = fmaxf(v[i], 0.f);   // DCN_FLAG_RELU_OUT
+    }
     if (r + 3 < g.HW && (g.HW & 3) == 0) {
-      *reinterpret_cast<float4*>(orow + r) =
-          make_float4(acc[0][j] + bv, acc[1][j] + bv, acc[2][j] + bv, acc[3][j] + bv);
+      *reinterpret_cast<float4*>(orow + r) = make_float4(v[0], v[1], v[2], v[3]);
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        if (r + i < g.HW) orow[r + i] = acc[i][j] + bv;
+        if (r + i < g.HW) orow[r + i] = v[i];
     }
   }
 }

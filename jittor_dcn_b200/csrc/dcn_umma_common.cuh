@@ -158,6 +158,7 @@ __host__ inline Geo plain_geo(const Geo& g, const Tiling& layer_tiling, bool pad
   Geo p = g;
   p.variant = DCN_VARIANT_DCNV1;
   p.plain = 1;
+  p.relu_out = 0;
   p.o_valid = 2 * g.N;
   p.Oimg = 2 * g.N;
   p.O = pad_o ? (2 * g.N + 15) / 16 * 16 : 2 * g.N;

@@ -333,7 +333,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float bv = P.bias ? __ldg(P.bias + c0 + i) : 0.f;
-            dst[(size_t)(c0 + i) * o_stride] = v[i] + bv;
+            const float r = v[i] + bv;
+            dst[(size_t)(c0 + i) * o_stride] = g.relu_out ? fmaxf(r, 0.f) : r;
           }
         }
         tc_fence_before();
@@ -362,7 +363,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
             for (int i = 0; i < 16; ++i) {
               if (PLAIN && c0 + i >= g.o_valid) break;   // padded accumulator columns of a plain problem
               const float bv = P.bias ? __ldg(P.bias + c0 + i) : 0.f;
-              P.out[out_off + (size_t)(c0 + i) * g.HW] = v[i] + bv;
+              const float r = v[i] + bv;
+              P.out[out_off + (size_t)(c0 + i) * g.HW] = g.relu_out ? fmaxf(r, 0.f) : r;
             }
           }
         }

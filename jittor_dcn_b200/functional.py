@@ -8,7 +8,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (FLAG_ACCUM_GRAD_X, FLAG_FORCE_SIMT, FLAG_NO_GRAD_X, FLAG_XT_STAGED, OPERAND_BF16, OPERAND_FP32,
+from ._lib import (FLAG_ACCUM_GRAD_X, FLAG_FORCE_SIMT, FLAG_NO_GRAD_X, FLAG_RELU_OUT, FLAG_XT_STAGED, OPERAND_BF16, OPERAND_FP32,
                    PHASE_BACKWARD, PHASE_FORWARD, PHASE_LAYER_BACKWARD, PHASE_LAYER_FORWARD, VARIANT_DCNV1,
                    VARIANT_JITTOR, VARIANT_TORCH)
 
@@ -281,14 +281,19 @@ class DeformLayerFunction(torch.autograd.Function):
         ctx.ws = layer_workspace(x, weight, kernel_size, stride, padding, variant, flags) if keep_staged else None
         offset, out = dcn_layer_forward(x, offset_weight, offset_bias, weight, bias, kernel_size, stride, padding,
                                         variant, flags, ws=ctx.ws)
-        ctx.save_for_backward(x, offset, offset_weight, weight)
+        # DCN_FLAG_RELU_OUT: the epilogue applied the ReLU; the backward entry points want the gradient of the
+        # pre-activation sum, i.e. grad_out masked with out > 0
+        ctx.relu = bool(flags & FLAG_RELU_OUT)
+        ctx.save_for_backward(x, offset, offset_weight, weight, *((out,) if ctx.relu else ()))
         ctx.cfg = cfg
         ctx.has = (offset_bias is not None, bias is not None)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        x, offset, offset_weight, weight = ctx.saved_tensors
+        x, offset, offset_weight, weight = ctx.saved_tensors[:4]
+        if ctx.relu:
+            grad_out = grad_out * (ctx.saved_tensors[4] > 0)
         kernel_size, stride, padding, variant, flags, _ = ctx.cfg
         gx, gwoff, gboff, gw, gb = dcn_layer_backward(
             x, offset, offset_weight, weight, grad_out, ctx.has[0], ctx.has[1], kernel_size, stride, padding, variant,
@@ -342,18 +347,22 @@ class DeformConvFunction(torch.autograd.Function):
             # private scratch that lives until backward: its head keeps the staged copy of x
             ctx.ws = staged_workspace(xd, wd, kernel_size, stride, padding, variant, operand, flags)
         out = dcn_forward(xd, od, wd, bd, kernel_size, stride, padding, variant, operand, flags, ws=ctx.ws)
-        ctx.save_for_backward(xd, od, wd)
+        ctx.relu = bool(flags & FLAG_RELU_OUT)    # see DeformLayerFunction
+        ctx.save_for_backward(xd, od, wd, *((out,) if ctx.relu else ()))
         ctx.cfg, ctx.home, ctx.has_bias = cfg, home, bias is not None
         ctx.dtypes = (x.dtype, offset.dtype, weight.dtype)
         return out if home == dev else out.to(home)
 
     @staticmethod
     def backward(ctx, grad_out):
-        xd, od, wd = ctx.saved_tensors
+        xd, od, wd = ctx.saved_tensors[:3]
         kernel_size, stride, padding, variant, operand, flags = ctx.cfg[:6]
         flags &= ~FLAG_ACCUM_GRAD_X     # autograd sums gradient terms itself; the output buffer here is fresh
         dev = xd.device
-        gx, goff, gw, gb = dcn_backward(xd, od, wd, _to_device(grad_out, dev), ctx.has_bias,
+        grad_out = _to_device(grad_out, dev)
+        if ctx.relu:
+            grad_out = grad_out * (ctx.saved_tensors[3] > 0)
+        gx, goff, gw, gb = dcn_backward(xd, od, wd, grad_out, ctx.has_bias,
                                         kernel_size, stride, padding, variant, operand, flags,
                                         need_grad_x=ctx.needs_input_grad[0], ws=ctx.ws,
                                         xt_staged=ctx.ws is not None)

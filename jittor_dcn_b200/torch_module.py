@@ -76,6 +76,26 @@ class TorchDeformConv2dJittorSemantics(TorchDeformConv2d):
     variant = _lib.VARIANT_JITTOR
 
 
+def fuse_eval_bn_relu(layer, bn):
+    """`relu(bn(layer(x)))` of the reference's detector (train.py:167-170, 329-332) for INFERENCE as one engine call:
+    returns a copy of `layer` whose weight / bias carry the eval-mode BatchNorm (running statistics) and whose forward
+    epilogue applies the ReLU (DCN_FLAG_RELU_OUT) — no separate post-op pass over the output.
+    The offset branch is untouched (BatchNorm acts on the layer's output only)."""
+    if bn.training:
+        raise ValueError("fuse_eval_bn_relu folds RUNNING statistics: call bn.eval() first")
+    import copy
+    fused = copy.deepcopy(layer)
+    with torch.no_grad():
+        inv = torch.rsqrt(bn.running_var + bn.eps)
+        scale = inv * (bn.weight if bn.weight is not None else 1.0)
+        shift = (bn.bias if bn.bias is not None else 0.0) - bn.running_mean * scale
+        fused.weight.mul_(scale.view(-1, 1, 1, 1))
+        old_bias = fused.bias if fused.bias is not None else torch.zeros_like(scale)
+        fused.bias = nn.Parameter(old_bias * scale + shift)
+    fused.engine_flags = layer.engine_flags | _lib.FLAG_RELU_OUT
+    return fused
+
+
 class BatchNormReLU2d(nn.BatchNorm2d):
     """`relu(bn(x))` of the reference's detector (train.py:167-170, 329-332) as one module: the parameters,
     buffers and state-dict keys of ``nn.BatchNorm2d`` (``weight``, ``bias``, ``running_mean``, ``running_var``,

@@ -153,3 +153,53 @@ def test_batch_variance_with_mean_far_above_std():
     assert float(((ours.running_var.cpu().double() - exp_rv).abs() / exp_rv).max()) < 1e-5
     exp_rm = 0.1 * m
     assert float((ours.running_mean.cpu().double() - exp_rm).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("variant_cls", [dcn.TorchDeformConv2d, dcn.TorchDeformConv2dJittorSemantics])
+@pytest.mark.parametrize("shape", [(2, 64, 64, 32, 32, 1), (2, 16, 32, 32, 32, 2), (2, 12, 20, 9, 11, 1)])
+@pytest.mark.parametrize("engine_offset_conv", [True, False])
+def test_relu_out_flag_and_folded_eval_batchnorm(shape, variant_cls, engine_offset_conv):
+    """DCN_FLAG_RELU_OUT: the forward epilogue applies the ReLU on every kernel family (tensor path
+    with and without the staged tensor-map store, whole-layer path, generic kernels for the odd shape), the autograd
+    nodes mask grad_out, and fuse_eval_bn_relu(layer, bn) reproduces relu(bn(layer(x))) in eval mode."""
+    B, C, O, H, W, s = shape
+    torch.manual_seed(21)
+    layer = variant_cls(C, O, 3, s, 1).cuda()
+    layer.engine_offset_conv = engine_offset_conv
+    with torch.no_grad():
+        layer.offset_conv.weight.normal_(0, 0.02)
+        layer.offset_conv.bias.normal_(0, 0.8)
+        layer.bias.normal_(0, 0.3)
+    x = torch.randn(B, C, H, W, device="cuda")
+    # (a) the flag alone
+    plain = layer(x).detach()
+    relu_layer = variant_cls(C, O, 3, s, 1).cuda()
+    relu_layer.load_state_dict(layer.state_dict())
+    relu_layer.engine_offset_conv = engine_offset_conv
+    relu_layer.engine_flags = dcn.FLAG_RELU_OUT
+    xa = x.clone().requires_grad_(True)
+    ya = relu_layer(xa)
+    assert torch.equal(ya.detach(), torch.relu(plain))
+    gout = torch.randn_like(ya)
+    ya.backward(gout)
+    xb = x.clone().requires_grad_(True)
+    layer.zero_grad()
+    torch.relu(layer(xb)).backward(gout)
+    assert rel_err(xa.grad.cpu().numpy(), xb.grad.cpu().numpy()) < 1e-5
+    for (n, pa), (_, pb) in zip(relu_layer.named_parameters(), layer.named_parameters()):
+        assert rel_err(pa.grad.cpu().numpy(), pb.grad.cpu().numpy()) < 1e-5, n
+    # (b) eval-mode BatchNorm folded into the layer
+    bn = torch.nn.BatchNorm2d(O).cuda()
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.5)
+        bn.running_var.uniform_(0.5, 2.0)
+        bn.weight.normal_(1.0, 0.2)
+        bn.bias.normal_(0, 0.3)
+    bn.eval()
+    with pytest.raises(ValueError):
+        dcn.fuse_eval_bn_relu(layer, torch.nn.BatchNorm2d(O).cuda().train())
+    fused = dcn.fuse_eval_bn_relu(layer, bn)
+    with torch.no_grad():
+        ref = torch.relu(bn(layer(x)))
+        got = fused(x)
+    assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 1e-5
