@@ -50,6 +50,10 @@ const Knobs& knobs() {
     v.bwd_no_fuse = env_int("DCN_BWD_NO_FUSE", 0);
     v.bwd_gbuf1 = env_int("DCN_BWD_GBUF", 0) == 1;
     v.bwd_data_simt = env_int("DCN_BWD_DATA_SIMT", 0);
+    v.conv_off = env_set("DCN_CONV_OFF");
+    v.conv_small_c = env_set("DCN_CONV_SMALL_C");
+    v.conv_debug = env_set("DCN_CONV_DEBUG");
+    v.conv_wstream = env_set("DCN_CONV_WSTREAM");
     return v;
   }();
   return k;

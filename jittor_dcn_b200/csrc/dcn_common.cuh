@@ -228,6 +228,11 @@ struct Knobs {
   int bwd_no_fuse;      // DCN_BWD_NO_FUSE      weight gradient as its own pass
   int bwd_gbuf1;        // DCN_BWD_GBUF=1       one grad_out tile buffer
   int bwd_data_simt;    // DCN_BWD_DATA_SIMT    fp32 data gradient on the generic kernels
+  int conv_wstream;     // DCN_CONV_WSTREAM     shifted-view conv: stream the weight tap images per K step even when they fit
+  int conv_debug;       // DCN_CONV_DEBUG       shifted-view conv: print per-role wait / work cycle counters of CTA 0
+  int conv_small_c;     // DCN_CONV_SMALL_C     shifted-view conv also for 16 / 32 input channels (slower; for A/B runs)
+  int conv_off;         // DCN_CONV_OFF         companion offset conv: the plain mode of the DCN kernels instead of the
+                        //                      shifted-view convolution kernels (dcn_conv.cu)
 };
 const Knobs& knobs();
 

@@ -75,6 +75,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       : "memory");
 }
 
+// One lane of a fully active, converged warp (elect.sync).  MMA issuers run their loop with ALL lanes and guard only
+// the tcgen05 instructions with this: the descriptor / address arithmetic then stays in the uniform datapath.  Inside an
+// `if (lane == 0)` region the compiler cannot prove the operands uniform and wraps every tcgen05.mma in a waterfall
+// loop (ELECT / BRA.U.ANY): measured 48 instead of 40 cycles per small MMA with loop-invariant operands, and ~130
+// cycles with per-MMA descriptor arithmetic (tools/mma_rate_probe.cu, profiles/r2_mma_rate.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- named barriers
 __device__ __forceinline__ void bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

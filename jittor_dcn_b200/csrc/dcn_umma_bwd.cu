@@ -45,10 +45,17 @@ bool umma_bwd_supported(const Geo& g, int operand) {
   return operand == DCN_OPERAND_FP32 || umma_bwd_data_supported(g, operand);
 }
 
+// shifted-view convolution kernels (dcn_conv.cu): preferred when they cover the shape
+bool conv_offset_bwd_supported(const Geo& g);
+size_t conv_offset_wtile_bytes(const Geo& g);
+int conv_offset_backward(const Geo& g, const float* xt, float* gxt, const float* goff, const float* woff, float* gwoff,
+                         uint8_t* wtiles, cudaStream_t st);
+
 // ---- companion offset convolution (PLAIN problem) inside the layer's backward pass ---------------------------------
 static bool plain_bwd_ok(const Geo& g) {
   Tiling t;
   if (!make_tiling(g, &t)) return false;
+  if (conv_offset_bwd_supported(g)) return true;
   const Geo gp = plain_geo(g, t, false);
   return umma_bwd_data_supported(gp, DCN_OPERAND_FP32) && umma_bwd_data_fuses_wgrad(gp, DCN_OPERAND_FP32);
 }
@@ -73,7 +80,8 @@ size_t umma_layer_bwd_workspace(const Geo& g) {
   if (!make_tiling(g, &t)) return 0;
   const Geo gp = plain_geo(g, t, false);
   const size_t tiles_dcn = umma_bwd_data_wtile_bytes(g0, DCN_OPERAND_FP32) + umma_bwd_data_gtile_bytes(g0, DCN_OPERAND_FP32);
-  const size_t tiles_pln = umma_bwd_data_wtile_bytes(gp, DCN_OPERAND_FP32) + umma_bwd_data_gtile_bytes(gp, DCN_OPERAND_FP32);
+  size_t tiles_pln = umma_bwd_data_wtile_bytes(gp, DCN_OPERAND_FP32) + umma_bwd_data_gtile_bytes(gp, DCN_OPERAND_FP32);
+  if (conv_offset_bwd_supported(g)) tiles_pln = conv_offset_wtile_bytes(g);
   const size_t a = umma_xt_bytes(g, DCN_OPERAND_FP32) + (tiles_dcn > tiles_pln ? tiles_dcn : tiles_pln);
   const size_t c = umma_wgrad_gtile_bytes(g0, DCN_OPERAND_FP32);
   return umma_xt_bytes(g, DCN_OPERAND_FP32) + (a > c ? a : c) + goff_bytes(g);
@@ -137,7 +145,13 @@ int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, cons
                                   (const uint8_t*)goutv + (size_t)o0 * g.HW * esz, goff, gwc, wtiles, gtiles, st)))
         return rc;
     }
-    if (woff) {
+    if (woff && conv_offset_bwd_supported(g)) {
+      const Geo gp = plain_geo(g, t, false);
+      uint8_t* wtiles2 = rest + umma_xt_bytes(g, DCN_OPERAND_FP32);
+      if ((rc = conv_offset_backward(g, (const float*)xt, want_gx ? gxt : nullptr, goff, woff, gwoff, wtiles2, st)))
+        return rc;
+      if ((rc = launch_bias_grad(gp, goff, DCN_OPERAND_FP32, gboff, st))) return rc;
+    } else if (woff) {
       const Geo gp = plain_geo(g, t, false);
       uint8_t* wtiles2 = rest + umma_xt_bytes(g, DCN_OPERAND_FP32);
       uint8_t* gtiles2 = wtiles2 + umma_bwd_data_wtile_bytes(gp, DCN_OPERAND_FP32);

@@ -423,8 +423,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
   } else if (warp == kEpiWarps) {
     if constexpr (MODE == MODE_FWD) {
     // ================================================================ MMA issuer (forward)
-    if (lane == 0) {
+    // The whole warp runs this (uniform) loop and elect.sync picks the issuing lane per instruction; every descriptor
+    // is one 64-bit add onto a per-stage base (the address field is the low 14 bits, 18-bit shared addresses never
+    // carry out of it).  Inside `if (lane == 0)` the compiler wraps every tcgen05.mma in a waterfall loop and the
+    // four descriptors of a K = 16 step cost ~40 dependent integer instructions: ~130 issue cycles per MMA, which is
+    // what an N = 256 MMA takes to EXECUTE (tools/mma_rate_probe.cu) — the issuer, not the tensor pipe, set the pace of
+    // the O = 256 layers.
+    {
       const uint32_t idesc = make_idesc_bf16(128, O, VARIANT == DCN_VARIANT_TORCH, false);
+      const uint64_t adesc0 = VARIANT == DCN_VARIANT_TORCH ? make_sdesc_sw128(smem_u32(stage_base), kAMnLbo, kAMnSbo)
+                                                           : make_sdesc_sw128(smem_u32(stage_base), 16, 1024);
+      const uint64_t bdesc0 = make_sdesc_sw128(smem_u32(stage_base) + NIMG * kATile, 16, 1024);
+      const uint32_t stage16 = P.stage_bytes >> 4, btile16 = P.b_tile >> 4;
+      constexpr uint32_t kATile16 = kATile >> 4;
+      constexpr uint32_t kAStep16 = VARIANT == DCN_VARIANT_TORCH ? (2 * kAMnSbo) >> 4 : 2;   // K = 16 step of the A image
       int s = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = tile0; tile < t.num_tiles; tile = next_tile(tile)) {
@@ -434,30 +446,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         for (int kb = 0; kb < t.KB; ++kb) {
           mbar_wait_relaxed(&full[s], phase, 64);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(stage_base + (size_t)s * P.stage_bytes);
-          const uint32_t a_lo = a_hi + kATile;
-          const uint32_t b_hi = a_hi + NIMG * kATile;
-          const uint32_t b_lo = b_hi + P.b_tile;
+          const uint64_t a_hi = adesc0 + (uint64_t)((uint32_t)s * stage16), b_hi = bdesc0 + (uint64_t)((uint32_t)s * stage16);
+          if (elect_one()) {
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            uint64_t dah, dal;
-            if (VARIANT == DCN_VARIANT_TORCH) {
-              dah = make_sdesc_sw128(a_hi + k4 * 2 * kAMnSbo, kAMnLbo, kAMnSbo);
-              dal = make_sdesc_sw128(a_lo + k4 * 2 * kAMnSbo, kAMnLbo, kAMnSbo);
-            } else {
-              dah = make_sdesc_sw128(a_hi + k4 * 32, 16, 1024);
-              dal = make_sdesc_sw128(a_lo + k4 * 32, 16, 1024);
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t dah = a_hi + (uint64_t)(k4 * kAStep16), dbh = b_hi + (uint64_t)(k4 * 2);
+              umma_bf16(d_tmem, dah, dbh, idesc, (kb | k4) ? 1u : 0u);
+              if (!BF) {
+                umma_bf16(d_tmem, dah, dbh + btile16, idesc, 1u);
+                umma_bf16(d_tmem, dah + kATile16, dbh, idesc, 1u);
+              }
             }
-            const uint64_t dbh = make_sdesc_sw128(b_hi + k4 * 32, 16, 1024);
-            const uint64_t dbl = make_sdesc_sw128(b_lo + k4 * 32, 16, 1024);
-            umma_bf16(d_tmem, dah, dbh, idesc, (kb | k4) ? 1u : 0u);
-            if (!BF) {
-              umma_bf16(d_tmem, dah, dbl, idesc, 1u);
-              umma_bf16(d_tmem, dal, dbh, idesc, 1u);
-            }
+            umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
+            if (kb == t.KB - 1) umma_commit(&tfull[acc]);
           }
-          umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
-          if (kb == t.KB - 1) umma_commit(&tfull[acc]);
+          __syncwarp();
           if (++s == P.stages) {
             s = 0;
             phase ^= 1;
@@ -1060,9 +1063,16 @@ int umma_forward_any(const Geo& g, int operand, const void* x, const float* off,
 // ---- the companion offset convolution (deform_conv.py:16-21,58 / train.py:80-85,98) as a PLAIN problem -----------
 // g is the DCN layer; the staged copy of x at the head of the workspace is the layer's (channel-permuted for the
 // Torch layout), so offset conv, dcn_forward and dcn_backward share ONE staging pass.
+// shifted-view convolution kernels (dcn_conv.cu): preferred when they cover the shape
+bool conv_offset_fwd_supported(const Geo& g);
+size_t conv_offset_wtile_bytes(const Geo& g);
+int conv_offset_forward(const Geo& g, const float* xt, const float* woff, const float* boff, float* offset_out,
+                        uint8_t* wtiles, cudaStream_t st);
+
 bool umma_offset_conv_fwd_supported(const Geo& g) {
   Tiling t;
   if (!make_tiling(g, &t)) return false;          // the layer's own staging layout
+  if (conv_offset_fwd_supported(g)) return true;
   const Geo gp = plain_geo(g, t, true);
   return umma_fwd_supported(gp, DCN_OPERAND_FP32);
 }
@@ -1070,7 +1080,9 @@ bool umma_offset_conv_fwd_supported(const Geo& g) {
 size_t umma_offset_conv_fwd_workspace(const Geo& g) {
   Tiling t;
   if (!make_tiling(g, &t)) return 0;
-  return umma_fwd_workspace(plain_geo(g, t, true), DCN_OPERAND_FP32);
+  const size_t a = umma_fwd_workspace(plain_geo(g, t, true), DCN_OPERAND_FP32);
+  const size_t b = umma_xt_bytes(g, DCN_OPERAND_FP32) + conv_offset_wtile_bytes(g);
+  return a > b ? a : b;
 }
 
 int umma_offset_conv_forward(const Geo& g, const void* x, const float* woff, const float* boff, float* offset_out,
@@ -1082,6 +1094,9 @@ int umma_offset_conv_forward(const Geo& g, const void* x, const float* woff, con
   }
   int rc;
   if (stage_x && (rc = launch_nchw_to_nhwc(g, t, x, workspace, DCN_OPERAND_FP32, st))) return rc;
+  if (conv_offset_fwd_supported(g))
+    return conv_offset_forward(g, (const float*)workspace, woff, boff, offset_out,
+                               (uint8_t*)workspace + umma_xt_bytes(g, DCN_OPERAND_FP32), st);
   const Geo gp = plain_geo(g, t, true);
   return umma_forward_any(gp, DCN_OPERAND_FP32, x, nullptr, woff, boff, offset_out, workspace, st, false);
 }
