@@ -631,7 +631,11 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
     }
   } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
+    // The whole warp runs this (uniform) loop; elect.sync picks the issuing lane per group of instructions and every
+    // descriptor is one 64-bit add onto a loop-invariant base (dcn_umma.cuh:elect_one, tools/mma_rate_probe.cu): inside
+    // `if (lane == 0)` each tcgen05.mma sat in a waterfall loop behind ~10 dependent integer instructions per descriptor,
+    // and this warp shares its scheduler with four scatter warps.
+    {
       const uint32_t idesc = make_idesc_bf16(128, ncols, false, false);
       const uint32_t idesc_w = make_idesc_bf16(128, ncols, true, true);  // A = g^T and B = S, both MN-major
       int s = 0, acc = 0, sb = 0, gb = 0;
@@ -651,16 +655,17 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
           // shared zero image), B = sample operand read MN-major
           const uint32_t g_lbo = P.OB >= 2 ? NIMG * P.g_img : g_zero_off - (uint32_t)gb * g_buf;
           const uint32_t d_tmem = d2_base + (uint32_t)((cb - cb0) * ncols);
+          const uint64_t dg0 = make_sdesc_sw128(g_hi, g_lbo, 1024), ds0 = make_sdesc_sw128(sbase, 1024, 1024);
+          const uint32_t gimg16 = P.g_img >> 4;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {  // 8 steps of 16 tile rows
-            const uint64_t dgh = make_sdesc_sw128(g_hi + ks * 2048, g_lbo, 1024);
-            const uint64_t dgl = make_sdesc_sw128(g_lo + ks * 2048, g_lbo, 1024);
-            const uint64_t dsh = make_sdesc_sw128(sbase + ks * 2048, 1024, 1024);
-            const uint64_t dsl = make_sdesc_sw128(sbase + s_img + ks * 2048, 1024, 1024);
-            umma_bf16(d_tmem, dgh, dsh, idesc_w, (first && ks == 0) ? 0u : 1u);
-            if (!BF) {
-              umma_bf16(d_tmem, dgh, dsl, idesc_w, 1u);
-              umma_bf16(d_tmem, dgl, dsh, idesc_w, 1u);
+            for (int ks = 0; ks < 8; ++ks) {  // 8 steps of 16 tile rows
+              const uint64_t dgh = dg0 + (uint64_t)(ks * 128), dsh = ds0 + (uint64_t)(ks * 128);
+              umma_bf16(d_tmem, dgh, dsh, idesc_w, (first && ks == 0) ? 0u : 1u);
+              if (!BF) {
+                umma_bf16(d_tmem, dgh, dsh + (s_img >> 4), idesc_w, 1u);
+                umma_bf16(d_tmem, dgh + gimg16, dsh, idesc_w, 1u);
+              }
             }
           }
         } else {
@@ -669,20 +674,22 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
           // (o contiguous; 64-o atoms = consecutive images): no padded operand rows at all
           const uint32_t g_lbo = NIMG * P.g_img;
           const uint32_t d_tmem = d2_base + (uint32_t)((cb - cb0) * P.o_cols);
+          const uint64_t ds0 = make_sdesc_sw128(sbase, 16, 1024), dg0 = make_sdesc_sw128(g_hi, g_lbo, 1024);
+          const uint32_t gimg16 = P.g_img >> 4;
+          if (elect_one()) {
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {  // 4 steps of 16 pixels
-            const uint64_t dsh = make_sdesc_sw128(sbase + k4 * 32, 16, 1024);
-            const uint64_t dsl = make_sdesc_sw128(sbase + s_img + k4 * 32, 16, 1024);
-            const uint64_t dgh = make_sdesc_sw128(g_hi + k4 * 2048, g_lbo, 1024);
-            const uint64_t dgl = make_sdesc_sw128(g_lo + k4 * 2048, g_lbo, 1024);
-            umma_bf16(d_tmem, dsh, dgh, idesc_wj, (first && k4 == 0) ? 0u : 1u);
-            if (!BF) {
-              umma_bf16(d_tmem, dsh, dgl, idesc_wj, 1u);
-              umma_bf16(d_tmem, dsl, dgh, idesc_wj, 1u);
+            for (int k4 = 0; k4 < 4; ++k4) {  // 4 steps of 16 pixels
+              const uint64_t dsh = ds0 + (uint64_t)(k4 * 2), dgh = dg0 + (uint64_t)(k4 * 128);
+              umma_bf16(d_tmem, dsh, dgh, idesc_wj, (first && k4 == 0) ? 0u : 1u);
+              if (!BF) {
+                umma_bf16(d_tmem, dsh, dgh + gimg16, idesc_wj, 1u);
+                umma_bf16(d_tmem, dsh + (s_img >> 4), dgh, idesc_wj, 1u);
+              }
             }
           }
         }
-        umma_commit(&sempty[sb]);
+        if (elect_one()) umma_commit(&sempty[sb]);
+        __syncwarp();
         sb ^= 1;
         if (sb == 0) sphase ^= 1;
       };
@@ -699,7 +706,8 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
       auto drain = [&]() {
         if (!pend) return;
         wgrad_mmas(pend_cb, pend_first, pend_gb);
-        if (pend_last) umma_commit(&gempty[pend_gb]);  // grad_out tile buffer may be overwritten
+        if (pend_last && elect_one()) umma_commit(&gempty[pend_gb]);  // grad_out tile buffer may be overwritten
+        __syncwarp();
         pend = false;
       };
       for (int tile = tile0; tile < P.num_tiles; tile += tile_step) {
@@ -725,27 +733,30 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
             const uint32_t a_lo = VARIANT == DCN_VARIANT_TORCH ? r_lo : w_lo;
             const uint32_t b_hi = VARIANT == DCN_VARIANT_TORCH ? w_hi : r_hi;
             const uint32_t b_lo = VARIANT == DCN_VARIANT_TORCH ? w_lo : r_lo;
+            const uint64_t da0 = make_sdesc_sw128(a_hi, 16, 1024), db0 = make_sdesc_sw128(b_hi, 16, 1024);
+            const uint32_t alo16 = (a_lo - a_hi) >> 4, blo16 = (b_lo - b_hi) >> 4;
+            if (elect_one()) {
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const uint64_t dah = make_sdesc_sw128(a_hi + k4 * 32, 16, 1024);
-              const uint64_t dal = make_sdesc_sw128(a_lo + k4 * 32, 16, 1024);
-              const uint64_t dbh = make_sdesc_sw128(b_hi + k4 * 32, 16, 1024);
-              const uint64_t dbl = make_sdesc_sw128(b_lo + k4 * 32, 16, 1024);
-              umma_bf16(d_tmem, dah, dbh, idesc, (ob | k4) ? 1u : 0u);
-              if (!BF) {
-                umma_bf16(d_tmem, dah, dbl, idesc, 1u);
-                umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint64_t dah = da0 + (uint64_t)(k4 * 2), dbh = db0 + (uint64_t)(k4 * 2);
+                umma_bf16(d_tmem, dah, dbh, idesc, (ob | k4) ? 1u : 0u);
+                if (!BF) {
+                  umma_bf16(d_tmem, dah, dbh + blo16, idesc, 1u);
+                  umma_bf16(d_tmem, dah + alo16, dbh, idesc, 1u);
+                }
               }
+              if (!P.w_resident) umma_commit(&wempty[s]);
             }
+            __syncwarp();
             if (!P.w_resident) {
-              umma_commit(&wempty[s]);
               if (++s == P.w_ring) {
                 s = 0;
                 phase ^= 1;
               }
             }
           }
-          umma_commit(&tfull[acc]);
+          if (elect_one()) umma_commit(&tfull[acc]);
+          __syncwarp();
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
           if (FUSE) {
@@ -757,8 +768,10 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
             pend_last = cb == cb1 - 1;
           }
         }
-        if (!FUSE) umma_commit(&gempty[gb]);
-        else if (P.g_nbuf == 1) drain();
+        if (!FUSE) {
+          if (elect_one()) umma_commit(&gempty[gb]);
+          __syncwarp();
+        } else if (P.g_nbuf == 1) drain();
         if (++gb == P.g_nbuf) {
           gb = 0;
           gphase ^= 1;
@@ -766,7 +779,8 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
         first_tile = false;
       }
       if (FUSE) drain();
-      if (FUSE) umma_commit(dfull);
+      if (FUSE && elect_one()) umma_commit(dfull);
+      __syncwarp();
     }
   } else if (warp == kLoadWarp) {
     // ================================================================ Wm^T tile loader
