@@ -193,6 +193,24 @@ DCN_API int dcn_layer_backward(const DcnShape* s, const void* x, const void* off
 DCN_API int dcn_debug_corners(const DcnShape* s, const void* offset, int32_t* y0, int32_t* x0,
                       float* w4, void* stream);
 
+/* ---- DeformRoIPool / DeformPSRoIPool (deform_conv.py:83-157, 160-241) ----------------------------------
+ * Only the pooled 1 x 1 case exists: both reference modules sum over the bin axis and then reshape [num_rois, C] to
+ * [num_rois, C, pooled_h, pooled_w] (:137-157, :236-241), which is only defined for one bin.  Semantics as written in
+ * the reference, including the clamp-then-subtract corner weights (:125-131):
+ *   features [B,C,H,W] f32   rois [R,5] f32 = (batch index, x1, y1, x2, y2)
+ *   offsets  [R,2] f32 = (x, y) of the single bin  (DeformRoIPool: offsets[:, 0, 0:2], scaled by roi_w / roi_h;
+ *                         DeformPSRoIPool: offsets[:, 0:2], scaled by roi_w / roi_h * trans_std, skipped if no_trans)
+ *   out      [R,C] f32 (the caller views it as [R,C,1,1])
+ * Backward: grad_features [B,C,H,W] is zeroed and accumulated (may be NULL), grad_offsets [R,2] (may be NULL); rois
+ * receive no gradient. */
+enum { DCN_ROI_POOL = 0, DCN_PSROI_POOL = 1 };
+DCN_API int dcn_roi_pool_forward(int kind, int B, int C, int H, int W, int R, const void* features, const void* rois,
+                                 const void* offsets, float spatial_scale, float trans_std, int no_trans, void* out,
+                                 void* stream);
+DCN_API int dcn_roi_pool_backward(int kind, int B, int C, int H, int W, int R, const void* features, const void* rois,
+                                  const void* offsets, float spatial_scale, float trans_std, int no_trans,
+                                  const void* grad_out, void* grad_features, void* grad_offsets, void* stream);
+
 /* ---- post-op: BatchNorm2d + ReLU ------------------------------------------
  * Replaces `relu(bn(x))` after every DeformConv2d layer of the reference's detector (modules
  * train.py:146-159 / 311-322, call sites train.py:167-170 / 329-332): nn.BatchNorm2d semantics

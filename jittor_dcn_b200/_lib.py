@@ -20,6 +20,7 @@ FLAG_RELU_OUT = 1 << 3     # forward epilogue stores max(acc + bias, 0) (SURVEY 
 FLAG_XT_STAGED = 1 << 4
 PHASE_FORWARD, PHASE_BACKWARD, PHASE_CORNERS = 0, 1, 2
 PHASE_LAYER_FORWARD, PHASE_LAYER_BACKWARD = 3, 4   # offset conv + DCN span (dcn_layer_*)
+ROI_POOL, PSROI_POOL = 0, 1                        # dcn_roi_pool_* kind (deform_conv.py:83 / :160)
 
 # every symbol include/dcn_b200.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = (
@@ -30,7 +31,7 @@ EXPORTS = (
     "dcn_comm_destroy", "dcn_bn_workspace_bytes", "dcn_bn_relu_forward", "dcn_bn_relu_backward",
     "dcn_offset_conv_forward", "dcn_layer_forward", "dcn_layer_backward",
     "dcn_p2p_handle_bytes", "dcn_p2p_create", "dcn_p2p_local_handle", "dcn_p2p_connect",
-    "dcn_p2p_allreduce_sum_f32", "dcn_p2p_destroy",
+    "dcn_p2p_allreduce_sum_f32", "dcn_p2p_destroy", "dcn_roi_pool_forward", "dcn_roi_pool_backward",
 )
 
 
@@ -93,6 +94,8 @@ def load():
     lib.dcn_bn_workspace_bytes.argtypes = [i32]
     lib.dcn_bn_relu_forward.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, sz, vp]
     lib.dcn_bn_relu_backward.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.dcn_roi_pool_forward.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, f32, f32, i32, vp, vp]
+    lib.dcn_roi_pool_backward.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, f32, f32, i32, vp, vp, vp, vp]
     _lib = lib
     return lib
 
