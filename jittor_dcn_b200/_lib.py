@@ -6,7 +6,9 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdcn_b200.so")
+# DCN_B200_LIB=dbg selects the debug build (python -m jittor_dcn_b200.build --debug: device-side bounds and
+# pipeline-agreement checks, csrc/dcn_common.cuh) — for test runs only
+LIB_PATH = os.path.join(HERE, "libdcn_b200_dbg.so" if os.environ.get("DCN_B200_LIB") == "dbg" else "libdcn_b200.so")
 
 VARIANT_JITTOR = 0   # deform_conv.py:56-81
 VARIANT_TORCH = 1    # train.py:95-140

@@ -41,7 +41,14 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, debug=False):
+    """debug=True: libdcn_b200_dbg.so with -DDCN_DEBUG_CHECKS (device-side bounds / pipeline-agreement checks,
+    csrc/dcn_common.cuh); tests and tools pick it with DCN_B200_LIB=dbg."""
+    global OBJ, LIB
+    if debug:
+        OBJ, LIB = os.path.join(CSRC, "_build_dbg"), os.path.join(HERE, "libdcn_b200_dbg.so")
+    else:
+        OBJ, LIB = os.path.join(CSRC, "_build"), os.path.join(HERE, "libdcn_b200.so")
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
@@ -53,7 +60,8 @@ def build(force=False, verbose=False):
         op = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         objs.append(op)
         if force or _stale(op, [sp] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + ["-Xptxas", "-v"] * bool(verbose) + ["-c", sp, "-o", op]
+            cmd = [nvcc] + NVCC_FLAGS + ["-DDCN_DEBUG_CHECKS=1"] * bool(debug) + ["-Xptxas", "-v"] * bool(verbose) + \
+                ["-c", sp, "-o", op]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     failed = False
     for src, p in procs:
@@ -71,4 +79,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

@@ -10,6 +10,27 @@
 
 #include "../../include/dcn_b200.h"
 
+// Debug build (python -m jittor_dcn_b200.build --debug -> libdcn_b200_dbg.so, selected with DCN_B200_LIB=dbg):
+// compute-sanitizer is closed on the GPU pool, so the kernels carry their own checks — bounds on every global address
+// the gather / scatter / epilogue code forms from plan entries, and at kernel exit the agreement of the step counts of
+// all roles that hand stages to each other through mbarriers (a role that ran one step more or less than its partner
+// would not necessarily hang).  A failed check prints its location and traps; the release build compiles them away.
+#ifdef DCN_DEBUG_CHECKS
+#include <cstdio>
+#define DCN_DEV_ASSERT(cond)                                                                                  \
+  do {                                                                                                        \
+    if (!(cond)) {                                                                                            \
+      printf("DCN_DEV_ASSERT failed: %s  at %s:%d  block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+             (int)threadIdx.x);                                                                               \
+      __trap();                                                                                               \
+    }                                                                                                         \
+  } while (0)
+#define DCN_DBG_ONLY(...) __VA_ARGS__
+#else
+#define DCN_DEV_ASSERT(cond) do { } while (0)
+#define DCN_DBG_ONLY(...)
+#endif
+
 namespace dcn {
 
 // Device-side problem geometry (passed by value to every kernel).

@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_kernel(const __grid_constant
             for (int i = 0; i < 16; ++i) {
               if (c0 + i >= P.O) break;
               const float bv = P.bias ? __ldg(P.bias + c0 + i) : 0.f;
+              DCN_DEV_ASSERT((size_t)(dst - P.out) + (size_t)(c0 + i) * P.Ho * P.Wo < (size_t)P.B * P.O * P.Ho * P.Wo);
               dst[(size_t)(c0 + i) * P.Ho * P.Wo] = v[i] + bv;
             }
           }
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_kernel(const __grid_constant
             valid = valid && fy >= 1 && fy <= P.H && fx >= 1 && fx <= P.W;
           }
           float* dst = img + ((size_t)fy * (P.W + 2) + fx) * P.C;
+          DCN_DEV_ASSERT(!valid || (size_t)(dst - P.gxt) + P.Nn <= (size_t)P.B * P.img_stride);
           const uint32_t taddr =
               tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((acc * nacc + a) * 2 * P.Nn);
           for (int c0 = 0; c0 < P.Nn; c0 += 16) {
@@ -529,6 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_kernel(const __grid_constant
           const bool oki = (item[i] >> 28) && q.ti.r0 + hr < P.GR && fy0 + hr * P.s <= P.H + 2 && fx0 + j <= P.W + 1;
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (oki) {
+            DCN_DEV_ASSERT(base >= P.xt && (size_t)(base - P.xt) + src_off[i] + 4 <= (size_t)P.B * P.img_stride);
             v[i] = __ldg(reinterpret_cast<const float4*>(base + src_off[i]));
             ok |= 1u << i;
           }

@@ -456,6 +456,8 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
             const float fx = __uint_as_float(e4.y), fy = __uint_as_float(e4.z);
             constexpr int XS = BF ? 1 : 0;
             const char* xp = xpair + (e4.x >> XS);
+            // the south-east corner's channel pair still lies inside this image of the framed copies
+            DCN_DEV_ASSERT((size_t)(e4.x >> 2) + (size_t)(PLAIN ? 0 : xt_row_pitch(g) + g.C) + (size_t)(chan - odd) + 2 <= img_stride);
             float2 v0, v1, v2, v3;
             if (PLAIN) {
               if (BF) {
@@ -540,6 +542,7 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
             // value index: lane bit 3 -> component (0 g_ix, 1 g_iy), bits 2..1 -> column inside the thread's four
             const int vi = (lane >> 1) & 7, col = cu0 + (vi & 3);
             const int gidx = pl[col].gidx;
+            DCN_DEV_ASSERT(gidx < 0 || (size_t)gidx + (size_t)P.ix_delta < (size_t)g.B * 2 * g.N * g.HW);
             if (gidx >= 0 && part_g[0] != 0.f)
               atomicAdd(P.goff + (size_t)gidx + (vi < 4 ? (size_t)P.ix_delta : 0),
                         part_g[0] * (vi < 4 ? P.scale_ix : P.scale_iy));

@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  DCN_DBG_ONLY(__shared__ int dbg_steps[5]; if (tid < 5) dbg_steps[tid] = -1; int dbg_n = 0;)
   const int O = g.O;
   // which (tile, K block) pairs this CTA walks: forward = all K blocks of every gridDim-th tile;
   // weight gradient = one slice of K blocks for one chunk of the row tiles
@@ -364,6 +365,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
               if (PLAIN && c0 + i >= g.o_valid) break;   // padded accumulator columns of a plain problem
               const float bv = P.bias ? __ldg(P.bias + c0 + i) : 0.f;
               const float r = v[i] + bv;
+              DCN_DEV_ASSERT(out_off + (size_t)(c0 + i) * g.HW < (size_t)g.B * g.Oimg * g.HW);
               P.out[out_off + (size_t)(c0 + i) * g.HW] = g.relu_out ? fmaxf(r, 0.f) : r;
             }
           }
@@ -461,6 +463,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
             if (kb == t.KB - 1) umma_commit(&tfull[acc]);
           }
           __syncwarp();
+          DCN_DBG_ONLY(++dbg_n;)
           if (++s == P.stages) {
             s = 0;
             phase ^= 1;
@@ -469,6 +472,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+      DCN_DBG_ONLY(if (lane == 0) dbg_steps[0] = dbg_n;)
     }
     } else {
     // ================================================================ MMA issuer (weight gradient)
@@ -545,12 +549,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
           uint8_t* dst = stage_base + (size_t)s * P.stage_bytes + NIMG * kATile;
           mbar_arrive_expect_tx(&full[s], NIMG * P.b_tile);
           bulk_g2s(dst, P.wtiles + (size_t)kb_of(kb) * NIMG * P.b_tile, NIMG * P.b_tile, &full[s]);
+          DCN_DBG_ONLY(++dbg_n;)
           if (++s == P.stages) {
             s = 0;
             phase ^= 1;
           }
         }
       }
+      DCN_DBG_ONLY(dbg_steps[1] = dbg_n;)
     }
   } else if (warp < kFirstProdWarp) {
     // ================================================================ plan warps
@@ -590,8 +596,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         }
         pbuf ^= 1;
         if (pbuf == 0) pphase ^= 1;
+        DCN_DBG_ONLY(++dbg_n;)
       }
     }
+    DCN_DBG_ONLY(if (pt == 0) dbg_steps[2] = dbg_n;)
   } else {
     // ================================================================ gather warps
     // kIt items (one 16-byte load per corner: 4 fp32 or 8 bf16 channels) per thread and K block,
@@ -682,6 +690,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         pl += tl * 128;
       }
       const XT* base = img[it] + jc;
+      DCN_DEV_ASSERT(base >= xt && pl[ent_idx[it]].off[0] >= 0 &&
+                     (size_t)(base - xt) + (size_t)pl[ent_idx[it]].off[3] + V <= (size_t)g.B * img_stride);
       if (PLAIN) {
         v[buf][0] = __ldg(reinterpret_cast<const uint4*>(base + pl[ent_idx[it]].off[0]));
       } else {
@@ -751,6 +761,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
           mbar_arrive(&full[q.s]);
           mbar_arrive(&pempty[q.pbuf]);
         }
+        DCN_DBG_ONLY(++dbg_n;)
       };
       auto start = [&](const Pos& q, const Pos& prev, uint4 (&dst)[kIt]) {
         if (q.tile != prev.tile) set_images(q.tile);
@@ -845,13 +856,23 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
         mbar_arrive(&full[cur.s]);
         mbar_arrive(&pempty[cur.pbuf]);
       }
+      DCN_DBG_ONLY(++dbg_n;)
       cur = nxt;
     }
     }
+    DCN_DBG_ONLY(if (pt == 0) dbg_steps[3] = dbg_n;)
   }
 
   tc_fence_before();
   __syncthreads();
+#ifdef DCN_DEBUG_CHECKS
+  // every role that exchanges stages through the mbarrier rings walked the same number of K steps
+  if (tid == 0) {
+    const int ref = dbg_steps[3];   // gather warps
+    DCN_DEV_ASSERT(dbg_steps[2] == ref);                                   // plan warps
+    if (MODE == MODE_FWD) DCN_DEV_ASSERT(dbg_steps[0] == ref && dbg_steps[1] == ref);   // MMA issuer, weight loader
+  }
+#endif
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols)
                  : "memory");

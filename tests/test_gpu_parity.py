@@ -549,3 +549,63 @@ def test_backward_accumulates_into_a_given_grad_x(variant, flags):
     assert rel_err(goff1.cpu().numpy(), goff0.cpu().numpy()) < 1e-5 and rel_err(gw1.cpu().numpy(), gw0.cpu().numpy()) < 1e-5
     with pytest.raises(ValueError):
         dcn.dcn_backward(x, off, w, gout, False, 3, 1, 1, variant, flags=flags | dcn.FLAG_ACCUM_GRAD_X)
+
+
+def test_detector_training_step_every_dcn_layer_at_1e3():
+    """the whole-step gradient check above needs 2e-2 because the step is not a continuous function
+    of round-off.  Here every DCN layer INSIDE that same training step is held to north_star's 1e-3: the step is run on
+    the CPU with the reference's op chain (oracle/torch_chain.py, pinned bit-for-bit to the unmodified reference and, as
+    a detector, to the golden step), each layer's input, offsets and output gradient are captured, and the engine is
+    given exactly those tensors — same offsets on both sides, so no sample changes its pixel cell:
+      span   dcn_forward / dcn_backward            vs the chain's out, grad_x (span term), grad_offset, grad_weight, grad_bias
+      layer  dcn_layer_backward (offset conv on the engine) vs the chain's total grad_x and offset_conv gradients."""
+    import torch.nn.functional as F
+    from jittor_dcn_b200.detector import EDNetDetection, detection_loss
+    from jittor_dcn_b200.functional import dcn_layer_backward, layer_supported
+    from oracle import torch_chain
+    g, ev = golden("detector_train_step"), golden("detector_eval")
+    torch.manual_seed(0)
+    m = EDNetDetection(dcn_cls=torch_chain.ChainLayer, fused_bn_relu=False).train()
+    m.load_state_dict({k[3:]: torch.as_tensor(v) for k, v in ev.items() if k.startswith("sd.")})
+    cap = {}
+    hooks = []
+    for name in ("conv2", "conv3", "conv4", "conv5"):
+        layer = getattr(m, name)
+        hooks.append(layer.register_forward_hook(
+            lambda mod, inp, out, name=name: cap.setdefault(name, {}).update(x=inp[0].detach().clone(), out=out.detach().clone())))
+        hooks.append(layer.register_full_backward_hook(
+            lambda mod, gin, gout, name=name: cap[name].update(gout=gout[0].detach().clone(), gx=gin[0].detach().clone())))
+    cls, bbox = m(torch.as_tensor(g["x"]))
+    detection_loss(cls, bbox, torch.as_tensor(g["labels"]), torch.as_tensor(g["boxes"])).backward()
+    for h in hooks:
+        h.remove()
+    for name in ("conv2", "conv3", "conv4", "conv5"):
+        layer, c = getattr(m, name), cap[name]
+        k, s, p = layer.k, layer.s, layer.p
+        O = layer.weight.shape[0]
+        x, gout = c["x"], c["gout"]
+        with torch.no_grad():
+            off = F.conv2d(x, layer.offset_conv.weight, layer.offset_conv.bias, stride=s, padding=p)
+        # the chain's span gradients on these offsets (CPU reference)
+        r_out, (r_gx, r_goff, r_gw, r_gb) = torch_chain.chain_forward_backward(
+            x, off, layer.weight.detach(), layer.bias.detach(), gout, variant="torch", kernel_size=k, stride=s, padding=p)
+        assert rel_err(r_out.numpy(), c["out"].numpy()) < 1e-6, name          # the capture is this layer's step
+        xd, od, wd, bd, gd = (t.cuda() for t in (x, off, layer.weight.detach(), layer.bias.detach(), gout))
+        out = dcn.dcn_forward(xd, od, wd, bd, k, s, p, dcn.VARIANT_TORCH)
+        gx, goff, gw, gb = dcn.dcn_backward(xd, od, wd, gd, True, k, s, p, dcn.VARIANT_TORCH)
+        assert rel_err(out.cpu().numpy(), r_out.numpy()) < FWD_TOL, name
+        for got, ref, nm in ((gx, r_gx, "gx"), (goff, r_goff, "goff"), (gw, r_gw, "gw")):
+            assert rel_err(got.cpu().numpy(), ref.numpy()) < GRAD_TOL, (name, nm)
+        # grad_bias sits in front of a BatchNorm: mathematically zero (the batch mean removes a bias), what both sides
+        # hold is the round-off of a sum of |grad_out| ~ bias_scale; compare on that scale
+        bias_scale = float(gout.abs().sum(dim=(0, 2, 3)).max())
+        assert float((gb.cpu() - r_gb).abs().max()) < 1e-5 * bias_scale, name
+        # whole layer: the offset conv's backward on the engine, against the step's own gradients
+        assert layer_supported(x.shape, O, k, s, p, dcn.VARIANT_TORCH)
+        lgx, lgwo, lgbo, lgw, lgb = dcn_layer_backward(xd, od, layer.offset_conv.weight.detach().cuda(), wd, gd, True, True,
+                                                       k, s, p, dcn.VARIANT_TORCH)
+        assert rel_err(lgx.cpu().numpy(), c["gx"].numpy()) < GRAD_TOL, name
+        assert rel_err(lgwo.cpu().numpy(), layer.offset_conv.weight.grad.numpy()) < GRAD_TOL, name
+        assert rel_err(lgbo.cpu().numpy(), layer.offset_conv.bias.grad.numpy()) < GRAD_TOL, name
+        assert rel_err(lgw.cpu().numpy(), layer.weight.grad.numpy()) < GRAD_TOL, name
+        assert float((lgb.cpu() - layer.bias.grad).abs().max()) < 1e-5 * bias_scale, name

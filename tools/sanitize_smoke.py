@@ -22,4 +22,23 @@ for (B, C, O, H, W, k, s, p) in cases:
             grads = dcn.dcn_backward(x, off, wt, gout, True, k, s, p, variant, flags=flags)
         torch.cuda.synchronize()
         print("ok", (B, C, O, H, W), "variant", variant, float(out.abs().sum()))
+# whole layer (offset conv on the engine: shifted-view kernels for C % 64 == 0, plain mode otherwise) + RoI pools
+from jittor_dcn_b200.functional import dcn_layer_backward, dcn_layer_forward
+for (B, C, O, H, W, s) in [(2, 64, 64, 16, 16, 1), (2, 16, 32, 32, 32, 2), (1, 128, 64, 12, 20, 1), (2, 64, 128, 16, 16, 2)]:
+    for variant in (dcn.VARIANT_TORCH, dcn.VARIANT_JITTOR):
+        x = torch.randn(B, C, H, W, device="cuda")
+        wt = torch.randn(O, C, 3, 3, device="cuda") * 0.1
+        wo = torch.randn(18, C, 3, 3, device="cuda") * 0.02
+        bo = torch.randn(18, device="cuda")
+        Ho, Wo = (H + 2 - 3) // s + 1, (W + 2 - 3) // s + 1
+        gout = torch.randn(B, O, Ho, Wo, device="cuda")
+        off, out = dcn_layer_forward(x, wo, bo, wt, None, 3, s, 1, variant)
+        grads = dcn_layer_backward(x, off, wo, wt, gout, True, False, 3, s, 1, variant)
+        torch.cuda.synchronize()
+        print("ok layer", (B, C, O, H, W, s), "variant", variant, float(out.abs().sum()))
+f = torch.randn(2, 40, 9, 11, device="cuda", requires_grad=True)
+rois = torch.tensor([[0, 1., 1., 6., 5.], [1, -3., 2., 20., 30.]], device="cuda")
+o = torch.randn(2, 1, 2, device="cuda", requires_grad=True)
+dcn.DeformRoIPool(1)(f, rois, o).sum().backward()
+torch.cuda.synchronize()
 print("sanitize smoke done")
