@@ -481,7 +481,8 @@ def run_stack(args):
     operand = dcn.OPERAND_BF16 if args.operand == "bf16" else dcn.OPERAND_FP32
     act = torch.bfloat16 if operand == dcn.OPERAND_BF16 else torch.float32
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    layers, paths, work = {}, {}, {"fwd": {"bytes": 0, "flops": 0}, "bwd": {"bytes": 0, "flops": 0}}
+    roles = ("fwd", "bwd_data", "bwd_weight", "bwd")
+    layers, paths, work = {}, {}, {r: {"bytes": 0, "flops": 0} for r in roles}
     for name in sorted(set(STACK_ORDER)):
         _, B, C, O, H, W, k, s, p = WORKLOADS[name]
         N = k * k
@@ -496,7 +497,7 @@ def run_stack(args):
         layers[name] = (x, off, wt, bias, gout, ws, (k, s, p))
         paths[name] = [lib.dcn_path_name(ctypes.byref(shp), ph).decode() for ph in (0, 1)]
         w1 = layer_bytes_flops(B, C, O, H, W, Ho, Wo, N, act_bytes=x.element_size())
-        for ph in ("fwd", "bwd"):
+        for ph in roles:
             for q in ("bytes", "flops"):
                 work[ph][q] += w1[ph][q] * STACK_ORDER.count(name)
     B = WORKLOADS["c3"][1]
@@ -552,8 +553,15 @@ def run_stack(args):
         # all launches of the dominant kernel in one step, against the work of all 13 layers in that role
         tot_s = prof[top][1] / args.steps * 1e-3
         ach = work[role]["flops"] / tot_s / 1e12
+        traffic, limiter = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            key = f"stack:{args.variant}:{args.operand}:{top}"
+            traffic = tj.get(key)          # DRAM bytes of all launches of this kernel in one step (ncu --set full)
+            limiter = tj.get("_limiter", {}).get(key)
         roofline = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16_sustained"], "traffic": None, "kernel": top,
+                    "frac": ach / pk["bf16_sustained"], "traffic": traffic, "measured_limiter": limiter, "kernel": top,
                     "avg_ms": tot_s * 1e3 / len(STACK_ORDER), "peak_source": pk["source"],
                     "algorithmic_bytes": work[role]["bytes"], "algorithmic_flops": work[role]["flops"],
                     "note": "sum over the 13 layers' launches of this kernel in one step"}

@@ -51,6 +51,7 @@ const Knobs& knobs() {
     v.bwd_gbuf1 = env_int("DCN_BWD_GBUF", 0) == 1;
     v.bwd_data_simt = env_int("DCN_BWD_DATA_SIMT", 0);
     v.conv_off = env_set("DCN_CONV_OFF");
+    v.gemm_off = env_set("DCN_GEMM_OFF");
     v.conv_small_c = env_set("DCN_CONV_SMALL_C");
     v.conv_debug = env_set("DCN_CONV_DEBUG");
     v.conv_wstream = env_set("DCN_CONV_WSTREAM");
@@ -149,6 +150,19 @@ static bool use_umma(const DcnShape* s, const Geo& g, int phase) {
   return umma_supported(g, s->operand, phase);
 }
 
+// Torch column layout with too few channels per sampling point for the fused kernels (dcn_gemm_path.cu):
+// materialised samples + plain GEMMs
+bool gemm_path_supported(const Geo& g, int operand);
+size_t gemm_path_workspace(const Geo& g, int operand, int phase);
+int gemm_path_forward(const Geo& g, int operand, const void* x, const float* off, const void* wt, const float* bias,
+                      float* out, void* workspace, cudaStream_t st);
+int gemm_path_backward(const Geo& g, int operand, int flags, const void* x, const float* off, const void* wt,
+                       const void* gout, float* gx, float* goff, float* gw, float* gb, void* workspace, cudaStream_t st);
+static bool use_gemm(const DcnShape* s, const Geo& g, int phase) {
+  if ((s->flags & DCN_FLAG_FORCE_SIMT) || (phase != DCN_PHASE_FORWARD && phase != DCN_PHASE_BACKWARD)) return false;
+  return !umma_supported(g, s->operand, phase) && gemm_path_supported(g, s->operand);
+}
+
 // whole-layer calls (offset conv + DCN span): fp32 operands on the tensor path only
 static bool layer_ok(const DcnShape* s, const Geo& g, int phase) {
   if ((s->flags & DCN_FLAG_FORCE_SIMT) || s->operand != DCN_OPERAND_FP32) return false;
@@ -204,6 +218,7 @@ size_t dcn_workspace_bytes(const DcnShape* s, int phase) {
   if (phase == DCN_PHASE_LAYER_FORWARD || phase == DCN_PHASE_LAYER_BACKWARD)
     return layer_ok(s, g, phase) ? layer_workspace(g, s->operand, phase) : 0;
   if (use_umma(s, g, phase)) return umma_workspace_bytes(g, s->operand, phase);
+  if (use_gemm(s, g, phase)) return gemm_path_workspace(g, s->operand, phase);
   return simt_workspace(g, s->operand, phase);
 }
 
@@ -212,7 +227,7 @@ const char* dcn_path_name(const DcnShape* s, int phase) {
   if (geo_or_error(s, &g)) return "invalid";
   if (phase == DCN_PHASE_LAYER_FORWARD || phase == DCN_PHASE_LAYER_BACKWARD)
     return layer_ok(s, g, phase) ? "umma" : "unsupported";
-  return use_umma(s, g, phase) ? "umma" : "simt";
+  return use_umma(s, g, phase) ? "umma" : (use_gemm(s, g, phase) ? "gemm" : "simt");
 }
 
 int dcn_profile_begin(void) {
@@ -285,6 +300,9 @@ int dcn_forward(const DcnShape* s, const void* x, const void* offset, const void
   if (use_umma(s, g, DCN_PHASE_FORWARD))
     return umma_forward(g, s->operand, s->flags, x, (const float*)offset, weight, (const float*)bias,
                         out, workspace, st);
+  if (use_gemm(s, g, DCN_PHASE_FORWARD))
+    return gemm_path_forward(g, s->operand, x, (const float*)offset, weight, (const float*)bias, (float*)out, workspace,
+                             st);
   Tap* plan = (Tap*)workspace;
   if (s->operand == DCN_OPERAND_BF16) {
     // shapes the tensor path does not tile: widen the bf16 operands once, run the fp32 kernels
@@ -322,6 +340,9 @@ int dcn_backward(const DcnShape* s, const void* x, const void* offset, const voi
     return umma_backward(g, s->operand, s->flags, x, (const float*)offset, weight, grad_out,
                          (float*)grad_x, (float*)grad_offset, (float*)grad_weight,
                          (float*)grad_bias, workspace, st);
+  if (use_gemm(s, g, DCN_PHASE_BACKWARD))
+    return gemm_path_backward(g, s->operand, s->flags, x, (const float*)offset, weight, grad_out, (float*)grad_x,
+                              (float*)grad_offset, (float*)grad_weight, (float*)grad_bias, workspace, st);
   Tap* plan = (Tap*)workspace;
   if (s->operand == DCN_OPERAND_BF16) {
     float* xf = (float*)((uint8_t*)workspace + plan_bytes(g));
