@@ -98,8 +98,9 @@ enum {
                                       dcn_layer_forward; sized for the largest phase used) and nothing has written
                                       to it since, so its head still holds the staged copy of x: skip re-staging.
                                       Honoured by dcn_forward, dcn_backward, dcn_offset_conv_forward and
-                                      dcn_layer_backward.  Only meaningful on the tensor path
-                                      (dcn_path_name == "umma"); ignored otherwise */
+                                      dcn_layer_backward.  Meaningful on the tensor path (dcn_path_name == "umma") and on
+                                      the materialised-sample path ("gemm": the sampling plan and the samples are kept
+                                      as well); ignored otherwise */
 };
 
 /* Problem description.  Constructor arguments of the reference modules
@@ -133,7 +134,8 @@ DCN_API int dcn_output_hw(const DcnShape* s, int32_t* h_out, int32_t* w_out);
 /* Bytes of caller-owned scratch the given phase needs (16-byte aligned). */
 DCN_API size_t dcn_workspace_bytes(const DcnShape* s, int phase);
 /* Name of the kernel family dcn_forward/dcn_backward will pick for this shape
- * ("umma" = tcgen05 implicit GEMM, "simt" = generic CUDA-core kernels). */
+ * ("umma" = fused tcgen05 implicit GEMM; "gemm" = Torch column layout whose gcd(Ho*Wo, C) is not a multiple of 16:
+ * samples materialised once, contractions as plain cuBLAS GEMMs; "simt" = generic CUDA-core kernels). */
 DCN_API const char* dcn_path_name(const DcnShape* s, int phase);
 /* Number of kernel launches issued by this library (all threads of the process) since the
  * last reset (bench.py's gpu_launches). */

@@ -154,8 +154,10 @@ __global__ void __launch_bounds__(256) sample_kernel(Geo g, const T* __restrict_
 // Backward of the sampling: gS[b, c, q] -> grad_x (red.global.add into the framed channels-last accumulator, 128-byte
 // coalesced) and grad_offset.  Every sampling point belongs to exactly one warp, which accumulates its coordinate
 // gradient over all channel tiles and writes grad_offset with plain stores.
+// (launch bounds: the fully unrolled version took 142 registers = ONE block per SM, 12 % occupancy, and sat in
+// long-scoreboard stalls on the corner loads: 1.53 ms for a C5 layer)
 template <typename T>
-__global__ void __launch_bounds__(256) scatter_kernel(Geo g, const T* __restrict__ xt, const Tap* __restrict__ plan,
+__global__ void __launch_bounds__(256, 4) scatter_kernel(Geo g, const T* __restrict__ xt, const Tap* __restrict__ plan,
                                                       const T* __restrict__ gS, float* __restrict__ gxt,
                                                       float* __restrict__ goff, float scale_iy, float scale_ix) {
   __shared__ float tile[kQT][kCT + 1];
@@ -282,11 +284,17 @@ static int gp_cublas_fail(cublasStatus_t st, const char* what) {
 }
 
 // stage x (identity channel order), plan, sample
+// staged = DCN_FLAG_XT_STAGED: the head of the workspace ([xt][plan][S], the same prefix in both phases) still holds
+// what the forward pass of this very call pair wrote — nothing to redo
 static int gp_stage_and_sample(const Geo& g, int operand, const void* x, const float* off, uint8_t* ws, cudaStream_t st,
-                               void** xt_out, Tap** plan_out, void** S_out) {
+                               void** xt_out, Tap** plan_out, void** S_out, bool staged = false) {
   void* xt = ws;
   Tap* plan = (Tap*)(ws + umma_xt_bytes(g, operand));
   void* S = (uint8_t*)plan + gp_plan_bytes(g);
+  *xt_out = xt;
+  *plan_out = plan;
+  *S_out = S;
+  if (staged) return DCN_OK;
   Tiling t;
   memset(&t, 0, sizeof(t));
   t.variant = DCN_VARIANT_JITTOR;   // identity channel order in the staged copy
@@ -303,9 +311,6 @@ static int gp_stage_and_sample(const Geo& g, int operand, const void* x, const f
       gp::sample_kernel<float><<<grid, 256, 0, st>>>(g, (const float*)xt, plan, (float*)S);
     DCN_KERNEL_CHECK("gemm_sample_kernel");
   }
-  *xt_out = xt;
-  *plan_out = plan;
-  *S_out = S;
   return DCN_OK;
 }
 
@@ -349,7 +354,7 @@ int gemm_path_backward(const Geo& g, int operand, int flags, const void* x, cons
   void *xt, *S;
   Tap* plan;
   int rc;
-  if ((rc = gp_stage_and_sample(g, operand, x, off, ws, st, &xt, &plan, &S))) return rc;
+  if ((rc = gp_stage_and_sample(g, operand, x, off, ws, st, &xt, &plan, &S, (flags & DCN_FLAG_XT_STAGED) != 0))) return rc;
   uint8_t* gS = (uint8_t*)S + gp_S_bytes(g, operand);
   float* gxt = (float*)(gS + gp_S_bytes(g, operand));
   uint8_t* goutT = (uint8_t*)gxt + umma_xt_bytes(g, DCN_OPERAND_FP32);

@@ -93,7 +93,8 @@ def staged_workspace(x, weight, kernel_size=3, stride=1, padding=1, variant=VARI
     (xt_staged=True) lets the backward pass reuse the staged copy of x (DCN_FLAG_XT_STAGED)."""
     lib = _lib.load()
     shp = _shape_of(x, weight, kernel_size, stride, padding, variant, operand, flags)
-    if any(_lib.path_name(shp, ph) != "umma" for ph in (PHASE_FORWARD, PHASE_BACKWARD)):
+    names = [_lib.path_name(shp, ph) for ph in (PHASE_FORWARD, PHASE_BACKWARD)]
+    if names not in (["umma", "umma"], ["gemm", "gemm"]):      # both keep the forward's staging at the workspace head
         return None
     need = max(lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_FORWARD),
                lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_BACKWARD))

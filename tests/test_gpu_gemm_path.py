@@ -130,3 +130,18 @@ def test_module_autograd_on_the_gemm_path():
     assert out.shape == (2, 48, 14, 14) and torch.isfinite(x.grad).all() and float(x.grad.abs().max()) > 0
     for p in m.parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all()
+
+
+def test_backward_reuses_the_forward_staging():
+    """DCN_FLAG_XT_STAGED on the gemm path: staged x, the sampling plan and the materialised samples of the forward pass
+    are reused by the backward pass (one scratch buffer for both phases)."""
+    from jittor_dcn_b200.functional import staged_workspace
+    sh, x, off, wt, bias, gout = _data(CASES[0], False)
+    tx, toff, twt, tb, tg = (torch.as_tensor(a).cuda() for a in (x, off, wt, bias, gout))
+    ws = staged_workspace(tx, twt, 3, 1, 1, dcn.VARIANT_TORCH)
+    assert ws is not None
+    out = dcn.dcn_forward(tx, toff, twt, tb, 3, 1, 1, dcn.VARIANT_TORCH, ws=ws)
+    staged = dcn.dcn_backward(tx, toff, twt, tg, True, 3, 1, 1, dcn.VARIANT_TORCH, ws=ws, xt_staged=True)
+    fresh = dcn.dcn_backward(tx, toff, twt, tg, True, 3, 1, 1, dcn.VARIANT_TORCH)
+    for a, b in zip(staged, fresh):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-6
