@@ -134,6 +134,15 @@ UMMA_LAYERS = {
 }
 
 
+# layer fixtures whose Torch-layout shapes run on the materialised-sample + GEMM path (csrc/dcn_gemm_path.cu,
+# dcn_path_name == "gemm": gcd(Ho*Wo, C) not a multiple of 16, C >= 32, O >= 32, K >= 256)
+GEMM_LAYERS = {
+    "gemm_a_c5like": (2, 64, 48, 14, 14, 3, 1, 1, 1.5, True),    # gcd(196, 64) = 4, the C5 situation
+    "gemm_b_gcd24":  (2, 96, 40, 10, 12, 3, 1, 1, 2.0, False),   # gcd(120, 96) = 24
+    "gemm_c_s2":     (2, 48, 32, 19, 21, 3, 2, 1, 1.0, True),    # stride 2: Ho*Wo = 110, gcd(110, 48) = 2
+}
+
+
 def make_layers(rng, layers=None):
     for name, (B, C, O, H, W, k, s, p, sigma, has_bias) in (layers or LAYERS).items():
         kh, kw = torch_chain._pair(k)
@@ -161,7 +170,7 @@ def make_layers(rng, layers=None):
         jar.update(out=out.numpy(), gx=grads[0].numpy(), goff=grads[1].numpy(), gw=grads[2].numpy())
         if has_bias:
             jar["gb"] = grads[3].numpy()
-        _save(name.replace("layer_", "jittor_").replace("umma_", "jittor_umma_"), **jar)
+        _save("jittor_" + (name[len("layer_"):] if name.startswith("layer_") else name), **jar)
 
 
 def make_module_golden():
@@ -329,6 +338,9 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     if "--only-module-umma" in sys.argv:
         make_module_umma_goldens()
+        return 0
+    if "--only-gemm" in sys.argv:
+        make_layers(np.random.default_rng(20261020), GEMM_LAYERS)   # own generator: added in round 2
         return 0
     make_layers(np.random.default_rng(20261019), UMMA_LAYERS)   # own generator: added in round 2
     make_module_umma_goldens()

@@ -96,13 +96,16 @@ def _paths(g, variant):
 
 
 @pytest.mark.parametrize("flags", FLAG_SETS)
-@pytest.mark.parametrize("name", golden_names("layer_") + golden_names("umma_"))
+@pytest.mark.parametrize("name", golden_names("layer_") + golden_names("umma_") + golden_names("gemm_"))
 def test_layer_against_reference_golden(name, flags):
     """Forward and all four gradients against the unmodified reference's own outputs.  The umma_* fixtures are the
-    ones whose shapes run on the tcgen05 kernels (both phases); the routing itself is asserted."""
+    ones whose shapes run on the tcgen05 kernels (both phases), the gemm_* ones on the materialised-sample + GEMM path
+    (Torch layout, gcd(Ho*Wo, C) not a multiple of 16); the routing itself is asserted."""
     g = golden(name)
     if name.startswith("umma_") and flags == 0:
         assert _paths(g, dcn.VARIANT_TORCH) == ["umma", "umma"]
+    if name.startswith("gemm_") and flags == 0:
+        assert _paths(g, dcn.VARIANT_TORCH) == ["gemm", "gemm"]
     out, gx, goff, gw, gb = _engine(g, dcn.VARIANT_TORCH, flags)
     assert rel_err(out.cpu().numpy(), g["out"]) < FWD_TOL
     assert rel_err(gx.cpu().numpy(), g["gx"]) < GRAD_TOL

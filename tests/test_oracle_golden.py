@@ -48,7 +48,7 @@ def test_roundtrip_wobble_bit_exact(S, n_low):
     assert ref_low == n_low
 
 
-@pytest.mark.parametrize("name", golden_names("layer_") + golden_names("umma_"))
+@pytest.mark.parametrize("name", golden_names("layer_") + golden_names("umma_") + golden_names("gemm_"))
 def test_c_oracle_matches_reference_layer(name):
     g = golden(name)
     s = shape_from_cfg(g["cfg"], orc.VARIANT_TORCH)
@@ -62,7 +62,7 @@ def test_c_oracle_matches_reference_layer(name):
         assert rel_err(gb, g["gb"]) < 5e-6
 
 
-@pytest.mark.parametrize("name", golden_names("layer_") + golden_names("umma_"))
+@pytest.mark.parametrize("name", golden_names("layer_") + golden_names("umma_") + golden_names("gemm_"))
 def test_torch_chain_is_bitwise_the_reference(name):
     """Same torch ops in the same order => identical bits (forward and autograd)."""
     g = golden(name)
