@@ -189,6 +189,24 @@ DCN_API int dcn_layer_backward(const DcnShape* s, const void* x, const void* off
                        void* grad_offset_bias, void* grad_weight, void* grad_bias, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* ---- chained inference: channels-last activations between consecutive engine layers ----------------
+ * dcn_layer_forward_chained is dcn_layer_forward whose epilogue writes the output DIRECTLY as the staged input of the
+ * consumer layer: the framed channels-last copy at the head of `consumer_workspace` (the layout dcn_layer_forward /
+ * dcn_forward would build from an NCHW tensor: [B][(Ho+3) x (Wo+2)][O] inside an all-zero frame, channels permuted
+ * for a Torch-layout consumer).  The consumer is then called with DCN_FLAG_XT_STAGED on that workspace (its `x`
+ * argument is not read), so no activation crosses the layer boundary in NCHW and no staging pass runs between the
+ * layers.  With DCN_FLAG_RELU_OUT and eval-mode BatchNorm folded into weight / bias this chains the whole
+ * relu(bn(conv(x))) stages of train.py:167-170.  Forward only (inference); fp32; both layers on the tensor path;
+ * consumer->C == s->O, consumer->H / W == this layer's output extent, O <= 256.
+ * The consumer's frame must be zero: dcn_staged_input_clear once after allocating its workspace is enough (the
+ * chained epilogue only ever writes interior pixels).  dcn_staged_input_bytes = size of that staged copy. */
+DCN_API size_t dcn_staged_input_bytes(const DcnShape* s);
+DCN_API int dcn_staged_input_clear(const DcnShape* s, void* workspace, void* stream);
+DCN_API int dcn_layer_forward_chained(const DcnShape* s, const DcnShape* consumer, const void* x,
+                                      const void* offset_weight, const void* offset_bias, const void* weight,
+                                      const void* bias, void* offset, void* consumer_workspace, void* workspace,
+                                      size_t workspace_bytes, void* stream);
+
 /* Sampling geometry only (bit-exactness probe): for every (b, n, h, w)
  *   y0,x0 [B,N,Ho,Wo] int32   floor'ed row / column of the north-west corner
  *   w4    [B,N,Ho,Wo,4] f32   corner weights nw, ne, sw, se (unmasked)                     */

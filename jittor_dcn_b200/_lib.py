@@ -34,6 +34,7 @@ EXPORTS = (
     "dcn_offset_conv_forward", "dcn_layer_forward", "dcn_layer_backward",
     "dcn_p2p_handle_bytes", "dcn_p2p_create", "dcn_p2p_local_handle", "dcn_p2p_connect",
     "dcn_p2p_allreduce_sum_f32", "dcn_p2p_destroy", "dcn_roi_pool_forward", "dcn_roi_pool_backward",
+    "dcn_staged_input_bytes", "dcn_staged_input_clear", "dcn_layer_forward_chained",
 )
 
 
@@ -96,6 +97,10 @@ def load():
     lib.dcn_bn_workspace_bytes.argtypes = [i32]
     lib.dcn_bn_relu_forward.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, sz, vp]
     lib.dcn_bn_relu_backward.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.dcn_staged_input_bytes.restype = sz
+    lib.dcn_staged_input_bytes.argtypes = [shp]
+    lib.dcn_staged_input_clear.argtypes = [shp, vp, vp]
+    lib.dcn_layer_forward_chained.argtypes = [shp, shp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.dcn_roi_pool_forward.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, f32, f32, i32, vp, vp]
     lib.dcn_roi_pool_backward.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, f32, f32, i32, vp, vp, vp, vp]
     _lib = lib

@@ -12,6 +12,7 @@
 
 #include "dcn_common.cuh"
 #include "dcn_umma.h"
+#include "dcn_umma_common.cuh"
 
 namespace dcn {
 
@@ -404,6 +405,72 @@ int dcn_layer_forward(const DcnShape* s, const void* x, const void* offset_weigh
     return rc;
   return umma_forward(g, s->operand, s->flags | DCN_FLAG_XT_STAGED, x, (const float*)offset, weight,
                       (const float*)bias, out, workspace, (cudaStream_t)stream);
+}
+
+// ---- chained inference: the producer's epilogue writes the consumer's staged input --------------------
+// Geo of the producer with out_framed set from the consumer's staging layout, or an error.
+static int chained_geo(const DcnShape* s, const DcnShape* consumer, Geo* g) {
+  int rc = geo_or_error(s, g);
+  if (rc) return rc;
+  Geo gc;
+  if ((rc = geo_or_error(consumer, &gc))) return rc;
+  if (s->operand != DCN_OPERAND_FP32 || consumer->operand != DCN_OPERAND_FP32 || g->O > 256 ||
+      gc.B != g->B || gc.C != g->O || gc.H != g->Ho || gc.W != g->Wo) {
+    set_error("chained forward: consumer must take this layer's output (B=%d C=%d H=%d W=%d, fp32, O <= 256); got "
+              "B=%d C=%d H=%d W=%d", g->B, g->O, g->Ho, g->Wo, gc.B, gc.C, gc.H, gc.W);
+    return DCN_ERR_BAD_SHAPE;
+  }
+  if (!use_umma(s, *g, DCN_PHASE_FORWARD) || !use_umma(consumer, gc, DCN_PHASE_FORWARD)) {
+    set_error("chained forward: both layers must run on the tensor path (dcn_path_name == \"umma\")");
+    return DCN_ERR_UNSUPPORTED;
+  }
+  Tiling tc;
+  if (!make_tiling(gc, &tc)) return DCN_ERR_UNSUPPORTED;
+  g->out_framed = 1;
+  g->out_G = gc.variant == DCN_VARIANT_TORCH ? tc.G : 0;
+  g->out_Cs = gc.variant == DCN_VARIANT_TORCH ? tc.Cs : 0;
+  return DCN_OK;
+}
+
+size_t dcn_staged_input_bytes(const DcnShape* s) {
+  Geo g;
+  if (geo_or_error(s, &g)) return 0;
+  return align_up(sizeof(float) * (size_t)g.B * xt_image_stride(g), 1024);
+}
+
+int dcn_staged_input_clear(const DcnShape* s, void* workspace, void* stream) {
+  Geo g;
+  int rc = geo_or_error(s, &g);
+  if (rc) return rc;
+  if ((rc = check_ptr(workspace, "workspace"))) return rc;
+  DCN_CUDA_TRY(cudaMemsetAsync(workspace, 0, dcn_staged_input_bytes(s), (cudaStream_t)stream));
+  return DCN_OK;
+}
+
+int dcn_layer_forward_chained(const DcnShape* s, const DcnShape* consumer, const void* x, const void* offset_weight,
+                              const void* offset_bias, const void* weight, const void* bias, void* offset,
+                              void* consumer_workspace, void* workspace, size_t workspace_bytes, void* stream) {
+  Geo g;
+  int rc = chained_geo(s, consumer, &g);
+  if (rc) return rc;
+  if ((rc = check_ptr(x, "x")) || (rc = check_ptr(offset_weight, "offset_weight")) ||
+      (rc = check_ptr(offset_bias, "offset_bias", false)) || (rc = check_ptr(weight, "weight")) ||
+      (rc = check_ptr(bias, "bias", false)) || (rc = check_ptr(offset, "offset")) ||
+      (rc = check_ptr(consumer_workspace, "consumer_workspace")) || (rc = check_ptr(workspace, "workspace")))
+    return rc;
+  if (!layer_ok(s, g, DCN_PHASE_LAYER_FORWARD)) {
+    set_error("chained layer forward: shape / operand / flags not supported (dcn_path_name(s, DCN_PHASE_LAYER_FORWARD))");
+    return DCN_ERR_UNSUPPORTED;
+  }
+  const size_t need = layer_workspace(g, s->operand, DCN_PHASE_LAYER_FORWARD);
+  if (workspace_bytes < need) {
+    set_error("chained layer forward workspace: have %zu bytes, need %zu", workspace_bytes, need);
+    return DCN_ERR_WORKSPACE;
+  }
+  if ((rc = dcn_offset_conv_forward(s, x, offset_weight, offset_bias, offset, workspace, workspace_bytes, stream)))
+    return rc;
+  return umma_forward(g, s->operand, s->flags | DCN_FLAG_XT_STAGED, x, (const float*)offset, weight,
+                      (const float*)bias, consumer_workspace, workspace, (cudaStream_t)stream);
 }
 
 int dcn_layer_backward(const DcnShape* s, const void* x, const void* offset, const void* offset_weight,

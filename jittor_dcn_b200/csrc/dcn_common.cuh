@@ -63,6 +63,11 @@ struct Geo {
   // DCN_FLAG_RELU_OUT: the forward epilogues store max(acc + bias, 0) (with eval-mode BatchNorm folded
   // into weight / bias by the caller this is the whole relu(bn(conv(x))) post-op of train.py:167-170 in the epilogue)
   int relu_out;
+  // Chained inference (dcn_layer_forward_chained): the forward epilogue writes `out` directly as the
+  // framed channels-last staging copy of the CONSUMER layer — [B][(Ho + 3) x (Wo + 2)][O], pixel (h, w) at frame
+  // position (h + 1, w + 1), channel o at out_G ? (o % out_Cs) * out_G + o / out_Cs : o (the consumer's Torch-layout
+  // permutation) — so that the consumer runs with DCN_FLAG_XT_STAGED and no activation crosses a layer boundary in NCHW
+  int out_framed, out_G, out_Cs;
 };
 
 __host__ __device__ __forceinline__ int off_row_ch(const Geo& g, int n) { return n * g.row_mul + g.row_add; }
@@ -102,6 +107,7 @@ __host__ inline int make_geo(const DcnShape* s, Geo* g) {
   g->o_valid = s->O;
   g->perm_G = g->perm_Cs = 0;
   g->relu_out = (s->flags & DCN_FLAG_RELU_OUT) ? 1 : 0;
+  g->out_framed = g->out_G = g->out_Cs = 0;
   g->N = s->kh * s->kw;
   g->Ho = (s->H + 2 * s->ph - s->kh) / s->sh + 1;
   g->Wo = (s->W + 2 * s->pw - s->kw) / s->sw + 1;

@@ -159,6 +159,7 @@ __host__ inline Geo plain_geo(const Geo& g, const Tiling& layer_tiling, bool pad
   p.variant = DCN_VARIANT_DCNV1;
   p.plain = 1;
   p.relu_out = 0;
+  p.out_framed = p.out_G = p.out_Cs = 0;
   p.o_valid = 2 * g.N;
   p.Oimg = 2 * g.N;
   p.O = pad_o ? (2 * g.N + 15) / 16 * 16 : 2 * g.N;

@@ -355,6 +355,26 @@ __global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_
           }
           if (P.n_ost == 2) ost ^= 1;
         }
+      } else if (!PLAIN && g.out_framed) {
+        // chained inference: this row's pixel of the CONSUMER's framed channels-last copy (Geo::out_framed)
+        const int bimg = (int)(out_off / ((size_t)g.Oimg * g.HW)), pix = (int)(out_off - (size_t)bimg * g.Oimg * g.HW);
+        uint32_t oh, ow;
+        t.divWo.divmod((uint32_t)(valid ? pix : 0), oh, ow);
+        float* dst = P.out + (((size_t)bimg * (g.Ho + 3) + oh + 1) * (g.Wo + 2) + ow + 1) * g.O;
+        for (int c0 = 0; c0 < O; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int o = c0 + i;
+              const float bv = P.bias ? __ldg(P.bias + o) : 0.f;
+              const float r = v[i] + bv;
+              const int od = g.out_G ? (o % g.out_Cs) * g.out_G + o / g.out_Cs : o;
+              dst[od] = g.relu_out ? fmaxf(r, 0.f) : r;
+            }
+          }
+        }
       } else {
         for (int c0 = 0; c0 < O; c0 += 16) {
           float v[16];
@@ -1042,7 +1062,7 @@ int umma_forward_any(const Geo& g, int operand, const void* x, const float* off,
   memset(&tmap, 0, sizeof(tmap));
   // (Rt = 2 only: with Rt >= 4 the direct stores already write 16-byte runs, and the staged path
   // measured slower there)
-  if (g.variant == DCN_VARIANT_TORCH && P.t.Rt == 2 && !knobs().fwd_no_tma_out) {
+  if (g.variant == DCN_VARIANT_TORCH && P.t.Rt == 2 && !knobs().fwd_no_tma_out && !g.out_framed) {
     const int box_r = P.t.Rt < 4 ? 4 : P.t.Rt;
     const size_t bytes = sizeof(float) * (size_t)g.O * P.t.Gt * box_r;
     if (P.t.R % box_r == 0 && bytes <= 64 * 1024 && g.O <= 256 &&

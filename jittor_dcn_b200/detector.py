@@ -44,6 +44,25 @@ class EDNetDetection(nn.Module):
         return self.fc_cls(feat), torch.sigmoid(self.fc_bbox(feat))
 
 
+def chained_eval_forward(model, x):
+    """Inference forward of an EDNetDetection with channels-last activations between its four DCN stages:
+    conv1 / bn1 / ReLU on the framework, then ONE layout pass into the engine, four chained `relu(bn(dcn(x)))` stages
+    (jittor_dcn_b200/chain.py) and one NCHW store for the heads.  Same result as `model.eval()(x)`."""
+    from .chain import ChainedDeformStages
+    if model.training:
+        raise ValueError("chained_eval_forward is inference only: call model.eval() first")
+    chain = getattr(model, "_chained_stages", None)
+    if chain is None:
+        chain = ChainedDeformStages([(getattr(model, f"conv{i}"), getattr(model, f"bn{i}")) for i, _, _ in _DCN_STAGES])
+        object.__setattr__(model, "_chained_stages", chain)     # not a sub-module: holds folded COPIES of the weights
+    with torch.no_grad():
+        act = (lambda t: t) if model.fused_bn_relu else model.relu
+        h = act(model.bn1(model.conv1(x)))
+        h = chain(h)
+        feat = model.gap(h).flatten(1)
+        return model.fc_cls(feat), torch.sigmoid(model.fc_bbox(feat))
+
+
 def detection_loss(cls_logits, bbox, labels, boxes):
     """CE + 5 * smooth-L1(beta=1), the recipe of train.py:195-199,247."""
     return nn.functional.cross_entropy(cls_logits, labels) + \
