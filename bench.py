@@ -105,6 +105,9 @@ def parse_args():
                          "launches) instead of the one-kernel peer-memory all-reduce inside the step's CUDA graph")
     ap.add_argument("--no-detector-dp", action="store_true",
                     help="default workload: skip the extra detector_dp measurement (BASELINE configs[4])")
+    ap.add_argument("--nchw-between-layers", action="store_true",
+                    help="detector workload: keep NCHW activations between the DCN layers (round-1 data flow) instead of the "
+                         "channels-last hand-over between every post-op and the next layer (SURVEY 8f.2)")
     ap.add_argument("--stock-bn", action="store_true",
                     help="detector workload: the framework's BatchNorm2d + ReLU instead of the engine's fused post-op")
     return ap.parse_args()
@@ -282,7 +285,8 @@ def measure_detector(args, world, rank, local_rank, dev, steps, warmup, want_e2e
     B = b1 - b0
     torch.manual_seed(0)                                   # replicated weights
     cls = dcn.TorchDeformConv2d if args.variant == "torch" else dcn.TorchDeformConv2dJittorSemantics
-    model = EDNetDetection(dcn_cls=cls, fused_bn_relu=not args.stock_bn).to(dev)
+    model = EDNetDetection(dcn_cls=cls, fused_bn_relu=not args.stock_bn,
+                           channels_last=not args.nchw_between_layers and not args.stock_bn).to(dev)
     with torch.no_grad():                                  # live offsets (the reference starts at zero)
         for m in model.modules():
             if isinstance(m, dcn.TorchDeformConv2d):
@@ -437,7 +441,10 @@ def run_detector(args):
                        "batch_per_gpu": r["batch_per_gpu"], "parallelism": f"dp{world}",
                        "launch": r["launch"],
                        "post_op": ("framework BatchNorm2d + ReLU (cuDNN)" if args.stock_bn else
-                                   "relu(bn(x)) on the engine (dcn_bn_relu_forward / _backward)"),
+                                   "relu(bn(x)) on the engine (dcn_bn_relu_forward / _backward)" if args.nchw_between_layers
+                                   else "relu(bn(x)) on the engine, writing the next DCN layer's staged channels-last input "
+                                        "and reading its channels-last grad_x (dcn_bn_relu_*_staged): no layout pass "
+                                        "between the layers"),
                        "allreduce": r["allreduce"],
                        "l2": "per-step activations (%.0f MB for conv2's input alone) exceed the 126 MB L2" %
                              (r["batch_per_gpu"] * 16 * 128 * 128 * 4 / 1e6)},

@@ -93,6 +93,11 @@ enum {
                                       producing kernel.  The backward entry points take grad_out with respect to
                                       the PRE-activation sum: the caller masks it with out > 0 (the Python autograd
                                       nodes do); the flag itself is ignored there */
+  DCN_FLAG_GRAD_X_FRAMED = 1 << 6, /* dcn_backward / dcn_layer_backward (tensor path): grad_x is NOT [B,C,H,W] but the framed
+                                      channels-last accumulator itself — [B][(H+3) x (W+2)][C] floats in the layer's
+                                      staging layout (dcn_staged_input_bytes) — overwritten; the post-op of the producer
+                                      layer reads it in that layout (dcn_bn_relu_backward_staged).  Excludes
+                                      DCN_FLAG_ACCUM_GRAD_X */
   DCN_FLAG_XT_STAGED = 1 << 4      /* the workspace is the very buffer a preceding call of this library for the
                                       same shape / operand was given (dcn_offset_conv_forward, dcn_forward or
                                       dcn_layer_forward; sized for the largest phase used) and nothing has written
@@ -206,6 +211,23 @@ DCN_API int dcn_layer_forward_chained(const DcnShape* s, const DcnShape* consume
                                       const void* offset_weight, const void* offset_bias, const void* weight,
                                       const void* bias, void* offset, void* consumer_workspace, void* workspace,
                                       size_t workspace_bytes, void* stream);
+
+/* ---- training: channels-last hand-over between a layer's post-op and the next layer -----------------
+ * dcn_bn_relu_forward_staged = dcn_bn_relu_forward whose normalise + ReLU pass writes its result DIRECTLY as the staged
+ * input of the consumer layer (the framed channels-last copy at the head of `consumer_workspace`, frame zeroed here) —
+ * the consumer then runs with DCN_FLAG_XT_STAGED; x [B,C,H,W] is the producer layer's NCHW output with
+ * B, C, H, W = consumer->B, C, H, W.  dcn_bn_relu_backward_staged takes the gradient in the same layout — the
+ * consumer's grad_x written with DCN_FLAG_GRAD_X_FRAMED — and returns grad_x [B,C,H,W] for the producer layer.
+ * Per layer boundary two passes over the activation disappear in each direction (bn_apply + staging transposition ->
+ * one kernel; un-staging transposition + bn_bwd_apply -> one kernel).  fp32; consumer on the tensor path.
+ * saved / workspace as for dcn_bn_relu_forward. */
+DCN_API int dcn_bn_relu_forward_staged(const DcnShape* consumer, int training, const void* x, const void* gamma,
+                                       const void* beta, void* running_mean, void* running_var, float momentum, float eps,
+                                       void* consumer_workspace, void* saved, void* workspace, size_t workspace_bytes,
+                                       void* stream);
+DCN_API int dcn_bn_relu_backward_staged(const DcnShape* consumer, int training, const void* x, const void* grad_staged,
+                                        const void* saved, void* grad_x, void* grad_gamma, void* grad_beta,
+                                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Sampling geometry only (bit-exactness probe): for every (b, n, h, w)
  *   y0,x0 [B,N,Ho,Wo] int32   floor'ed row / column of the north-west corner

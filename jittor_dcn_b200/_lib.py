@@ -20,6 +20,7 @@ FLAG_FORCE_SIMT = 1 << 1
 FLAG_NO_GRAD_X = 1 << 2
 FLAG_RELU_OUT = 1 << 3     # forward epilogue stores max(acc + bias, 0)
 FLAG_XT_STAGED = 1 << 4
+FLAG_GRAD_X_FRAMED = 1 << 6   # grad_x = the framed channels-last accumulator itself (training hand-over)
 PHASE_FORWARD, PHASE_BACKWARD, PHASE_CORNERS = 0, 1, 2
 PHASE_LAYER_FORWARD, PHASE_LAYER_BACKWARD = 3, 4   # offset conv + DCN span (dcn_layer_*)
 ROI_POOL, PSROI_POOL = 0, 1                        # dcn_roi_pool_* kind (deform_conv.py:83 / :160)
@@ -35,6 +36,7 @@ EXPORTS = (
     "dcn_p2p_handle_bytes", "dcn_p2p_create", "dcn_p2p_local_handle", "dcn_p2p_connect",
     "dcn_p2p_allreduce_sum_f32", "dcn_p2p_destroy", "dcn_roi_pool_forward", "dcn_roi_pool_backward",
     "dcn_staged_input_bytes", "dcn_staged_input_clear", "dcn_layer_forward_chained",
+    "dcn_bn_relu_forward_staged", "dcn_bn_relu_backward_staged",
 )
 
 
@@ -97,6 +99,8 @@ def load():
     lib.dcn_bn_workspace_bytes.argtypes = [i32]
     lib.dcn_bn_relu_forward.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, sz, vp]
     lib.dcn_bn_relu_backward.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.dcn_bn_relu_forward_staged.argtypes = [shp, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, sz, vp]
+    lib.dcn_bn_relu_backward_staged.argtypes = [shp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.dcn_staged_input_bytes.restype = sz
     lib.dcn_staged_input_bytes.argtypes = [shp]
     lib.dcn_staged_input_clear.argtypes = [shp, vp, vp]

@@ -132,6 +132,13 @@ static size_t simt_workspace(const Geo& g, int operand, int phase) {
 }
 
 size_t bn_workspace_bytes(int C);
+int bn_relu_forward_staged(const Geo& g, const Tiling& t, int training, const float* x, const float* gamma,
+                           const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                           float* xt, float* saved, void* workspace, cudaStream_t st);
+int bn_relu_backward_staged(const Geo& g, const Tiling& t, int training, const float* x, const float* gxt,
+                            const float* saved, float* grad_x, float* grad_gamma, float* grad_beta, void* workspace,
+                            cudaStream_t st);
+
 int bn_relu_forward(int B, int C, int HW, int training, const float* x, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, float momentum, float eps, float* y, float* saved,
                     void* workspace, cudaStream_t st);
@@ -471,6 +478,58 @@ int dcn_layer_forward_chained(const DcnShape* s, const DcnShape* consumer, const
     return rc;
   return umma_forward(g, s->operand, s->flags | DCN_FLAG_XT_STAGED, x, (const float*)offset, weight,
                       (const float*)bias, consumer_workspace, workspace, (cudaStream_t)stream);
+}
+
+static int staged_consumer(const DcnShape* consumer, Geo* g, Tiling* t) {
+  int rc = geo_or_error(consumer, g);
+  if (rc) return rc;
+  if (consumer->operand != DCN_OPERAND_FP32 || !use_umma(consumer, *g, DCN_PHASE_FORWARD) || !make_tiling(*g, t)) {
+    set_error("staged post-op: the consumer layer must run on the tensor path with fp32 operands");
+    return DCN_ERR_UNSUPPORTED;
+  }
+  return DCN_OK;
+}
+
+int dcn_bn_relu_forward_staged(const DcnShape* consumer, int training, const void* x, const void* gamma, const void* beta,
+                               void* running_mean, void* running_var, float momentum, float eps,
+                               void* consumer_workspace, void* saved, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  Geo g;
+  Tiling t;
+  int rc = staged_consumer(consumer, &g, &t);
+  if (rc) return rc;
+  if ((rc = check_ptr(x, "x")) || (rc = check_ptr(consumer_workspace, "consumer_workspace")) ||
+      (rc = check_ptr(saved, "saved")) || (rc = check_ptr(workspace, "workspace")))
+    return rc;
+  if (!training && (!running_mean || !running_var)) {
+    set_error("staged post-op: eval mode needs running_mean / running_var");
+    return DCN_ERR_NULL_POINTER;
+  }
+  if (workspace_bytes < bn_workspace_bytes(g.C)) {
+    set_error("staged post-op workspace: have %zu bytes, need %zu", workspace_bytes, bn_workspace_bytes(g.C));
+    return DCN_ERR_WORKSPACE;
+  }
+  return bn_relu_forward_staged(g, t, training, (const float*)x, (const float*)gamma, (const float*)beta,
+                                (float*)running_mean, (float*)running_var, momentum, eps, (float*)consumer_workspace,
+                                (float*)saved, workspace, (cudaStream_t)stream);
+}
+
+int dcn_bn_relu_backward_staged(const DcnShape* consumer, int training, const void* x, const void* grad_staged,
+                                const void* saved, void* grad_x, void* grad_gamma, void* grad_beta, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  Geo g;
+  Tiling t;
+  int rc = staged_consumer(consumer, &g, &t);
+  if (rc) return rc;
+  if ((rc = check_ptr(x, "x")) || (rc = check_ptr(grad_staged, "grad_staged")) || (rc = check_ptr(saved, "saved")) ||
+      (rc = check_ptr(grad_x, "grad_x", false)) || (rc = check_ptr(workspace, "workspace")))
+    return rc;
+  if (workspace_bytes < bn_workspace_bytes(g.C)) {
+    set_error("staged post-op workspace: have %zu bytes, need %zu", workspace_bytes, bn_workspace_bytes(g.C));
+    return DCN_ERR_WORKSPACE;
+  }
+  return bn_relu_backward_staged(g, t, training, (const float*)x, (const float*)grad_staged, (const float*)saved,
+                                 (float*)grad_x, (float*)grad_gamma, (float*)grad_beta, workspace, (cudaStream_t)stream);
 }
 
 int dcn_layer_backward(const DcnShape* s, const void* x, const void* offset, const void* offset_weight,

@@ -11,7 +11,7 @@
 //   backward  bn_bwd_reduce (read x, dy) -> bn_bwd_finalize -> bn_bwd_apply (read x, dy, write dx)  5 passes
 // ReLU is fused on both sides: the backward mask is recomputed from x with the SAME fmaf(x, scale, shift)
 // the forward pass evaluated, so y is never re-read and the mask is bit-identical.
-#include "dcn_common.cuh"
+#include "dcn_umma_common.cuh"
 
 namespace dcn {
 
@@ -337,6 +337,322 @@ int bn_relu_backward(int B, int C, int HW, int training, const float* x, const f
       bn_bwd_apply_kernel<false, true><<<grid, kThreads, 0, st>>>(n_items, C, HW, x, grad_y, scale, shift, save_mean,
                                                                 k1, k2, grad_x);
     DCN_KERNEL_CHECK("bn_bwd_apply_kernel");
+  }
+  return DCN_OK;
+}
+
+
+// ---- channels-last hand-over between stacked engine layers in TRAINING -----------------------------
+// The post-op sits between two DCN layers: its input is the producer's NCHW output (batch statistics need the complete
+// tensor), its output is only ever read by the consumer layer — as that layer's framed channels-last staging copy.
+// So the normalise + ReLU pass writes that copy directly (it IS the staging transposition, with the affine map applied
+// in registers), and the backward pass reads the consumer's channels-last grad_x accumulator directly (the un-staging
+// transposition with the BatchNorm backward applied in registers).  Per layer boundary this removes two passes over
+// the activation in each direction (bn_apply + nchw_to_nhwc -> one kernel; nhwc_to_nchw + bn_bwd_apply -> one kernel).
+namespace bn {
+
+__device__ __forceinline__ size_t frame_px_of(const Geo& g, const FastDiv& divW, int p) {
+  uint32_t y, xx;
+  divW.divmod((uint32_t)p, y, xx);
+  return (size_t)((y + 1) * (g.W + 2) + xx + 1) * g.C;
+}
+
+// Register tile of the transposing kernels: a thread owns 4 staged channels x 4 pixels.  Lanes: CGL along the channels
+// (4 channels each) x 32 / CGL along the pixels; CGL = 8 covers 32 channels per warp row, CGL = 4 is for 16-channel
+// tensors (the detector's first DCN layer), where the 8-lane layout would leave half of every warp idle.
+template <int CGL>
+struct TileMap {
+  static constexpr int kPixPerWarp = 4 * (32 / CGL), kPixPerBlock = 8 * kPixPerWarp, kChPerRow = 4 * CGL;
+  __device__ static int chan(int by, int lane) { return by * kChPerRow + (lane % CGL) * 4; }
+  __device__ static int pix(int tile, int warp, int lane) { return tile * kPixPerBlock + warp * kPixPerWarp + (lane / CGL) * 4; }
+};
+
+// xt[b, frame(p), perm(c)] = max(0, x[b, c, p] * scale[c] + shift[c]); tile structure of nchw_to_nhwc_kernel
+template <int CGL>
+__global__ void __launch_bounds__(256) bn_stage_kernel(Geo g, int variant, int G, int Cs, FastDiv divW,
+                                                       const float* __restrict__ x, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, float* __restrict__ xt) {
+  const int HWi = g.H * g.W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = TileMap<CGL>::chan(blockIdx.y, lane);            // destination (staged) channels d..d+3
+  const int p = TileMap<CGL>::pix(blockIdx.x, warp, lane);       // pixels p..p+3
+  if (d >= g.C || p >= HWi) return;
+  const int b = blockIdx.z;
+  const bool vec_ok = (HWi & 3) == 0;
+  float v[4][4];   // [channel][pixel]
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int dd = d + k;
+    const int c = variant == DCN_VARIANT_TORCH ? (dd % G) * Cs + dd / G : dd;   // source channel of staged channel dd
+    const float* src = x + ((size_t)b * g.C + c) * HWi + p;
+    const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+    if (vec_ok) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+      v[k][0] = t.x; v[k][1] = t.y; v[k][2] = t.z; v[k][3] = t.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[k][i] = p + i < HWi ? __ldg(src + i) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[k][i] = fmaxf(fmaf(v[k][i], sc, sh), 0.f);
+  }
+  float* img = xt + (size_t)b * xt_image_stride(g) + d;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (p + i >= HWi) break;
+    *reinterpret_cast<float4*>(img + frame_px_of(g, divW, p + i)) = make_float4(v[0][i], v[1][i], v[2][i], v[3][i]);
+  }
+}
+
+// sums[c] += {sum dyr, sum dyr * (x - mean[c])}, dyr = gxt[b, frame(p), perm(c)] * [fmaf(x, scale, shift) > 0].
+// Block (slice, channel row): walks its share of the (image, pixel block) tiles with the register tile of the
+// transposing kernels and reduces once at the end.
+template <int CGL>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_cl_kernel(Geo g, int variant, int G, int Cs, FastDiv divW, int pblocks,
+                                                               int tiles_per_slice, const float* __restrict__ x,
+                                                               const float* __restrict__ gxt,
+                                                               const float* __restrict__ scale,
+                                                               const float* __restrict__ shift,
+                                                               const float* __restrict__ mean,
+                                                               double* __restrict__ sums) {
+  __shared__ double red[8][CGL][4][2];
+  const int HWi = g.H * g.W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = TileMap<CGL>::chan(blockIdx.y, lane);
+  const bool live = d < g.C;
+  int c[4];
+  float sc[4], sh[4], mu[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int dd = live ? d + k : 0;
+    c[k] = variant == DCN_VARIANT_TORCH ? (dd % G) * Cs + dd / G : dd;
+    sc[k] = scale[c[k]];
+    sh[k] = shift[c[k]];
+    mu[k] = mean[c[k]];
+  }
+  const bool vec_ok = (HWi & 3) == 0;
+  double A[4] = {0, 0, 0, 0}, Q[4] = {0, 0, 0, 0};
+  float af[4] = {0.f, 0.f, 0.f, 0.f}, qf[4] = {0.f, 0.f, 0.f, 0.f};   // fp32 partial sums of <= 32 elements, then double
+  int pending = 0;
+  const int total = g.B * pblocks, t0 = blockIdx.x * tiles_per_slice, t1 = min(total, t0 + tiles_per_slice);
+  for (int tile = t0; tile < t1; ++tile) {
+    const int b = tile / pblocks, p = TileMap<CGL>::pix(tile - b * pblocks, warp, lane);
+    if (!live || p >= HWi) continue;
+    const float* img = gxt + (size_t)b * xt_image_stride(g) + d;
+    float gv[4][4];   // [pixel][channel]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p + i < HWi) t = __ldg(reinterpret_cast<const float4*>(img + frame_px_of(g, divW, p + i)));
+      gv[i][0] = t.x; gv[i][1] = t.y; gv[i][2] = t.z; gv[i][3] = t.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float* src = x + ((size_t)b * g.C + c[k]) * HWi + p;
+      float xv[4];
+      if (vec_ok) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+        xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[i] = p + i < HWi ? __ldg(src + i) : 0.f;
+      }
+      float a = 0.f, q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float gr = (p + i < HWi && fmaf(xv[i], sc[k], sh[k]) > 0.f) ? gv[i][k] : 0.f;
+        a += gr;
+        q += gr * (xv[i] - mu[k]);
+      }
+      af[k] += a;
+      qf[k] += q;
+    }
+    if (++pending == 8) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        A[k] += (double)af[k];
+        Q[k] += (double)qf[k];
+        af[k] = qf[k] = 0.f;
+      }
+      pending = 0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    A[k] += (double)af[k];
+    Q[k] += (double)qf[k];
+  }
+  // lanes with equal (lane % CGL) hold the same four channels
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int o = CGL; o < 32; o <<= 1) {
+      A[k] += __shfl_xor_sync(0xffffffffu, A[k], o);
+      Q[k] += __shfl_xor_sync(0xffffffffu, Q[k], o);
+    }
+  }
+  if (lane < CGL) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      red[warp][lane][k][0] = A[k];
+      red[warp][lane][k][1] = Q[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 * CGL) {
+    const int grp = threadIdx.x >> 2, k = threadIdx.x & 3;
+    double a = 0.0, q = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      a += red[w][grp][k][0];
+      q += red[w][grp][k][1];
+    }
+    const int dd = blockIdx.y * TileMap<CGL>::kChPerRow + grp * 4 + k;
+    if (dd < g.C) {
+      const int cc = variant == DCN_VARIANT_TORCH ? (dd % G) * Cs + dd / G : dd;
+      atomicAdd(sums + 2 * cc, a);
+      atomicAdd(sums + 2 * cc + 1, q);
+    }
+  }
+}
+
+// dx[b, c, p] = scale[c] * (dyr - k1[c] - (x - mean[c]) * k2[c]); tile structure of nhwc_to_nchw_kernel
+template <int CGL>
+__global__ void __launch_bounds__(256) bn_bwd_apply_cl_kernel(Geo g, int variant, int G, int Cs, FastDiv divW,
+                                                              const float* __restrict__ x, const float* __restrict__ gxt,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ shift,
+                                                              const float* __restrict__ mean, const float* __restrict__ k1,
+                                                              const float* __restrict__ k2, float* __restrict__ dx) {
+  const int HWi = g.H * g.W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = TileMap<CGL>::chan(blockIdx.y, lane);
+  const int p = TileMap<CGL>::pix(blockIdx.x, warp, lane);
+  if (d >= g.C || p >= HWi) return;
+  const int b = blockIdx.z;
+  const float* img = gxt + (size_t)b * xt_image_stride(g) + d;
+  float gv[4][4];   // [pixel][channel]
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p + i < HWi) t = __ldg(reinterpret_cast<const float4*>(img + frame_px_of(g, divW, p + i)));
+    gv[i][0] = t.x; gv[i][1] = t.y; gv[i][2] = t.z; gv[i][3] = t.w;
+  }
+  const bool vec_ok = (HWi & 3) == 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int dd = d + k;
+    const int c = variant == DCN_VARIANT_TORCH ? (dd % G) * Cs + dd / G : dd;
+    const float sc = __ldg(scale + c), sh = __ldg(shift + c), mu = __ldg(mean + c), a1 = __ldg(k1 + c), a2 = __ldg(k2 + c);
+    const size_t o = ((size_t)b * g.C + c) * HWi + p;
+    float xv[4], r[4];
+    if (vec_ok) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(x + o));
+      xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i] = p + i < HWi ? __ldg(x + o + i) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = sc * ((fmaf(xv[i], sc, sh) > 0.f ? gv[i][k] : 0.f) - a1 - (xv[i] - mu) * a2);
+    if (vec_ok) {
+      *reinterpret_cast<float4*>(dx + o) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (p + i < HWi) dx[o + i] = r[i];
+    }
+  }
+}
+
+}  // namespace bn
+
+// g = the CONSUMER layer's geometry (its input is this post-op's output), t = its staging layout
+int bn_relu_forward_staged(const Geo& g, const Tiling& t, int training, const float* x, const float* gamma,
+                           const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                           float* xt, float* saved, void* workspace, cudaStream_t st) {
+  using namespace bn;
+  const int B = g.B, C = g.C, HW = g.H * g.W;
+  const bool vec = (HW & 3) == 0;
+  float *save_mean = saved, *save_invstd = saved + C, *scale = saved + 2 * C, *shift = saved + 3 * C;
+  if (training) {
+    double* sums = (double*)workspace;
+    DCN_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)C, st));
+    int slices, bpb;
+    reduce_grid(B, C, &slices, &bpb);
+    {
+      KernelScope scope("bn_stats_kernel", st);
+      if (vec)
+        bn_reduce_kernel<0, true><<<dim3(C, slices), kThreads, 0, st>>>(B, C, HW, bpb, x, nullptr, nullptr, nullptr,
+                                                                     nullptr, sums);
+      else
+        bn_reduce_kernel<0, false><<<dim3(C, slices), kThreads, 0, st>>>(B, C, HW, bpb, x, nullptr, nullptr, nullptr,
+                                                                      nullptr, sums);
+      DCN_KERNEL_CHECK("bn_stats_kernel");
+    }
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, HW, x, (double)B * HW, sums, gamma, beta, eps, momentum,
+                                                      running_mean, running_var, save_mean, save_invstd, scale,
+                                                      shift);
+    DCN_KERNEL_CHECK("bn_finalize_kernel");
+  } else {
+    bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, running_mean, running_var, eps,
+                                                         save_mean, save_invstd, scale, shift);
+    DCN_KERNEL_CHECK("bn_eval_affine_kernel");
+  }
+  // frame of the staged copy (the workspace belongs to the caller: re-zeroed on every call, as the plain staging does)
+  int rc = launch_xt_frame_zero(g, xt, st);
+  if (rc) return rc;
+  KernelScope scope("bn_relu_stage_kernel", st);
+  if (C <= 16) {
+    const dim3 grid((HW + 255) / 256, (C + 15) / 16, B);
+    bn_stage_kernel<4><<<grid, 256, 0, st>>>(g, t.variant, t.G, t.Cs, FastDiv::make(g.W), x, scale, shift, xt);
+  } else {
+    const dim3 grid((HW + 127) / 128, (C + 31) / 32, B);
+    bn_stage_kernel<8><<<grid, 256, 0, st>>>(g, t.variant, t.G, t.Cs, FastDiv::make(g.W), x, scale, shift, xt);
+  }
+  DCN_KERNEL_CHECK("bn_relu_stage_kernel");
+  return DCN_OK;
+}
+
+int bn_relu_backward_staged(const Geo& g, const Tiling& t, int training, const float* x, const float* gxt,
+                            const float* saved, float* grad_x, float* grad_gamma, float* grad_beta, void* workspace,
+                            cudaStream_t st) {
+  using namespace bn;
+  const int B = g.B, C = g.C, HW = g.H * g.W;
+  const float *save_mean = saved, *save_invstd = saved + C, *scale = saved + 2 * C, *shift = saved + 3 * C;
+  double* sums = (double*)workspace;
+  float* k1 = (float*)(sums + 2 * (size_t)C);
+  float* k2 = k1 + C;
+  DCN_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)C, st));
+  const bool narrow = C <= 16;
+  const int pblocks = narrow ? (HW + 255) / 256 : (HW + 127) / 128, cgroups = narrow ? (C + 15) / 16 : (C + 31) / 32;
+  const int total = B * pblocks;
+  int slices = (148 * 8 + cgroups - 1) / cgroups;
+  if (slices > total) slices = total;
+  const int tps = (total + slices - 1) / slices;
+  slices = (total + tps - 1) / tps;
+  {
+    KernelScope scope("bn_bwd_reduce_kernel", st);
+    if (narrow)
+      bn_bwd_reduce_cl_kernel<4><<<dim3(slices, cgroups), 256, 0, st>>>(g, t.variant, t.G, t.Cs, FastDiv::make(g.W), pblocks,
+                                                                      tps, x, gxt, scale, shift, save_mean, sums);
+    else
+      bn_bwd_reduce_cl_kernel<8><<<dim3(slices, cgroups), 256, 0, st>>>(g, t.variant, t.G, t.Cs, FastDiv::make(g.W), pblocks,
+                                                                      tps, x, gxt, scale, shift, save_mean, sums);
+    DCN_KERNEL_CHECK("bn_bwd_reduce_kernel");
+  }
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, (double)B * HW, training, sums, save_invstd, grad_gamma,
+                                                        grad_beta, k1, k2);
+  DCN_KERNEL_CHECK("bn_bwd_finalize_kernel");
+  if (grad_x) {
+    KernelScope scope("bn_bwd_unstage_kernel", st);
+    const dim3 grid(pblocks, cgroups, B);
+    if (narrow)
+      bn_bwd_apply_cl_kernel<4><<<grid, 256, 0, st>>>(g, t.variant, t.G, t.Cs, FastDiv::make(g.W), x, gxt, scale, shift,
+                                                     save_mean, k1, k2, grad_x);
+    else
+      bn_bwd_apply_cl_kernel<8><<<grid, 256, 0, st>>>(g, t.variant, t.G, t.Cs, FastDiv::make(g.W), x, gxt, scale, shift,
+                                                     save_mean, k1, k2, grad_x);
+    DCN_KERNEL_CHECK("bn_bwd_unstage_kernel");
   }
   return DCN_OK;
 }

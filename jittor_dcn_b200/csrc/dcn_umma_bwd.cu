@@ -129,7 +129,10 @@ int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, cons
   const bool want_gx = !(flags & DCN_FLAG_NO_GRAD_X) && gx != nullptr;
   bool all_fused = true;
   if (operand != DCN_OPERAND_FP32 || use_umma_data(g0, operand)) {
-    float* gxt = (float*)rest;
+    // DCN_FLAG_GRAD_X_FRAMED: grad_x IS the framed channels-last accumulator (the producer-side post-op reads it in
+    // that layout, dcn_bn_relu_backward_staged): scatter straight into the caller's buffer, no transposition at the end
+    const bool gx_framed = (flags & DCN_FLAG_GRAD_X_FRAMED) != 0;
+    float* gxt = gx_framed ? gx : (float*)rest;
     uint8_t* wtiles = rest + umma_xt_bytes(g, DCN_OPERAND_FP32);
     uint8_t* gtiles = wtiles + umma_bwd_data_wtile_bytes(g0, operand);
     if (want_gx) DCN_CUDA_TRY(cudaMemsetAsync(gxt, 0, sizeof(float) * (size_t)g.B * xt_image_stride(g), st));
@@ -161,7 +164,7 @@ int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, cons
         return rc;
       if ((rc = launch_bias_grad(gp, goff, DCN_OPERAND_FP32, gboff, st))) return rc;
     }
-    if (want_gx && (rc = launch_nhwc_to_nchw_add(g, t, gxt, gx, (flags & DCN_FLAG_ACCUM_GRAD_X) ? 1 : 0, st)))
+    if (want_gx && !gx_framed && (rc = launch_nhwc_to_nchw_add(g, t, gxt, gx, (flags & DCN_FLAG_ACCUM_GRAD_X) ? 1 : 0, st)))
       return rc;
     if ((rc = launch_bias_grad(g, goutv, operand, gb, st))) return rc;
     if (all_fused) return DCN_OK;

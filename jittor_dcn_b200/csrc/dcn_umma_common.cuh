@@ -182,6 +182,7 @@ struct __align__(16) PlanEntry {
 // x / xt: float (DCN_OPERAND_FP32) or bfloat16 (DCN_OPERAND_BF16)
 // (the frame is re-zeroed on every call: the workspace belongs to the caller)
 int launch_nchw_to_nhwc(const Geo& g, const Tiling& t, const void* x, void* xt, int operand, cudaStream_t st);
+int launch_xt_frame_zero(const Geo& g, float* xt, cudaStream_t st);
 int launch_nhwc_to_nchw_add(const Geo& g, const Tiling& t, const float* gxt, float* gx, int accumulate,
                             cudaStream_t st);
 // weight images for the forward GEMM: per K block [hi: O x 64 K-major SW128][lo: same]

@@ -88,6 +88,16 @@ __global__ void __launch_bounds__(256) xt_frame_zero_kernel(Geo g, T* __restrict
   }
 }
 
+// zero the frame of a float staging copy (the interior is written by someone else: bn_relu_stage_kernel)
+int launch_xt_frame_zero(const Geo& g, float* xt, cudaStream_t st) {
+  KernelScope scope("xt_frame_zero_kernel", st);
+  const long long chunks = (long long)g.B * (3 * (g.W + 2) + 2 * g.H) * (g.C / 4);
+  const int blocks = (int)((chunks + 255) / 256 < 4096 ? (chunks + 255) / 256 : 4096);
+  xt_frame_zero_kernel<float><<<blocks, 256, 0, st>>>(g, xt);
+  DCN_KERNEL_CHECK("xt_frame_zero_kernel");
+  return DCN_OK;
+}
+
 int launch_nchw_to_nhwc(const Geo& g, const Tiling& t, const void* x, void* xt, int operand, cudaStream_t st) {
   const int HWi = g.H * g.W;
   dim3 grid((HWi + 127) / 128, (g.C + 31) / 32, g.B);

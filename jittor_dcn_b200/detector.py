@@ -14,8 +14,12 @@ _DCN_STAGES = ((2, 16, 32), (3, 32, 64), (4, 64, 128), (5, 128, 256))
 
 
 class EDNetDetection(nn.Module):
-    def __init__(self, num_classes=10, groups=2, dcn_cls=TorchDeformConv2d, fused_bn_relu=True):
+    def __init__(self, num_classes=10, groups=2, dcn_cls=TorchDeformConv2d, fused_bn_relu=True, channels_last=False):
         super().__init__()
+        # channels_last (needs fused_bn_relu): every relu(bn(x)) in front of a DCN layer writes that layer's staged
+        # channels-last input directly and takes its gradient in the same layout: no NCHW <-> channels-last
+        # transposition between the layers, in either direction
+        self.channels_last = bool(channels_last) and fused_bn_relu
         # fused_bn_relu: relu(bn(x)) as ONE engine op (BatchNormReLU2d, same state-dict keys as nn.BatchNorm2d);
         # False keeps the framework's BatchNorm2d + ReLU as the reference has them
         self.fused_bn_relu = fused_bn_relu
@@ -36,10 +40,25 @@ class EDNetDetection(nn.Module):
         self.fc_bbox = nn.Linear(256, 4)
 
     def forward(self, x):
+        if self.channels_last and x.is_cuda:
+            return self._forward_channels_last(x)
         act = (lambda t: t) if self.fused_bn_relu else self.relu
         x = act(self.bn1(self.conv1(x)))
         for idx, _, _ in _DCN_STAGES:
             x = act(getattr(self, f"bn{idx}")(getattr(self, f"conv{idx}")(x)))
+        feat = self.gap(x).flatten(1)
+        return self.fc_cls(feat), torch.sigmoid(self.fc_bbox(feat))
+
+    def _forward_channels_last(self, x):
+        raw = self.conv1(x)                                   # NCHW, framework conv
+        bn = self.bn1
+        for idx, _, _ in _DCN_STAGES:
+            layer = getattr(self, f"conv{idx}")
+            hw = raw.shape[2:]
+            xt = bn.forward_staged(raw, layer)                # relu(bn(raw)) -> the layer's staged channels-last input
+            raw = layer.forward_staged(xt, hw)                # offset conv + DCN span, NCHW out (batch statistics next)
+            bn = getattr(self, f"bn{idx}")
+        x = bn(raw)
         feat = self.gap(x).flatten(1)
         return self.fc_cls(feat), torch.sigmoid(self.fc_bbox(feat))
 

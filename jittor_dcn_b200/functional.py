@@ -461,3 +461,151 @@ class BatchNormReLUFunction(torch.autograd.Function):
 def batch_norm_relu(x, weight, bias, running_mean, running_var, training, momentum=0.1, eps=1e-5):
     """relu(F.batch_norm(x, running_mean, running_var, weight, bias, training, momentum, eps)) for NCHW float32."""
     return BatchNormReLUFunction.apply(x, weight, bias, running_mean, running_var, training, momentum, eps)
+
+
+# ---- training: channels-last hand-over between a layer's post-op and the next layer (SURVEY 8f.2) ----------------
+# The post-op writes the NEXT layer's staged input (framed channels-last copy at the head of that layer's workspace);
+# the tensor that travels between the two autograd nodes is a float32 view of that workspace head, and its gradient
+# is the consumer's channels-last grad_x accumulator (DCN_FLAG_GRAD_X_FRAMED) — nothing crosses the boundary in NCHW.
+def _framed_view(ws, B, H, W, C):
+    n = B * (H + 3) * (W + 2) * C
+    return ws[:4 * n].view(torch.float32).view(B, H + 3, W + 2, C)
+
+
+def _storage_tensor(t):
+    """uint8 tensor over the WHOLE storage `t` lives in (the workspace a staged tensor is the head of)."""
+    return torch.empty(0, dtype=torch.uint8, device=t.device).set_(t.untyped_storage())
+
+
+def _consumer_shape(x_shape, consumer):
+    out_channels, kernel_size, stride, padding, variant, flags = consumer
+    B, C, H, W = (int(v) for v in x_shape)
+    return _lib.make_shape(B, C, int(out_channels), H, W, kernel_size, stride, padding, variant, OPERAND_FP32, flags)
+
+
+class BatchNormReLUStagedFunction(torch.autograd.Function):
+    """relu(batch_norm(x)) whose result is written as the staged input of `consumer` (a DCN layer).  Returns the float32
+    view [B, H + 3, W + 2, C] of the consumer's workspace head."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, consumer):
+        lib = _lib.load()
+        x = _dev_ready(x)
+        B, C, H, W = x.shape
+        shp = _consumer_shape(x.shape, consumer)
+        need = max(lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_LAYER_FORWARD),
+                   lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_LAYER_BACKWARD))
+        if need == 0:
+            raise _lib.DcnError("staged post-op: the consumer layer does not run on the tensor path")
+        dev = x.device
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        saved = torch.empty(4 * C, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            bws = torch.empty(lib.dcn_bn_workspace_bytes(C), dtype=torch.uint8, device=dev)
+            rc = lib.dcn_bn_relu_forward_staged(ctypes.byref(shp), 1 if training else 0, _ptr(x), _ptr(weight), _ptr(bias),
+                                                _ptr(running_mean), _ptr(running_var), float(momentum), float(eps),
+                                                _ptr(ws), _ptr(saved), _ptr(bws), bws.numel(),
+                                                ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "dcn_bn_relu_forward_staged")
+        ctx.save_for_backward(x, saved)
+        ctx.consumer, ctx.training = consumer, bool(training)
+        ctx.has_affine = (weight is not None, bias is not None)
+        return _framed_view(ws, B, H, W, C)
+
+    @staticmethod
+    def backward(ctx, grad_staged):
+        lib = _lib.load()
+        x, saved = ctx.saved_tensors
+        C = x.shape[1]
+        dev = x.device
+        shp = _consumer_shape(x.shape, ctx.consumer)
+        g = _dev_ready(grad_staged)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gg = torch.empty(C, dtype=torch.float32, device=dev) if ctx.has_affine[0] else None
+        gb = torch.empty(C, dtype=torch.float32, device=dev) if ctx.has_affine[1] else None
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            bws = torch.empty(lib.dcn_bn_workspace_bytes(C), dtype=torch.uint8, device=dev)
+            rc = lib.dcn_bn_relu_backward_staged(ctypes.byref(shp), 1 if ctx.training else 0, _ptr(x), _ptr(g), _ptr(saved),
+                                                 _ptr(gx), _ptr(gg), _ptr(gb), _ptr(bws), bws.numel(),
+                                                 ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "dcn_bn_relu_backward_staged")
+        return gx, gg, gb, None, None, None, None, None, None
+
+
+def batch_norm_relu_staged(x, weight, bias, running_mean, running_var, training, momentum, eps, consumer):
+    """consumer = (out_channels, kernel_size, stride, padding, variant, flags) of the DCN layer that reads the result."""
+    return BatchNormReLUStagedFunction.apply(x, weight, bias, running_mean, running_var, training, momentum, eps, consumer)
+
+
+class DeformLayerFramedFunction(torch.autograd.Function):
+    """The whole layer (offset conv + DCN span) on an input that is ALREADY staged: `xt` is the view a staged post-op
+    returned (head of this layer's workspace).  Its gradient is returned in the same framed channels-last layout."""
+
+    @staticmethod
+    def forward(ctx, xt, offset_weight, offset_bias, weight, bias, cfg):
+        lib = _lib.load()
+        (C, H, W), kernel_size, stride, padding, variant, flags = cfg
+        B = int(xt.shape[0])
+        if tuple(xt.shape) != (B, H + 3, W + 2, C) or xt.dtype != torch.float32 or not xt.is_contiguous():
+            raise ValueError(f"staged input of shape {tuple(xt.shape)} does not match the layer input {(B, C, H, W)}")
+        ws = _storage_tensor(xt)
+        shp = _lib.make_shape(B, C, int(weight.shape[0]), H, W, kernel_size, stride, padding, variant, OPERAND_FP32,
+                              flags | FLAG_XT_STAGED)
+        need = max(lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_LAYER_FORWARD),
+                   lib.dcn_workspace_bytes(ctypes.byref(shp), PHASE_LAYER_BACKWARD))
+        if need == 0 or ws.numel() < need or xt.data_ptr() != ws.data_ptr():
+            raise _lib.DcnError("staged input is not the head of a workspace of this layer")
+        Ho, Wo = _lib.output_hw(shp)
+        N = shp.kh * shp.kw
+        dev = xt.device
+        weight, bias = _dev_ready(weight), _dev_ready(bias)
+        offset_weight, offset_bias = _dev_ready(offset_weight), _dev_ready(offset_bias)
+        offset = torch.empty((B, 2 * N, Ho, Wo), dtype=torch.float32, device=dev)
+        out = torch.empty((B, shp.O, Ho, Wo), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            rc = lib.dcn_layer_forward(ctypes.byref(shp), _ptr(ws), _ptr(offset_weight), _ptr(offset_bias), _ptr(weight),
+                                       _ptr(bias), _ptr(offset), _ptr(out), _ptr(ws), ws.numel(),
+                                       ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "dcn_layer_forward")
+        ctx.relu = bool(flags & FLAG_RELU_OUT)
+        ctx.save_for_backward(xt, offset, offset_weight, weight, *((out,) if ctx.relu else ()))
+        ctx.cfg = cfg
+        ctx.has = (offset_bias is not None, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        xt, offset, offset_weight, weight = ctx.saved_tensors[:4]
+        if ctx.relu:
+            grad_out = grad_out * (ctx.saved_tensors[4] > 0)
+        (C, H, W), kernel_size, stride, padding, variant, flags = ctx.cfg
+        B = int(xt.shape[0])
+        ws = _storage_tensor(xt)
+        need_gx = ctx.needs_input_grad[0]
+        fl = (flags & ~FLAG_ACCUM_GRAD_X) | FLAG_XT_STAGED | _lib.FLAG_GRAD_X_FRAMED | (0 if need_gx else FLAG_NO_GRAD_X)
+        shp = _lib.make_shape(B, C, int(weight.shape[0]), H, W, kernel_size, stride, padding, variant, OPERAND_FP32, fl)
+        dev = xt.device
+        grad_out = _dev_ready(grad_out)
+        gxt = torch.empty_like(xt) if need_gx else None
+        gwoff = torch.empty(offset_weight.shape, dtype=torch.float32, device=dev)
+        gboff = torch.empty((offset_weight.shape[0],), dtype=torch.float32, device=dev) if ctx.has[0] else None
+        gw = torch.empty(weight.shape, dtype=torch.float32, device=dev)
+        gb = torch.empty((shp.O,), dtype=torch.float32, device=dev) if ctx.has[1] else None
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            rc = lib.dcn_layer_backward(ctypes.byref(shp), _ptr(ws), _ptr(offset), _ptr(offset_weight), _ptr(weight),
+                                        _ptr(grad_out), _ptr(gxt), _ptr(gwoff), _ptr(gboff), _ptr(gw), _ptr(gb), _ptr(ws),
+                                        ws.numel(), ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "dcn_layer_backward")
+        return gxt, gwoff, gboff, gw, gb, None
+
+
+def deform_layer_framed(xt, in_chw, offset_weight, offset_bias, weight, bias=None, kernel_size=3, stride=1, padding=1,
+                        variant=VARIANT_TORCH, flags=0):
+    """Whole layer on a staged input (see batch_norm_relu_staged); in_chw = (C, H, W) of the layer's logical input."""
+    cfg = (tuple(int(v) for v in in_chw), _lib._pair(kernel_size), _lib._pair(stride), _lib._pair(padding), variant, flags)
+    return DeformLayerFramedFunction.apply(xt, offset_weight, offset_bias, weight, bias, cfg)

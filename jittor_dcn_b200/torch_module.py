@@ -12,7 +12,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import batch_norm_relu, deform_conv2d, deform_layer, layer_supported
+from .functional import (batch_norm_relu, batch_norm_relu_staged, deform_conv2d, deform_layer, deform_layer_framed,
+                         layer_supported)
 
 
 class TorchDeformConv2d(nn.Module):
@@ -65,6 +66,17 @@ class TorchDeformConv2d(nn.Module):
                              self.padding, self.variant, self.operand, self.engine_flags,
                              keep_staged=self.keep_staged_input and torch.is_grad_enabled())
 
+    def consumer_cfg(self):
+        """What a staged post-op needs to know about this layer to write its staged input."""
+        return (self.out_channels, self.kernel_size, self.stride, self.padding, self.variant, self.engine_flags)
+
+    def forward_staged(self, xt, in_hw):
+        """forward on an input that a staged post-op (BatchNormReLU2d.forward_staged) already wrote as this layer's
+        channels-last staging copy; in_hw = (H, W) of the logical input."""
+        return deform_layer_framed(xt, (self.in_channels, int(in_hw[0]), int(in_hw[1])), self.offset_conv.weight,
+                                   self.offset_conv.bias, self.weight, self.bias, self.kernel_size, self.stride,
+                                   self.padding, self.variant, self.engine_flags)
+
     def extra_repr(self):
         return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, "
                 f"stride={self.stride}, padding={self.padding}, bias={self.bias is not None}")
@@ -114,7 +126,25 @@ class BatchNormReLU2d(nn.BatchNorm2d):
             self.num_batches_tracked.add_(1)
             if self.momentum is None:
                 momentum = 1.0 / float(self.num_batches_tracked)
-        return batch_norm_relu(x, self.weight, self.bias,
-                               self.running_mean if self.track_running_stats else None,
-                               self.running_var if self.track_running_stats else None,
-                               use_batch_stats, momentum, self.eps)
+        return self._apply_op(x, use_batch_stats, momentum, None)
+
+    def forward_staged(self, x, consumer):
+        """relu(bn(x)) written directly as the staged channels-last input of `consumer` (a TorchDeformConv2d): returns
+        the tensor to hand to consumer.forward_staged (csrc/dcn_bn.cu: bn_stage_kernel)."""
+        if x.dim() != 4 or x.dtype != torch.float32 or not x.is_cuda:
+            raise ValueError("BatchNormReLU2d.forward_staged expects a float32 NCHW CUDA tensor")
+        use_batch_stats = self.training or not self.track_running_stats
+        momentum = 0.0 if self.momentum is None else self.momentum
+        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+            if self.momentum is None:
+                momentum = 1.0 / float(self.num_batches_tracked)
+        return self._apply_op(x, use_batch_stats, momentum, consumer.consumer_cfg())
+
+    def _apply_op(self, x, use_batch_stats, momentum, consumer_cfg):
+        rm = self.running_mean if self.track_running_stats else None
+        rv = self.running_var if self.track_running_stats else None
+        if consumer_cfg is not None:
+            return batch_norm_relu_staged(x, self.weight, self.bias, rm, rv, use_batch_stats, momentum, self.eps,
+                                          consumer_cfg)
+        return batch_norm_relu(x, self.weight, self.bias, rm, rv, use_batch_stats, momentum, self.eps)
