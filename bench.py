@@ -590,6 +590,72 @@ def run_stack(args):
     return 0
 
 
+def measure_other_configs(args, dev, variant):
+    """The other BASELINE configs next to the headline, so that the driver's default run sees them (N = 1 only):
+    configs[2] (cfg3: 256 -> 256 @ 28 x 28, batch 64, fp32) and configs[3] (the 13-layer ResNet-50 C3-C5 stack, batch 128,
+    bf16 operands), each fwd+bwd through the C ABI with inputs resident in HBM, W = 3 warm-up and K = 5 timed steps, an
+    L2 flush (512 MB write) before every timed step.  Compact: images/s, ms/step, the dominant kernel and its share."""
+    import torch
+    import jittor_dcn_b200 as dcn
+    from jittor_dcn_b200 import _lib
+    from jittor_dcn_b200.functional import staged_workspace
+    out = {}
+    stream = torch.cuda.current_stream(dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(4321)
+
+    def make(name, operand):
+        _, B, C, O, H, W, k, s, p = WORKLOADS[name]
+        act = torch.bfloat16 if operand == dcn.OPERAND_BF16 else torch.float32
+        shp = dcn.make_shape(B, C, O, H, W, k, s, p, variant, operand=operand)
+        Ho, Wo = _lib.output_hw(shp)
+        x = torch.randn(B, C, H, W, device=dev, generator=gen).to(act)
+        off = torch.randn(B, 2 * k * k, Ho, Wo, device=dev, generator=gen) * args.offset_sigma
+        wt = (torch.randn(O, C, k, k, device=dev, generator=gen) * (2.0 / (C * k * k)) ** 0.5).to(act)
+        bias = torch.randn(O, device=dev, generator=gen) * 0.1
+        gout = torch.randn(B, O, Ho, Wo, device=dev, generator=gen).to(act)
+        ws = staged_workspace(x, wt, k, s, p, variant, operand, 0)
+        return (x, off, wt, bias, gout, ws, (k, s, p), operand)
+
+    def run(layer):
+        x, off, wt, bias, gout, ws, (k, s, p), operand = layer
+        dcn.dcn_forward(x, off, wt, bias, k, s, p, variant, operand=operand, ws=ws)
+        dcn.dcn_backward(x, off, wt, gout, True, k, s, p, variant, operand=operand, ws=ws, xt_staged=ws is not None)
+
+    def timed(step, batch, label, steps=5, warmup=3):
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize(dev)
+        _lib.profile_begin()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            flush.fill_(1)
+            a.record(stream)
+            step()
+            b.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+        prof = _lib.profile_end()
+        top = max(prof, key=lambda n: prof[n][1]) if prof else None
+        return {"workload": label, "images_per_s": batch / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "warmup": warmup,
+                "l2": "flushed (512 MB write) before every timed step",
+                "top_kernel": top, "top_kernel_share": (prof[top][1] / steps / ms) if top else None,
+                "kernel_ms_per_step": {n: v[1] / steps for n, v in prof.items() if v[1] / steps >= 0.05}}
+
+    cfg3 = make("cfg3", dcn.OPERAND_FP32)
+    out["cfg3"] = timed(lambda: run(cfg3), WORKLOADS["cfg3"][1], "cfg3: " + WORKLOADS["cfg3"][0] + ", fp32, variant " + args.variant)
+    del cfg3
+    layers = {n: make(n, dcn.OPERAND_BF16) for n in sorted(set(STACK_ORDER))}
+
+    def stack_step():
+        for n in STACK_ORDER:
+            run(layers[n])
+    out["stack_bf16"] = timed(stack_step, WORKLOADS["c3"][1], STACK_DESC + ", bf16 operands, variant " + args.variant)
+    del layers, flush
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     args = parse_args()
     claim_stdout()
@@ -891,6 +957,12 @@ def main():
                            "steps": 10, "warmup": 3}
         except Exception as e:  # noqa: BLE001 - the headline line must still be printed
             detector_dp = {"error": f"{type(e).__name__}: {e}"[:300]}
+    other_configs = None
+    if args.workload == "cfg2" and world == 1 and not args.no_detector_dp:
+        try:
+            other_configs = measure_other_configs(args, dev, variant)
+        except Exception as e:  # noqa: BLE001
+            other_configs = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
         line = {
@@ -910,7 +982,7 @@ def main():
                        "l2": l2_note, "staging": staging_note,
                        "allreduce": allreduce_kind, "parallelism": f"dp{world}"},
             "roofline": roofline, "kernels": kernels, "fwd_only": fwd_only, "cpu_baseline": cpu, "e2e": e2e,
-            "detector_dp": detector_dp, "gpu_launches": launches, "clocks": clocks,
+            "detector_dp": detector_dp, "other_configs": other_configs, "gpu_launches": launches, "clocks": clocks,
         }
         emit(line)
     if comm is not None:
