@@ -44,7 +44,7 @@ struct CublasApi {
 };
 static CublasApi g_api;
 static std::once_flag g_once;
-static std::mutex g_mu;
+static std::mutex g_mu, g_use_mu;
 static cublasHandle_t g_handles[64] = {};
 
 static bool load_cublas() {
@@ -333,6 +333,7 @@ int gemm_path_forward(const Geo& g, int operand, const void* x, const float* off
   const cudaDataType dt = operand == DCN_OPERAND_BF16 ? CUDA_R_16BF : CUDA_R_32F;
   const float one = 1.f;
   cublasStatus_t cs;
+  std::lock_guard<std::mutex> use(gp::g_use_mu);   // a cuBLAS handle must not be driven by two host threads at once
   if ((cs = gp::g_api.SetStream(h, st)) != CUBLAS_STATUS_SUCCESS) return gp_cublas_fail(cs, "cublasSetStream");
   if (gp::g_api.SetWorkspace) gp::g_api.SetWorkspace(h, cws, gp::kCublasWs);
   // row-major out_b[O, HW] += Wm[O, K] * A_b^T  <=>  column-major C'[HW, O] = op_T(A'[K, HW]) * B'[K, O]
@@ -363,6 +364,7 @@ int gemm_path_backward(const Geo& g, int operand, int flags, const void* x, cons
   const cudaDataType dt = operand == DCN_OPERAND_BF16 ? CUDA_R_16BF : CUDA_R_32F;
   const float one = 1.f, zero = 0.f;
   cublasStatus_t cs;
+  std::lock_guard<std::mutex> use(gp::g_use_mu);   // see gemm_path_forward
   if ((cs = gp::g_api.SetStream(h, st)) != CUBLAS_STATUS_SUCCESS) return gp_cublas_fail(cs, "cublasSetStream");
   if (gp::g_api.SetWorkspace) gp::g_api.SetWorkspace(h, cws, gp::kCublasWs);
   // row-major gS_b[HW, K] = gout_b^T[HW, O] * Wm[O, K]  <=>  column-major C'[K, HW] = B'[K, O] * op_T(gout'[HW, O])
