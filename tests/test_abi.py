@@ -181,3 +181,36 @@ def test_bn_relu_module_keeps_the_batchnorm_interface():
         ours(torch.zeros(1, 16, 1, 1))
     with pytest.raises(ValueError):
         ours(torch.zeros(2, 16, 4))
+
+
+def test_round2_entry_points_validate_their_arguments_without_a_gpu():
+    """Chained / staged / RoI entry points refuse bad descriptions before touching CUDA."""
+    lib = dcn.load()
+    buf = ctypes.create_string_buffer(1 << 12)
+    ok = ctypes.c_void_p((ctypes.addressof(buf) + 255) // 256 * 256)
+    f = ctypes.c_float
+    prod = dcn.make_shape(2, 16, 32, 32, 32, 3, 2, 1, dcn.VARIANT_TORCH)           # -> [2, 32, 16, 16]
+    good = dcn.make_shape(2, 32, 64, 16, 16, 3, 2, 1, dcn.VARIANT_TORCH)
+    bad = dcn.make_shape(2, 32, 64, 20, 16, 3, 2, 1, dcn.VARIANT_TORCH)            # wrong input extent
+    assert lib.dcn_staged_input_bytes(ctypes.byref(good)) >= 2 * (16 + 3) * (16 + 2) * 32 * 4
+    rc = lib.dcn_layer_forward_chained(ctypes.byref(prod), ctypes.byref(bad), ok, ok, ok, ok, ok, ok, ok, ok, 1 << 30, None)
+    assert rc == -1 and b"consumer" in lib.dcn_last_error()
+    rc = lib.dcn_layer_forward_chained(ctypes.byref(prod), ctypes.byref(good), None, ok, ok, ok, ok, ok, ok, ok, 1 << 30, None)
+    assert rc == -2                                                               # x is NULL
+    rc = lib.dcn_layer_forward_chained(ctypes.byref(prod), ctypes.byref(good), ok, ok, ok, ok, ok, ok, ok, ok, 16, None)
+    assert rc == -4                                                               # workspace too small
+    odd = dcn.make_shape(2, 5, 7, 9, 13, 3, 1, 1, dcn.VARIANT_TORCH)               # consumer on the generic kernels
+    rc = lib.dcn_bn_relu_forward_staged(ctypes.byref(odd), 1, ok, ok, ok, ok, ok, f(0.1), f(1e-5), ok, ok, ok, 1 << 20, None)
+    assert rc == -6
+    rc = lib.dcn_bn_relu_backward_staged(ctypes.byref(good), 1, ok, None, ok, ok, ok, ok, ok, 1 << 20, None)
+    assert rc == -2
+    assert lib.dcn_roi_pool_forward(7, 1, 4, 8, 8, 2, ok, ok, ok, f(1.0), f(0.1), 0, ok, None) == -1
+    assert lib.dcn_roi_pool_forward(0, 1, 4, 8, 8, 2, None, ok, ok, f(1.0), f(0.1), 0, ok, None) == -2
+    assert lib.dcn_roi_pool_forward(0, 1, 4, 8, 8, 0, ok, ok, ok, f(1.0), f(0.1), 0, ok, None) == 0       # no rois: nothing to do
+    for cls in (dcn.DeformRoIPool, dcn.DeformPSRoIPool):
+        with pytest.raises(ValueError):
+            cls(7)
+    # path names of the three kernel families
+    for shape, name in (((256, 64, 64, 128, 128), b"umma"), ((128, 512, 512, 14, 14), b"gemm"), ((3, 5, 7, 9, 13), b"simt")):
+        s = dcn.make_shape(*shape, 3, 1, 1, dcn.VARIANT_TORCH)
+        assert lib.dcn_path_name(ctypes.byref(s), 0) == name and lib.dcn_path_name(ctypes.byref(s), 1) == name
