@@ -4,7 +4,7 @@
 //                 consumed in place by the bilinear col2im scatter (red.global.add.f32 into a
 //                 channels-last grad copy) and the warp-shuffle coordinate-gradient reduction
 //                 (both column layouts; shapes it cannot tile use dcn_simt.cu:bwd_data_kernel).
-//   grad_weight   Torch layout, O <= 128: FUSED into the kernel above — its scatter warps already
+//   grad_weight   Torch layout, O <= 128 (bf16 operands: O <= 256): FUSED into the kernel above — its scatter warps already
 //                 hold every sample's four corner values, so they also emit the blended sample as
 //                 a bf16 hi/lo operand and a second TMEM accumulator set collects gW = gout^T * S:
 //                 the whole backward touches x once.  Otherwise dcn_umma_fwd.cu (MODE_WGRAD):

@@ -84,10 +84,12 @@ struct Params {
   int cblocks;           // blocks per tile: Torch ceil(K / ncols) column blocks, Jittor ceil(K / 128) lane blocks
   int OB;                // ceil(O / 64) K blocks of the GEMM
   int plan_cap;          // entries per plan buffer = Rt * ncols
-  // fused weight gradient (Torch layout, O <= 128): the scatter warps also form the blended
+  // fused weight gradient (Torch layout, O <= 256 while the grad_out tile fits): the scatter warps also form the blended
   // sample S = sum_k w_k v_k they already hold the corners of, store it as a bf16 hi/lo B
   // operand, and a second accumulator set collects gW[o, j] += g^T S over all tiles of the CTA
   int fuse_w;            // 0 / 1
+  int o_halves;          // Torch layout, fused: 128-channel halves of the o axis (1, or 2 when 128 < O <= 256), one gW
+                         // accumulator set per half
   int o_cols;            // Jittor layout, fused: TMEM columns of one gW accumulator block = O rounded up to 16
   float* gw;             // [O, K], zeroed
   int nslices, nchunks, cb_per_slice;  // CTA = (slice of column blocks, chunk of tiles)
@@ -590,22 +592,24 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
       mbar_wait_relaxed(dfull, 0);
       tc_fence_after();
       if (VARIANT == DCN_VARIANT_TORCH) {
-        const int o = quarter * 32 + lane;
         const int wcols = (cb1 - cb0) * ncols, per_part = (wcols + 3) >> 2;
-        const uint32_t taddr = d2_base + ((uint32_t)(quarter * 32) << 16);
-        for (int c0 = part * per_part; c0 < min(wcols, (part + 1) * per_part); c0 += 8) {
-          uint32_t raw[8];
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                       : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]), "=r"(raw[4]), "=r"(raw[5]),
-                         "=r"(raw[6]), "=r"(raw[7])
-                       : "r"(taddr + c0)
-                       : "memory");
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (o < g.O) {
+        for (int hf = 0; hf < P.o_halves; ++hf) {
+          const int o = hf * 128 + quarter * 32 + lane;
+          const uint32_t taddr = d2_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(hf * P.cb_per_slice * ncols);
+          for (int c0 = part * per_part; c0 < min(wcols, (part + 1) * per_part); c0 += 8) {
+            uint32_t raw[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]), "=r"(raw[4]), "=r"(raw[5]),
+                           "=r"(raw[6]), "=r"(raw[7])
+                         : "r"(taddr + c0)
+                         : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (o < g.O) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int j = cb0 * ncols + c0 + u;
-              if (j < g.K) atomicAdd(P.gw + (size_t)o * g.K + j, __uint_as_float(raw[u]));
+              for (int u = 0; u < 8; ++u) {
+                const int j = cb0 * ncols + c0 + u;
+                if (j < g.K) atomicAdd(P.gw + (size_t)o * g.K + j, __uint_as_float(raw[u]));
+              }
             }
           }
         }
@@ -656,20 +660,27 @@ __global__ void __launch_bounds__(threads_of(PW), 1) bwd_data_kernel(const __gri
           // gW[o, cols of block] += g^T[o, 128 rows] * S[128 rows, cols]: A = the resident grad_out images read
           // MN-major (o contiguous; 64-o atoms = this buffer's image, then its second image or — O <= 64 — the
           // shared zero image), B = sample operand read MN-major
-          const uint32_t g_lbo = P.OB >= 2 ? NIMG * P.g_img : g_zero_off - (uint32_t)gb * g_buf;
-          const uint32_t d_tmem = d2_base + (uint32_t)((cb - cb0) * ncols);
-          const uint64_t dg0 = make_sdesc_sw128(g_hi, g_lbo, 1024), ds0 = make_sdesc_sw128(sbase, 1024, 1024);
+          // (128 < O <= 256: a second pass over images 2, 3 into the second accumulator set)
+          const uint64_t ds0 = make_sdesc_sw128(sbase, 1024, 1024);
           const uint32_t gimg16 = P.g_img >> 4;
-          if (elect_one()) {
+          for (int hf = 0; hf < P.o_halves; ++hf) {
+            const uint32_t g_h = g_hi + (uint32_t)(2 * hf) * NIMG * P.g_img;
+            const uint32_t g_lbo = 2 * hf + 1 < P.OB ? NIMG * P.g_img
+                                                     : g_zero_off - (uint32_t)gb * g_buf - (uint32_t)(2 * hf) * NIMG * P.g_img;
+            const uint32_t d_tmem = d2_base + (uint32_t)((hf * P.cb_per_slice + cb - cb0) * ncols);
+            const uint64_t dg0 = make_sdesc_sw128(g_h, g_lbo, 1024);
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {  // 8 steps of 16 tile rows
-              const uint64_t dgh = dg0 + (uint64_t)(ks * 128), dsh = ds0 + (uint64_t)(ks * 128);
-              umma_bf16(d_tmem, dgh, dsh, idesc_w, (first && ks == 0) ? 0u : 1u);
-              if (!BF) {
-                umma_bf16(d_tmem, dgh, dsh + (s_img >> 4), idesc_w, 1u);
-                umma_bf16(d_tmem, dgh + gimg16, dsh, idesc_w, 1u);
+              for (int ks = 0; ks < 8; ++ks) {  // 8 steps of 16 tile rows
+                const uint64_t dgh = dg0 + (uint64_t)(ks * 128), dsh = ds0 + (uint64_t)(ks * 128);
+                umma_bf16(d_tmem, dgh, dsh, idesc_w, (first && ks == 0) ? 0u : 1u);
+                if (!BF) {
+                  umma_bf16(d_tmem, dgh, dsh + (s_img >> 4), idesc_w, 1u);
+                  umma_bf16(d_tmem, dgh + gimg16, dsh, idesc_w, 1u);
+                }
               }
             }
+            __syncwarp();
           }
         } else {
           // Jittor layout: gW^T[j of this lane block, o] += S^T[j, pixels] * g[pixels, o]: A = the sample operand,
@@ -1058,6 +1069,7 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
   const size_t nimg = operand == DCN_OPERAND_BF16 ? 1 : 2;
   if (!make_tiling(g, &P->t)) return false;
   P->fuse_w = 0;
+  P->o_halves = 1;
   P->w_resident = 0;
   P->w_ring = 2;
   P->g_nbuf = 1;
@@ -1085,22 +1097,24 @@ static bool bwd_data_tiling(const Geo& g, int operand, bd::Params* P, bool allow
     P->divChunks = FastDiv::make(P->chunks);
     P->g_imgs = P->OB;
     // fused weight gradient: 64-column blocks, <= 6 blocks of gW accumulators next to the 2 gA buffers
-    if (allow_fuse && g.O <= 128) {
+    if (allow_fuse && g.O <= 256) {
       const int ncols = 64;
+      const int halves = g.O > 128 ? 2 : 1;  // the gW MMAs take 128 channels (two 64-o images) at a time
       const size_t plan = 2 * (size_t)P->Rt * ncols * sizeof(bd::ScatEntry);
       const size_t rest = 2 * (size_t)(nimg * ncols * 128) + 2 * nimg * (size_t)(128 * 128) + plan + 256 + 1024;
-      const size_t zero = (size_t)(2 - P->OB) * nimg * bd::kGImg, real = (size_t)P->OB * nimg * bd::kGImg;
+      const size_t zero = (size_t)(2 * halves - P->OB) * nimg * bd::kGImg, real = (size_t)P->OB * nimg * bd::kGImg;
       if (P->Rt * ncols <= bd::plan_max_of(4) && real + zero + rest <= 227 * 1024) {
         P->fuse_w = 1;
-        P->g_imgs = 2;
+        P->o_halves = halves;
+        P->g_imgs = 2 * halves;
         P->ncols = ncols;
         P->cblocks = (g.K + ncols - 1) / ncols;
         P->plan_cap = P->Rt * ncols;
         P->g_img = bd::kGImg;
         P->w_stage = (uint32_t)nimg * ncols * 128;
         P->tmem_cols = 512;
-        int max_cb = 6;  // 512 TMEM columns - 2 gA buffers
-        max_cb = knobs().bwd_slice_cb < 1 ? 1 : (knobs().bwd_slice_cb > 6 ? 6 : knobs().bwd_slice_cb);
+        const int cap_cb = 6 / halves;  // 512 TMEM columns - 2 gA buffers, one accumulator set per half
+        const int max_cb = knobs().bwd_slice_cb < 1 ? 1 : (knobs().bwd_slice_cb > cap_cb ? cap_cb : knobs().bwd_slice_cb);
         choose_slices(P, max_cb, real, zero, rest - 2 * (size_t)P->w_stage);
         return true;
       }

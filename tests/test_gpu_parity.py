@@ -293,6 +293,12 @@ BF16_CASES = [
     (2, 16, 32, 32, 32, 3, 2, 1, 1.0),
     (2, 64, 128, 12, 20, 3, 1, 1, 2.0),
     (1, 128, 128, 16, 16, 3, 1, 1, 1.0),
+    # 128 < O <= 256: Torch layout fuses the weight gradient over two 128-channel halves (O = 192: the second
+    # half's upper image is the shared zero image; O = 160: a partly filled image)
+    (2, 64, 256, 16, 16, 3, 1, 1, 1.5),
+    (3, 64, 192, 16, 16, 3, 1, 1, 1.5),
+    (2, 32, 160, 16, 24, 3, 1, 1, 2.0),
+    (1, 256, 256, 16, 16, 3, 1, 1, 1.0),
 ]
 
 
