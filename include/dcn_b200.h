@@ -253,6 +253,17 @@ DCN_API int dcn_roi_pool_backward(int kind, int B, int C, int H, int W, int R, c
                                   const void* offsets, float spatial_scale, float trans_std, int no_trans,
                                   const void* grad_out, void* grad_features, void* grad_offsets, void* stream);
 
+/* ---- producer of the first DCN layer's input (train.py:145,166 / 307,328: conv1 = Conv2d(1, 16, 3, 1, 1)) ------------
+ * A 3 x 3, stride 1, padding 1 convolution with Cin <= 4 input channels and O in {16, 32} outputs, float32 NCHW,
+ * W % 4 == 0 (anything else: DCN_ERR_UNSUPPORTED, the caller keeps the framework's conv).  The framework's kernels for
+ * this layer were 4.7 ms of the 24 ms detector step at batch 1024; these are two streaming kernels at the HBM floor.
+ *   x [B,Cin,H,W]   weight [O,Cin,3,3]   bias [O] or NULL   out [B,O,H,W]
+ * Backward: grad_weight [O,Cin,3,3] and grad_bias [O] are overwritten; there is no input gradient (network input). */
+DCN_API int dcn_stem_conv_forward(int B, int Cin, int O, int H, int W, const void* x, const void* weight,
+                                  const void* bias, void* out, void* stream);
+DCN_API int dcn_stem_conv_backward(int B, int Cin, int O, int H, int W, const void* x, const void* grad_out,
+                                   void* grad_weight, void* grad_bias, void* stream);
+
 /* ---- post-op: BatchNorm2d + ReLU ------------------------------------------
  * Replaces `relu(bn(x))` after every DeformConv2d layer of the reference's detector (modules
  * train.py:146-159 / 311-322, call sites train.py:167-170 / 329-332): nn.BatchNorm2d semantics

@@ -36,7 +36,7 @@ EXPORTS = (
     "dcn_p2p_handle_bytes", "dcn_p2p_create", "dcn_p2p_local_handle", "dcn_p2p_connect",
     "dcn_p2p_allreduce_sum_f32", "dcn_p2p_destroy", "dcn_roi_pool_forward", "dcn_roi_pool_backward",
     "dcn_staged_input_bytes", "dcn_staged_input_clear", "dcn_layer_forward_chained",
-    "dcn_bn_relu_forward_staged", "dcn_bn_relu_backward_staged",
+    "dcn_bn_relu_forward_staged", "dcn_bn_relu_backward_staged", "dcn_stem_conv_forward", "dcn_stem_conv_backward",
 )
 
 
@@ -107,6 +107,8 @@ def load():
     lib.dcn_layer_forward_chained.argtypes = [shp, shp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.dcn_roi_pool_forward.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, f32, f32, i32, vp, vp]
     lib.dcn_roi_pool_backward.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, f32, f32, i32, vp, vp, vp, vp]
+    lib.dcn_stem_conv_forward.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.dcn_stem_conv_backward.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 

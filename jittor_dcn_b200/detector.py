@@ -1,13 +1,14 @@
 """Harness model for BASELINE configs 1 and 5: the reference's toy detector topology
 (`TorchEDNetDetection`, train.py:142-175) with its four DeformConv2d layers running on the B200
-engine.  Only the DCN layers are ours; conv1 / BatchNorm / ReLU / pooling / the two heads are
-stock framework ops, as in the reference.  Module and parameter names follow the reference so
+engine.  The DCN layers are ours, and with them (fused_bn_relu) the ops either side of them: relu(bn(x)) and conv1, the
+producer of the first DCN layer's input (StemConv2d); pooling, the two heads and the optimiser are stock framework
+ops, as in the reference.  Module and parameter names follow the reference so
 that its checkpoints (train.py:293, test.py:17-22) load unchanged.
 """
 import torch
 import torch.nn as nn
 
-from .torch_module import BatchNormReLU2d, TorchDeformConv2d
+from .torch_module import BatchNormReLU2d, StemConv2d, TorchDeformConv2d
 
 # (name suffix, in, out) of the stride-2 DCN stages, train.py:149-158
 _DCN_STAGES = ((2, 16, 32), (3, 32, 64), (4, 64, 128), (5, 128, 256))
@@ -25,7 +26,8 @@ class EDNetDetection(nn.Module):
         self.fused_bn_relu = fused_bn_relu
         bn_cls = BatchNormReLU2d if fused_bn_relu else nn.BatchNorm2d
         del groups  # dead argument in the reference too (train.py:143,145)
-        self.conv1 = nn.Conv2d(1, 16, 3, 1, 1)
+        # conv1 on the engine's streaming kernels when the engine path is on (same parameters / state-dict keys)
+        self.conv1 = (StemConv2d if fused_bn_relu else nn.Conv2d)(1, 16, 3, 1, 1)
         self.bn1 = bn_cls(16)
         self.relu = nn.ReLU(inplace=True)
         for idx, cin, cout in _DCN_STAGES:

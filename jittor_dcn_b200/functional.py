@@ -467,6 +467,56 @@ def batch_norm_relu(x, weight, bias, running_mean, running_var, training, moment
 # The post-op writes the NEXT layer's staged input (framed channels-last copy at the head of that layer's workspace);
 # the tensor that travels between the two autograd nodes is a float32 view of that workspace head, and its gradient
 # is the consumer's channels-last grad_x accumulator (DCN_FLAG_GRAD_X_FRAMED) — nothing crosses the boundary in NCHW.
+def stem_conv_supported(x, weight):
+    """dcn_stem_conv_* takes this convolution (csrc/dcn_stem.cu: 3 x 3, stride 1, padding 1, Cin <= 4, O in {16, 32},
+    W % 4 == 0, float32 CUDA tensors, no input gradient wanted)."""
+    return (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and weight.dtype == torch.float32
+            and tuple(weight.shape[2:]) == (3, 3) and weight.shape[1] == x.shape[1] <= 4
+            and weight.shape[0] in (16, 32) and x.shape[3] % 4 == 0 and not x.requires_grad)
+
+
+class StemConvFunction(torch.autograd.Function):
+    """conv2d(x, weight, bias, stride 1, padding 1) of the detector's first layer (train.py:145,166) on the engine's two
+    streaming kernels.  x is the network input: no gradient flows to it."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        lib = _lib.load()
+        xd, wd = _dev_ready(x), _dev_ready(weight)
+        bd = _dev_ready(bias) if bias is not None else None
+        B, Cin, H, W = xd.shape
+        O = wd.shape[0]
+        out = torch.empty(B, O, H, W, dtype=torch.float32, device=xd.device)
+        with torch.cuda.device(xd.device):
+            stream = torch.cuda.current_stream(xd.device)
+            rc = lib.dcn_stem_conv_forward(B, Cin, O, H, W, _ptr(xd), _ptr(wd), _ptr(bd), _ptr(out),
+                                           ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "dcn_stem_conv_forward")
+        ctx.save_for_backward(xd)
+        ctx.O, ctx.has_bias = O, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        xd, = ctx.saved_tensors
+        B, Cin, H, W = xd.shape
+        go = _dev_ready(grad_out)
+        gw = torch.empty(ctx.O, Cin, 3, 3, dtype=torch.float32, device=xd.device)
+        gb = torch.empty(ctx.O, dtype=torch.float32, device=xd.device)
+        with torch.cuda.device(xd.device):
+            stream = torch.cuda.current_stream(xd.device)
+            rc = lib.dcn_stem_conv_backward(B, Cin, ctx.O, H, W, _ptr(xd), _ptr(go), _ptr(gw), _ptr(gb),
+                                            ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "dcn_stem_conv_backward")
+        return None, gw, gb if ctx.has_bias else None
+
+
+def stem_conv(x, weight, bias=None):
+    """The detector's conv1 on the engine; the caller checks stem_conv_supported first."""
+    return StemConvFunction.apply(x, weight, bias)
+
+
 def _framed_view(ws, B, H, W, C):
     n = B * (H + 3) * (W + 2) * C
     return ws[:4 * n].view(torch.float32).view(B, H + 3, W + 2, C)

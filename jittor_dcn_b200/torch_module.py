@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import _lib
 from .functional import (batch_norm_relu, batch_norm_relu_staged, deform_conv2d, deform_layer, deform_layer_framed,
-                         layer_supported)
+                         layer_supported, stem_conv, stem_conv_supported)
 
 
 class TorchDeformConv2d(nn.Module):
@@ -148,3 +148,16 @@ class BatchNormReLU2d(nn.BatchNorm2d):
             return batch_norm_relu_staged(x, self.weight, self.bias, rm, rv, use_batch_stats, momentum, self.eps,
                                           consumer_cfg)
         return batch_norm_relu(x, self.weight, self.bias, rm, rv, use_batch_stats, momentum, self.eps)
+
+
+class StemConv2d(nn.Conv2d):
+    """``nn.Conv2d`` (same parameters, initialisation and state-dict keys) whose 3 x 3 / stride 1 / padding 1 case on
+    the network input — the detector's ``conv1 = Conv2d(1, 16, 3, 1, 1)``, train.py:145 / :307 — runs on the engine's
+    two streaming kernels (csrc/dcn_stem.cu); every other configuration, a CPU tensor or an input that wants a
+    gradient takes the framework's convolution unchanged."""
+
+    def forward(self, x):
+        if (self.stride == (1, 1) and self.padding == (1, 1) and self.dilation == (1, 1) and self.groups == 1
+                and self.padding_mode == "zeros" and stem_conv_supported(x, self.weight)):
+            return stem_conv(x, self.weight, self.bias)
+        return super().forward(x)

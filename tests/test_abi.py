@@ -210,6 +210,13 @@ def test_round2_entry_points_validate_their_arguments_without_a_gpu():
     for cls in (dcn.DeformRoIPool, dcn.DeformPSRoIPool):
         with pytest.raises(ValueError):
             cls(7)
+    # the detector's conv1 (csrc/dcn_stem.cu): extents, supported set, pointers
+    assert lib.dcn_stem_conv_forward(0, 1, 16, 8, 8, ok, ok, ok, ok, None) == -1
+    assert lib.dcn_stem_conv_forward(2, 1, 24, 8, 8, ok, ok, ok, ok, None) == -6 and b"O in {16, 32}" in lib.dcn_last_error()
+    assert lib.dcn_stem_conv_forward(2, 1, 16, 8, 6, ok, ok, ok, ok, None) == -6           # W % 4
+    assert lib.dcn_stem_conv_forward(2, 5, 16, 8, 8, ok, ok, ok, ok, None) == -6           # Cin > 4
+    assert lib.dcn_stem_conv_forward(2, 1, 16, 8, 8, None, ok, ok, ok, None) == -2
+    assert lib.dcn_stem_conv_backward(2, 1, 16, 8, 8, ok, ok, None, ok, None) == -2
     # path names of the three kernel families
     for shape, name in (((256, 64, 64, 128, 128), b"umma"), ((128, 512, 512, 14, 14), b"gemm"), ((3, 5, 7, 9, 13), b"simt")):
         s = dcn.make_shape(*shape, 3, 1, 1, dcn.VARIANT_TORCH)
