@@ -37,6 +37,10 @@ WORKLOADS = {
              64, 256, 256, 28, 28, 3, 1, 1),
     "det2": ("detector conv2 16->32 3x3 s2 p1, 128x128, batch 1024 per GPU (BASELINE configs[4] layer), fwd+bwd",
              1024, 16, 32, 128, 128, 3, 2, 1),
+    "det3": ("detector conv3 32->64 3x3 s2 p1, 64x64, batch 1024 per GPU (BASELINE configs[4] layer), fwd+bwd",
+             1024, 32, 64, 64, 64, 3, 2, 1),
+    "det4": ("detector conv4 64->128 3x3 s2 p1, 32x32, batch 1024 per GPU (BASELINE configs[4] layer), fwd+bwd",
+             1024, 64, 128, 32, 32, 3, 2, 1),
     "det5": ("detector conv5 128->256 3x3 s2 p1, 16x16, batch 1024 per GPU (BASELINE configs[4] layer), fwd+bwd",
              1024, 128, 256, 16, 16, 3, 2, 1),
     "c3": ("ResNet-50 C3 DCN layer 128->128 3x3 s1 p1, 56x56, batch 128 per GPU (BASELINE configs[3] layer), fwd+bwd",

@@ -258,6 +258,9 @@ struct Knobs {
   int conv_wstream;     // DCN_CONV_WSTREAM     shifted-view conv: stream the weight tap images per K step even when they fit
   int conv_debug;       // DCN_CONV_DEBUG       shifted-view conv: print per-role wait / work cycle counters of CTA 0
   int conv_small_c;     // DCN_CONV_SMALL_C     shifted-view conv also for 16 / 32 input channels (slower; for A/B runs)
+  int conv_small_off;   // DCN_CONV_SMALL_OFF   companion offset conv of layers with < 64 input channels (and the stride-2
+                        //                      data gradient of wider ones): plain mode of the DCN kernels instead of
+                        //                      the warp-MMA kernels (dcn_conv_small.cu)
   int gemm_off;         // DCN_GEMM_OFF         Torch layout with gcd(HoWo, C) % 16 != 0: generic kernels instead of the
                         //                      materialised-sample + cuBLAS path (dcn_gemm_path.cu)
   int conv_off;         // DCN_CONV_OFF         companion offset conv: the plain mode of the DCN kernels instead of the

@@ -854,15 +854,32 @@ static size_t conv_smem(const cv::Params& P, int mode) {
   return (size_t)P.stages * P.stage_bytes + (mode == cv::MODE_WGRAD ? 2 * 2 * 2 * 32 * 128 : 0) + P.w_res_bytes + 256 + 1024;
 }
 
-bool conv_offset_fwd_supported(const Geo& g) {
-  if (knobs().conv_off) return false;
+// warp-MMA kernels (dcn_conv_small.cu): narrow layers and whatever else the shifted-view kernels refuse
+bool conv_small_supported(const Geo& g);
+size_t conv_small_wfrag_bytes(const Geo& g);
+int conv_small_forward(const Geo& g, const float* xt, const float* woff, const float* boff, float* offset_out,
+                       uint8_t* wfrag, cudaStream_t st);
+int conv_small_backward(const Geo& g, const float* xt, float* gxt, const float* goff, const float* woff, float* gwoff,
+                        uint8_t* wfrag, cudaStream_t st);
+
+static bool conv_fwd_shifted(const Geo& g) {
   cv::Params P;
   return conv_params(g, cv::MODE_FWD, &P);
 }
-bool conv_offset_bwd_supported(const Geo& g) {
-  if (knobs().conv_off) return false;
+static bool conv_bwd_shifted(const Geo& g) {
   cv::Params P;
   return conv_params(g, cv::MODE_DGRAD, &P) && conv_params(g, cv::MODE_WGRAD, &P);
+}
+
+bool conv_offset_fwd_supported(const Geo& g) {
+  if (knobs().conv_off) return false;
+  return conv_fwd_shifted(g) || conv_small_supported(g);
+}
+bool conv_offset_bwd_supported(const Geo& g) {
+  if (knobs().conv_off) return false;
+  // measured on the detector's layers (batch 1024): the warp-MMA backward wins below 64 channels (conv2 1.4 vs 1.8 ms,
+  // conv3 0.7 vs 0.7 ms); at 64 / 128 channels the plain mode of the fused DCN backward kernel is faster (0.23 vs 0.35 ms)
+  return conv_bwd_shifted(g) || (g.C < 64 && conv_small_supported(g));
 }
 
 // bytes of weight tap images one pass needs (the backward passes run one after the other and share the region)
@@ -874,6 +891,8 @@ size_t conv_offset_wtile_bytes(const Geo& g) {
     const size_t d = (size_t)P.nchunks_n * P.kh * P.kw * 2 * P.w_tile;
     need = d > need ? d : need;
   }
+  const size_t sm = conv_small_wfrag_bytes(g);
+  need = sm > need ? sm : need;
   return align_up(need, 1024);
 }
 
@@ -918,6 +937,7 @@ static int conv_weight_tiles(const cv::Params& P, int dgrad, const float* w, uin
 int conv_offset_forward(const Geo& g, const float* xt, const float* woff, const float* boff, float* offset_out,
                         uint8_t* wtiles, cudaStream_t st) {
   cv::Params P;
+  if (!conv_fwd_shifted(g) && conv_small_supported(g)) return conv_small_forward(g, xt, woff, boff, offset_out, wtiles, st);
   if (!conv_params(g, cv::MODE_FWD, &P)) {
     set_error("offset conv (shifted-view kernel): shape not supported");
     return DCN_ERR_UNSUPPORTED;
@@ -937,6 +957,8 @@ int conv_offset_backward(const Geo& g, const float* xt, float* gxt, const float*
                          uint8_t* wtiles, cudaStream_t st) {
   cv::Params P;
   int rc;
+  if (!conv_bwd_shifted(g) && g.C < 64 && conv_small_supported(g))
+    return conv_small_backward(g, xt, gxt, goff, woff, gwoff, wtiles, st);
   const int sms = conv_sms();
   if (gxt) {
     if (!conv_params(g, cv::MODE_DGRAD, &P)) {
