@@ -292,11 +292,13 @@ __device__ __forceinline__ void wgrad_load(const Params& P, int u, int kh, int m
 template <int NT>
 __global__ void __launch_bounds__(kWgradThreads) wgrad_kernel(Params P) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  // the role is uniform over the block (its four warps are four streams of it): one shared-memory reduction and one
+  // atomicAdd per block and entry at the end.  gridDim.x is a multiple of the role count.
+  constexpr int kWarps = kWgradThreads / 32;
   const int roles = 3 * P.KS;
-  const int wid = blockIdx.x * (kWgradThreads / 32) + (threadIdx.x >> 5);
-  const int nstreams = gridDim.x * (kWgradThreads / 32) / roles;
-  const int role = wid % roles, stream = wid / roles;
-  if (stream >= nstreams) return;
+  const int warp = threadIdx.x >> 5;
+  const int role = blockIdx.x % roles;
+  const int nstreams = gridDim.x / roles * kWarps, stream = blockIdx.x / roles * kWarps + warp;
   const int kh = role % 3, mt = role / 3;
   const int units = P.B * P.chunks;
   float acc[3][NT][4];
@@ -336,17 +338,37 @@ __global__ void __launch_bounds__(kWgradThreads) wgrad_kernel(Params P) {
     }
     cur = nxt;
   }
+  // block reduction: warps 1..3 park their accumulators in shared memory, warp 0 adds them up
+  __shared__ float red[kWarps - 1][3 * NT * 4][32];
+  if (warp > 0) {
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) red[warp - 1][(kw * NT + nt) * 4 + e][lane] = acc[kw][nt][e];
+  }
+  __syncthreads();
+  if (warp > 0) return;
   // D rows g / g + 8 = staged channels mt * 16 + 2g / + 1, columns = outputs nt * 8 + 2t (+1)
+  int crow[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int csn = mt * 16 + 2 * g + h;
+    crow[h] = P.perm_G ? (csn % P.perm_G) * P.perm_Cs + csn / P.perm_G : csn;
+  }
 #pragma unroll
   for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int csn = mt * 16 + 2 * g + (e >> 1), o = nt * 8 + 2 * t + (e & 1);
+        const int o = nt * 8 + 2 * t + (e & 1);
         if (o >= P.O) continue;
-        const int c = P.perm_G ? (csn % P.perm_G) * P.perm_Cs + csn / P.perm_G : csn;
-        atomicAdd(P.gw + ((size_t)o * P.C + c) * 9 + kh * 3 + kw, acc[kw][nt][e]);
+        float v = acc[kw][nt][e];
+#pragma unroll
+        for (int w2 = 0; w2 < kWarps - 1; ++w2) v += red[w2][(kw * NT + nt) * 4 + e][lane];
+        atomicAdd(P.gw + ((size_t)o * P.C + crow[e >> 1]) * 9 + kh * 3 + kw, v);
       }
 }
 
@@ -466,12 +488,13 @@ int conv_small_backward(const Geo& g, const float* xt, float* gxt, const float* 
   DCN_CUDA_TRY(cudaMemsetAsync(gwoff, 0, sizeof(float) * (size_t)P.O * P.C * 9, st));
   P.gw = gwoff;
   {
-    // warps = roles x streams: enough streams to fill the machine, not more than there are chunks
+    // blocks = roles x groups of four streams: enough to fill the machine (four blocks per SM by registers), at least
+    // 16 chunks per stream
     const int roles = 3 * P.KS;
-    long long streams = std::max<long long>(1, (long long)sms * 16 / roles);
-    streams = std::min<long long>(streams, units);
     const int wpb = cs::kWgradThreads / 32;
-    const int grid = (int)((streams * roles + wpb - 1) / wpb);
+    long long groups = std::max<long long>(1, (long long)sms * 4 / roles);
+    groups = std::max<long long>(1, std::min<long long>(groups, units / (16 * wpb)));
+    const int grid = (int)(groups * roles);
     KernelScope scope("conv_small_wgrad_kernel", st);
     switch (NT) {
       case 1: cs::wgrad_kernel<1><<<grid, cs::kWgradThreads, 0, st>>>(P); break;

@@ -6,7 +6,7 @@ stores / global reductions), from `cuobjdump -sass` of the built library:
 
 Mnemonics (B200_PROFILING.md): UTCHMMA = tcgen05.mma kind::f16, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit,
 UBLKCP = cp.async.bulk, UBLKRED = cp.reduce.async.bulk, UTMASTG / UTMALDG = cp.async.bulk.tensor store / load,
-REDG = red.global, SYNCS = mbarrier, LDGSTS = cp.async, ATOMG = atom.global."""
+HMMA = mma.sync (warp-level tensor-core path of dcn_conv_small.cu), REDG = red.global, SYNCS = mbarrier, LDGSTS = cp.async, ATOMG = atom.global."""
 import collections
 import os
 import re
@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "jittor_dcn_b200", "libdcn_b200.so")
-KEYS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTCATOMSWS", "UBLKCP", "UBLKRED", "UTMASTG", "UTMALDG", "UTMAREDG", "REDG", "RED.",
+KEYS = ["UTCHMMA", "HMMA", "UTCBAR", "LDTM", "STTM", "UTCATOMSWS", "UBLKCP", "UBLKRED", "UTMASTG", "UTMALDG", "UTMAREDG", "REDG", "RED.",
         "ATOMG", "SYNCS", "LDGSTS", "LDG", "STG", "LDS", "STS", "SHFL", "BAR"]
 
 
