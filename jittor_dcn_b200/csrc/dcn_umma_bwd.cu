@@ -27,7 +27,7 @@ size_t umma_bwd_data_wtile_bytes(const Geo& g, int operand);
 bool umma_bwd_data_fuses_wgrad(const Geo& g, int operand);
 int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, const float* off, const void* wt,
                       const void* gout, float* goff, float* gw, uint8_t* wtiles, uint8_t* gtiles,
-                      cudaStream_t st);
+                      cudaStream_t st, float* gb_fused = nullptr);
 size_t umma_bwd_data_gtile_bytes(const Geo& g, int operand);
 bool o_groups(const Geo& g, int* size);
 Geo o_group_geo(const Geo& g, int o0, int size);
@@ -137,6 +137,9 @@ int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, cons
     uint8_t* gtiles = wtiles + umma_bwd_data_wtile_bytes(g0, operand);
     if (want_gx) DCN_CUDA_TRY(cudaMemsetAsync(gxt, 0, sizeof(float) * (size_t)g.B * xt_image_stride(g), st));
     DCN_CUDA_TRY(cudaMemsetAsync(goff, 0, sizeof(float) * (size_t)g.B * 2 * g.N * g.HW, st));
+    // Torch layout: the staging pass of grad_out sums grad_bias on its way (every element passes through it once)
+    const bool gb_rides = gb != nullptr && g.variant == DCN_VARIANT_TORCH;
+    if (gb_rides) DCN_CUDA_TRY(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)g.O, st));
     for (int o0 = 0; o0 < g.O; o0 += gsize) {
       const Geo gc = o_group_geo(g, o0, gsize);
       const bool fused = umma_bwd_data_fuses_wgrad(gc, operand);  // one pass over the samples yields gW as well
@@ -145,7 +148,8 @@ int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, cons
       if (fused) DCN_CUDA_TRY(cudaMemsetAsync(gwc, 0, sizeof(float) * (size_t)gc.O * g.K, st));
       if ((rc = umma_bwd_data_any(gc, operand, xt, want_gx ? gxt : nullptr, off,
                                   (const uint8_t*)wtv + (size_t)o0 * g.K * esz,
-                                  (const uint8_t*)goutv + (size_t)o0 * g.HW * esz, goff, gwc, wtiles, gtiles, st)))
+                                  (const uint8_t*)goutv + (size_t)o0 * g.HW * esz, goff, gwc, wtiles, gtiles, st,
+                                  gb_rides ? gb + o0 : nullptr)))
         return rc;
     }
     if (woff && conv_offset_bwd_supported(g)) {
@@ -166,7 +170,7 @@ int umma_backward_any(const Geo& g, int operand, int flags, const void* xv, cons
     }
     if (want_gx && !gx_framed && (rc = launch_nhwc_to_nchw_add(g, t, gxt, gx, (flags & DCN_FLAG_ACCUM_GRAD_X) ? 1 : 0, st)))
       return rc;
-    if ((rc = launch_bias_grad(g, goutv, operand, gb, st))) return rc;
+    if (!gb_rides && (rc = launch_bias_grad(g, goutv, operand, gb, st))) return rc;
     if (all_fused) return DCN_OK;
   } else {
     if (woff) {

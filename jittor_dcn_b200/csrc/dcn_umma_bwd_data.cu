@@ -72,6 +72,8 @@ struct Params {
   const void* gout;      // float or bfloat16
   const uint8_t* wtiles; // [cblocks][OB][hi|lo][ncols x 64] K-major SW128 images of Wm^T
   const uint8_t* gtiles; // Torch layout: [tile][OB][hi|lo][128 rows x 64 o] K-major SW128 images of grad_out
+  float* gb_fused;       // staging kernel only (Torch layout): grad_bias [O] accumulated from the tiles it stages
+                         // (zeroed by the caller), or null
   int row_v;             // staging kernel only: 0 = rows ordered (instance, channel) as this kernel wants them;
                          // V = 4 / 8: the forward-kernel order (channel / V, instance, channel % V) for MODE_WGRAD
   float* goff;           // grad_offset accumulators (zeroed)
@@ -936,6 +938,27 @@ __global__ void __launch_bounds__(256) gout_tiles_torch_kernel(const __grid_cons
     }
   }
   __syncthreads();
+  if (P.gb_fused) {
+    // grad_bias rides along: the block holds 256 (instance, channel) rows x 32 output channels of grad_out; every
+    // element of grad_out is staged exactly once, rows of no instance are zero.  Lanes = output channels (odd row
+    // stride: no bank conflicts), 8 warps = 8 groups of 32 rows.
+    __shared__ float gb_part[8][32];
+    const int ol = tid & 31, part = tid >> 5;
+    float sum = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) {
+      const int row = part * 32 + q;  // (instance r, channel i2)
+      sum += gt_buf[(row >> 4) * kGtIS + (row & 15) * kGtRow + ol];
+    }
+    gb_part[part][ol] = sum;
+    __syncthreads();
+    if (tid < 32 && o0 + tid < g.O) {
+      float tot = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tot += gb_part[q][tid];
+      atomicAdd(P.gb_fused + o0 + tid, tot);
+    }
+  }
   // 16-byte chunks (8 o) of the images: lanes = 4 chunks x 8 consecutive rows of one instance
   const uint32_t img_bytes = 128u * 128u;
   const int ob = o0 >> 6, c_base = (o0 & 63) >> 3;
@@ -1279,9 +1302,10 @@ size_t umma_bwd_data_gtile_bytes(const Geo& g, int operand) {
 
 // gxt (channels-last grad_x, may be null), goff and — when the shape fuses the weight gradient
 // (umma_bwd_data_fuses_wgrad) — gw must be zero on entry.
+// gb_fused (Torch layout only, may be null): grad_bias [g.O], zeroed by the caller, summed by the grad_out staging pass
 int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, const float* off, const void* wt,
                       const void* gout, float* goff, float* gw, uint8_t* wtiles, uint8_t* gtiles,
-                      cudaStream_t st) {
+                      cudaStream_t st, float* gb_fused) {
   bd::Params P;
   P.g = g;
   const bool bf = operand == DCN_OPERAND_BF16;
@@ -1310,6 +1334,7 @@ int umma_bwd_data_any(const Geo& g, int operand, const void* xt, float* gxt, con
   P.wtiles = wtiles;
   P.gtiles = gtiles;
   P.row_v = 0;
+  P.gb_fused = g.variant == DCN_VARIANT_TORCH ? gb_fused : nullptr;
   {
     int rc = g.variant == DCN_VARIANT_TORCH ? launch_gout_tiles(P, bf, gtiles, st)
                                             : launch_gout_tiles_pix(g, operand, gout, gtiles, st);
