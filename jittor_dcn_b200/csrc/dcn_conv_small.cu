@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(Params P) {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           // rows g / g + 8: channels ks * 16 + 4t .. + 3 = K slots 2t, 2t + 1 | 2t + 8, 2t + 9
+          DCN_DEV_ASSERT((size_t)((kh * P.pitch + kw) * P.C + max(roff[mt][0], roff[mt][1]) + ks * 16 + 4) <= P.img_stride);
           const float4 v0 = __ldg(reinterpret_cast<const float4*>(xtap + roff[mt][0] + ks * 16));
           const float4 v1 = __ldg(reinterpret_cast<const float4*>(xtap + roff[mt][1] + ks * 16));
           ptx::split_pair(v0.x, v0.y, ahi[mt][0], alo[mt][0]);
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(kThreads) dgrad_kernel(Params P) {
             mma16816(acc[h], ahi[ks], bl);
             mma16816(acc[h], ahi[ks], bh);
           }
+        DCN_DEV_ASSERT((size_t)(pix_off(P, min(qb, P.HoWo - 1)) + 4 * t + toff + cp * 16 + 4) <= P.img_stride);
         if (oka)
           atomicAdd(reinterpret_cast<float4*>(ga + toff + cp * 16), make_float4(acc[0][0], acc[0][1], acc[1][0], acc[1][1]));
         if (okb)
@@ -267,6 +269,7 @@ __device__ __forceinline__ void wgrad_load(const Params& P, int u, int kh, int m
     }
     const float* xp = xb + pix_off(P, in ? q0 : 0);
     const int step = P.s * P.C;
+    DCN_DEV_ASSERT((size_t)(kh * P.pitch * P.C + mt * 16 + 2 * g + pix_off(P, in ? q0 : 0) + 3 * step + 2 * P.C + 2) <= P.img_stride);
 #pragma unroll
     for (int e = 0; e < 4; ++e)
 #pragma unroll
