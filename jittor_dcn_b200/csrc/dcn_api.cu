@@ -45,6 +45,7 @@ const Knobs& knobs() {
     v.fwd_no_tma_out = env_set("DCN_FWD_NO_TMA_OUT");
     v.fwd_stages = env_int("DCN_FWD_STAGES", 3);
     v.fwd_no_kperm = env_set("DCN_FWD_NO_KPERM");
+    v.fwd_no_split88 = env_set("DCN_FWD_NO_SPLIT88");
     v.bwd_no_resident = env_set("DCN_BWD_NO_RESIDENT");
     v.bwd_no_ring1 = env_set("DCN_BWD_NO_RING1");
     v.bwd_slice_cb = env_int("DCN_BWD_SLICE_CB", 6);

@@ -252,6 +252,8 @@ struct Knobs {
   int bwd_no_resident;  // DCN_BWD_NO_RESIDENT  fused backward: always stream the Wm^T images through the ring
   int bwd_no_ring1;     // DCN_BWD_NO_RING1     fused backward: never take the 1-stage ring plan
   int bwd_slice_cb;     // DCN_BWD_SLICE_CB     fused backward (Torch layout): max column blocks per slice (1..6)
+  int fwd_no_split88;   // DCN_FWD_NO_SPLIT88   forward, Torch layout with 16 channels per sampling point: 4 plan + 16 gather warps
+                        //                      like every other shape instead of 8 + 8
   int bwd_no_fuse;      // DCN_BWD_NO_FUSE      weight gradient as its own pass
   int bwd_gbuf1;        // DCN_BWD_GBUF=1       one grad_out tile buffer
   int bwd_data_simt;    // DCN_BWD_DATA_SIMT    fp32 data gradient on the generic kernels

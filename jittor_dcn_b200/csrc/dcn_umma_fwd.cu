@@ -188,9 +188,18 @@ __device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
 // operand is ONE bf16 image and every K step ONE MMA; otherwise fp32 with the hi/lo split (two
 // images, three MMAs).  A gather item is one 16-byte load per corner: V = 4 fp32 or 8 bf16 channels.
 // PLAIN = regular convolution on the same machinery (the companion offset conv): one exact pixel per entry.
-template <int VARIANT, int MODE, bool BF, bool PLAIN = false>
-__global__ void __launch_bounds__(kFwdThreads, 1) umma_gemm_kernel(const __grid_constant__ FwdParams P,
-                                                                   const __grid_constant__ CUtensorMap tmap_out) {
+// PW / GW = plan / gather warps.  4 + 16 everywhere except the Torch layout with 16 channels per sampling point
+// (Rt = 8: 512 coordinate chains per K block for 2048 gather items — the 4 plan warps, one per scheduler, were the
+// critical path and the gather warps waited 40 % of the time, profiles/r1_ncu_det2.txt): 8 + 8 there.
+template <int VARIANT, int MODE, bool BF, bool PLAIN = false, int PW = 4, int GW = 16>
+__global__ void __launch_bounds__((kFirstPlanWarp + PW + GW) * 32, 1)
+    umma_gemm_kernel(const __grid_constant__ FwdParams P, const __grid_constant__ CUtensorMap tmap_out) {
+  // role layout of this instantiation (shadows the file-scope defaults)
+  constexpr int kPlanWarps = PW, kProdWarps = GW;
+  constexpr int kPlanThreads = PW * 32, kProdThreads = GW * 32;
+  constexpr int kFirstProdWarp = kFirstPlanWarp + PW;
+  constexpr int kFwdThreads = (kFirstProdWarp + GW) * 32;
+  constexpr int kPlanPerThread = kPlanMax / kPlanThreads;
   constexpr int V = BF ? 8 : 4;
   constexpr int NIMG = BF ? 1 : 2;
   constexpr int kIt = 128 * 64 / V / kProdThreads;  // gather items per thread and K block: 4 or 2
@@ -1020,6 +1029,27 @@ static int launch_gemm(const Geo& g, int operand, const FwdParams& P, const CUte
     umma_gemm_kernel<V, MODE, BFV><<<grid, kFwdThreads, smem, st>>>(P, tmap);                              \
   } while (0)
   const bool bf = operand == DCN_OPERAND_BF16;
+  // more than 256 coordinate chains per K block (16 channels per sampling point: Torch layout with Rt = 8, pixel-row
+  // layouts with 4 taps per K block): 8 plan + 8 gather warps
+  const int n_ent = g.variant == DCN_VARIANT_TORCH ? P.t.Rt * 64 : 128 * P.t.taps_per_kb;
+  if (MODE == MODE_FWD && n_ent > 256 && !knobs().fwd_no_split88) {
+    constexpr int kThreads88 = (kFirstPlanWarp + 8 + 8) * 32;
+#define DCN_GEMM_CASE88(V, BFV)                                                                            \
+  do {                                                                                                     \
+    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<V, MODE_FWD, BFV, false, 8, 8>,                     \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    umma_gemm_kernel<V, MODE_FWD, BFV, false, 8, 8><<<grid, kThreads88, smem, st>>>(P, tmap);              \
+  } while (0)
+    if (g.variant == DCN_VARIANT_TORCH) {
+      if (bf) DCN_GEMM_CASE88(DCN_VARIANT_TORCH, true);
+      else DCN_GEMM_CASE88(DCN_VARIANT_TORCH, false);
+    } else {
+      if (bf) DCN_GEMM_CASE88(DCN_VARIANT_JITTOR, true);
+      else DCN_GEMM_CASE88(DCN_VARIANT_JITTOR, false);
+    }
+#undef DCN_GEMM_CASE88
+    return DCN_OK;
+  }
   if (g.variant == DCN_VARIANT_TORCH) {
     if (bf) DCN_GEMM_CASE(DCN_VARIANT_TORCH, true);
     else DCN_GEMM_CASE(DCN_VARIANT_TORCH, false);
