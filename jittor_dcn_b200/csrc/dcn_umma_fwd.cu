@@ -1032,13 +1032,13 @@ static int launch_gemm(const Geo& g, int operand, const FwdParams& P, const CUte
   // more than 256 coordinate chains per K block (16 channels per sampling point: Torch layout with Rt = 8, pixel-row
   // layouts with 4 taps per K block): 8 plan + 8 gather warps
   const int n_ent = g.variant == DCN_VARIANT_TORCH ? P.t.Rt * 64 : 128 * P.t.taps_per_kb;
-  if (MODE == MODE_FWD && n_ent > 256 && !knobs().fwd_no_split88) {
+  if (n_ent > 256 && !knobs().fwd_no_split88) {
     constexpr int kThreads88 = (kFirstPlanWarp + 8 + 8) * 32;
 #define DCN_GEMM_CASE88(V, BFV)                                                                            \
   do {                                                                                                     \
-    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<V, MODE_FWD, BFV, false, 8, 8>,                     \
+    DCN_CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<V, MODE, BFV, false, 8, 8>,                         \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-    umma_gemm_kernel<V, MODE_FWD, BFV, false, 8, 8><<<grid, kThreads88, smem, st>>>(P, tmap);              \
+    umma_gemm_kernel<V, MODE, BFV, false, 8, 8><<<grid, kThreads88, smem, st>>>(P, tmap);                  \
   } while (0)
     if (g.variant == DCN_VARIANT_TORCH) {
       if (bf) DCN_GEMM_CASE88(DCN_VARIANT_TORCH, true);
