@@ -221,3 +221,17 @@ def test_round2_entry_points_validate_their_arguments_without_a_gpu():
     for shape, name in (((256, 64, 64, 128, 128), b"umma"), ((128, 512, 512, 14, 14), b"gemm"), ((3, 5, 7, 9, 13), b"simt")):
         s = dcn.make_shape(*shape, 3, 1, 1, dcn.VARIANT_TORCH)
         assert lib.dcn_path_name(ctypes.byref(s), 0) == name and lib.dcn_path_name(ctypes.byref(s), 1) == name
+
+
+def test_stem_conv_module_is_a_drop_in_on_cpu():
+    """StemConv2d (the detector's conv1) keeps nn.Conv2d's parameters and, without a CUDA input, its kernels too."""
+    import torch
+    import torch.nn as nn
+    torch.manual_seed(0)
+    ref, eng = nn.Conv2d(1, 16, 3, 1, 1), dcn.StemConv2d(1, 16, 3, 1, 1)
+    assert [(k, tuple(v.shape)) for k, v in eng.state_dict().items()] == [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+    eng.load_state_dict(ref.state_dict())
+    x = torch.randn(2, 1, 12, 16)
+    assert torch.equal(eng(x), ref(x))
+    from jittor_dcn_b200.functional import stem_conv_supported
+    assert not stem_conv_supported(x, eng.weight)                      # CPU tensor
