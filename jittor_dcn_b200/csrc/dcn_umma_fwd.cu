@@ -1032,6 +1032,7 @@ static int launch_gemm(const Geo& g, int operand, const FwdParams& P, const CUte
   // more than 256 coordinate chains per K block (16 channels per sampling point: Torch layout with Rt = 8, pixel-row
   // layouts with 4 taps per K block): 8 plan + 8 gather warps
   const int n_ent = g.variant == DCN_VARIANT_TORCH ? P.t.Rt * 64 : 128 * P.t.taps_per_kb;
+  // (measured at 256 and 128 chains per block — det3, c3, cfg2 — the 8 + 8 split is 18 - 43 % SLOWER: those are gather-bound)
   if (n_ent > 256 && !knobs().fwd_no_split88) {
     constexpr int kThreads88 = (kFirstPlanWarp + 8 + 8) * 32;
 #define DCN_GEMM_CASE88(V, BFV)                                                                            \
