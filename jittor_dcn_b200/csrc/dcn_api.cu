@@ -54,6 +54,7 @@ const Knobs& knobs() {
     v.bwd_data_simt = env_int("DCN_BWD_DATA_SIMT", 0);
     v.conv_off = env_set("DCN_CONV_OFF");
     v.gemm_off = env_set("DCN_GEMM_OFF");
+    v.gemm_sgemm = env_set("DCN_GEMM_SGEMM");
     v.conv_small_c = env_set("DCN_CONV_SMALL_C");
     v.conv_small_off = env_set("DCN_CONV_SMALL_OFF");
     v.conv_debug = env_set("DCN_CONV_DEBUG");

@@ -263,6 +263,8 @@ struct Knobs {
   int conv_small_off;   // DCN_CONV_SMALL_OFF   companion offset conv of layers with < 64 input channels (and the stride-2
                         //                      data gradient of wider ones): plain mode of the DCN kernels instead of
                         //                      the warp-MMA kernels (dcn_conv_small.cu)
+  int gemm_sgemm;       // DCN_GEMM_SGEMM       GEMM path, fp32 operands: true-fp32 cuBLAS GEMMs instead of three bf16 tensor-core
+                        //                      GEMMs over (hi, lo) splits
   int gemm_off;         // DCN_GEMM_OFF         Torch layout with gcd(HoWo, C) % 16 != 0: generic kernels instead of the
                         //                      materialised-sample + cuBLAS path (dcn_gemm_path.cu)
   int conv_off;         // DCN_CONV_OFF         companion offset conv: the plain mode of the DCN kernels instead of the

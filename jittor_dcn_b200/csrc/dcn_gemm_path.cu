@@ -20,6 +20,7 @@
 
 #include <mutex>
 
+#include "dcn_umma.cuh"
 #include "dcn_umma_common.cuh"
 
 namespace dcn {
@@ -108,9 +109,12 @@ __device__ __forceinline__ Corner corner_of(const Geo& g, const Tap& tp) {
 // S[b, c, q] = bilinear sample of channel c at sampling point q (deform_conv.py:47-52 / train.py:121-127).
 // Block = 32 points of one image; loop over 128-channel tiles: warps gather point by point (lane = channel: 128-byte
 // coalesced corner reads), the tile is transposed through shared memory and written with lane = point.
-template <typename T>
+// SPLIT (fp32 operands): S is written as TWO bfloat16 matrices, hi = bf16(v) and lo = bf16(v - hi), for the three-term
+// tensor-core GEMMs (see gemm_path_forward)
+template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(256) sample_kernel(Geo g, const T* __restrict__ xt, const Tap* __restrict__ plan,
-                                                     T* __restrict__ S) {
+                                                     T* __restrict__ S, __nv_bfloat16* __restrict__ S_hi,
+                                                     __nv_bfloat16* __restrict__ S_lo) {
   __shared__ float tile[kQT][kCT + 1];
   const int b = blockIdx.y, q0 = blockIdx.x * kQT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -145,7 +149,17 @@ __global__ void __launch_bounds__(256) sample_kernel(Geo g, const T* __restrict_
 #pragma unroll
     for (int j = 0; j < kCT / 8; ++j) {
       const int cl = warp + 8 * j, c = c0 + cl;
-      if (c < g.C && q < g.P) S[((size_t)b * g.C + c) * g.P + q] = (T)tile[lane][cl];
+      if (c < g.C && q < g.P) {
+        const size_t idx = ((size_t)b * g.C + c) * g.P + q;
+        if (SPLIT) {
+          __nv_bfloat16 hi, lo;
+          ptx::split_bf16(tile[lane][cl], hi, lo);
+          S_hi[idx] = hi;
+          S_lo[idx] = lo;
+        } else {
+          S[idx] = (T)tile[lane][cl];
+        }
+      }
     }
     __syncthreads();
   }
@@ -251,6 +265,36 @@ __global__ void __launch_bounds__(256) gout_rows_kernel(int B, int O, int Oimg, 
   for (int p = threadIdx.x; p < HW; p += 256) dst[p] = src[p];
 }
 
+// fp32 -> (hi, lo) bfloat16 pair, flat (the weight matrix)
+__global__ void __launch_bounds__(256) split_flat_kernel(size_t n, const float* __restrict__ src,
+                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    __nv_bfloat16 h, l;
+    ptx::split_bf16(src[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// grad_out [B, Oimg, HW] fp32 -> hi / lo bfloat16 in BOTH orders the backward GEMMs read: compact [b][o][p] (data
+// gradient) and [o][b][p] (weight gradient); one read of grad_out
+__global__ void __launch_bounds__(256) gout_split_kernel(int B, int O, int Oimg, int HW, const float* __restrict__ gout,
+                                                         __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo,
+                                                         __nv_bfloat16* __restrict__ gT_hi,
+                                                         __nv_bfloat16* __restrict__ gT_lo) {
+  const int o = blockIdx.x, b = blockIdx.y;
+  const float* src = gout + ((size_t)b * Oimg + o) * HW;
+  const size_t d = ((size_t)b * O + o) * HW, dT = ((size_t)o * B + b) * HW;
+  for (int p = threadIdx.x; p < HW; p += 256) {
+    __nv_bfloat16 h, l;
+    ptx::split_bf16(src[p], h, l);
+    g_hi[d + p] = h;
+    g_lo[d + p] = l;
+    gT_hi[dT + p] = h;
+    gT_lo[dT + p] = l;
+  }
+}
+
 }  // namespace gp
 
 // ---------------------------------------------------------------------------- host side
@@ -269,12 +313,22 @@ bool gemm_path_supported(const Geo& g, int operand) {
   return true;
 }
 
-// forward: [xt][plan][S][cuBLAS workspace]; backward: [xt][plan][S][gS][gxt][goutT][cuBLAS workspace]
+// fp32 operands on tensor cores: every operand of the three GEMMs as a (hi, lo) bfloat16 pair, every product as
+// lo*hi + hi*lo + hi*hi with fp32 accumulation (the split of the tcgen05 kernels; relative error ~5e-6).  The true-fp32
+// cuBLAS GEMMs took 2.5 ms each for a C5 layer (47 TFLOP/s) against 0.5 ms for one bf16 GEMM.
+static bool gp_split(int operand) { return operand == DCN_OPERAND_FP32 && !knobs().gemm_sgemm; }
+static size_t gp_W_bytes(const Geo& g, int operand) { return gp_split(operand) ? align_up(4 * (size_t)g.O * g.K, 1024) : 0; }
+static size_t gp_gout_bytes(const Geo& g, int operand) {
+  return align_up(gp_esz(operand) * (size_t)g.B * g.O * g.HW, 1024);
+}
+
+// forward: [xt][plan][S][W hi|lo][cuBLAS workspace]; backward: [xt][plan][S][gS][gxt][goutT][gout hi|lo][W hi|lo][cuBLAS
+// workspace] — S and goutT hold (hi | lo) halves in split mode (same bytes as the fp32 matrix)
 size_t gemm_path_workspace(const Geo& g, int operand, int phase) {
-  size_t b = umma_xt_bytes(g, operand) + gp_plan_bytes(g) + gp_S_bytes(g, operand) + gp::kCublasWs;
+  size_t b = umma_xt_bytes(g, operand) + gp_plan_bytes(g) + gp_S_bytes(g, operand) + gp_W_bytes(g, operand) + gp::kCublasWs;
   if (phase == DCN_PHASE_BACKWARD)
-    b += gp_S_bytes(g, operand) + umma_xt_bytes(g, DCN_OPERAND_FP32) +
-         align_up(gp_esz(operand) * (size_t)g.B * g.O * g.HW, 1024);
+    b += gp_S_bytes(g, operand) + umma_xt_bytes(g, DCN_OPERAND_FP32) + gp_gout_bytes(g, operand) +
+         (gp_split(operand) ? gp_gout_bytes(g, operand) : 0);
   return b;
 }
 
@@ -306,9 +360,13 @@ static int gp_stage_and_sample(const Geo& g, int operand, const void* x, const f
   {
     KernelScope scope("gemm_sample_kernel", st);
     if (operand == DCN_OPERAND_BF16)
-      gp::sample_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(g, (const __nv_bfloat16*)xt, plan, (__nv_bfloat16*)S);
+      gp::sample_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(g, (const __nv_bfloat16*)xt, plan, (__nv_bfloat16*)S,
+                                                                    nullptr, nullptr);
+    else if (gp_split(operand))
+      gp::sample_kernel<float, true><<<grid, 256, 0, st>>>(g, (const float*)xt, plan, nullptr, (__nv_bfloat16*)S,
+                                                           (__nv_bfloat16*)S + (size_t)g.B * g.C * g.P);
     else
-      gp::sample_kernel<float><<<grid, 256, 0, st>>>(g, (const float*)xt, plan, (float*)S);
+      gp::sample_kernel<float, false><<<grid, 256, 0, st>>>(g, (const float*)xt, plan, (float*)S, nullptr, nullptr);
     DCN_KERNEL_CHECK("gemm_sample_kernel");
   }
   return DCN_OK;
@@ -324,13 +382,22 @@ int gemm_path_forward(const Geo& g, int operand, const void* x, const float* off
   Tap* plan;
   int rc;
   if ((rc = gp_stage_and_sample(g, operand, x, off, ws, st, &xt, &plan, &S))) return rc;
-  uint8_t* cws = (uint8_t*)S + gp_S_bytes(g, operand);
+  uint8_t* whl = (uint8_t*)S + gp_S_bytes(g, operand);
+  uint8_t* cws = whl + gp_W_bytes(g, operand);
+  const bool split = gp_split(operand);
   {
     KernelScope scope("gemm_bias_fill_kernel", st);
     gp::bias_fill_kernel<<<1024, 256, 0, st>>>(g.B, g.O, g.Oimg, g.HW, bias, out);
     DCN_KERNEL_CHECK("gemm_bias_fill_kernel");
   }
-  const cudaDataType dt = operand == DCN_OPERAND_BF16 ? CUDA_R_16BF : CUDA_R_32F;
+  const size_t nS = (size_t)g.B * g.C * g.P, nW = (size_t)g.O * g.K;
+  __nv_bfloat16 *w_hi = (__nv_bfloat16*)whl, *w_lo = w_hi + nW;
+  if (split) {
+    KernelScope scope("gemm_split_kernel", st);
+    gp::split_flat_kernel<<<256, 256, 0, st>>>(nW, (const float*)wt, w_hi, w_lo);
+    DCN_KERNEL_CHECK("gemm_split_kernel");
+  }
+  const cudaDataType dt = operand == DCN_OPERAND_FP32 && !split ? CUDA_R_32F : CUDA_R_16BF;
   const float one = 1.f;
   cublasStatus_t cs;
   std::lock_guard<std::mutex> use(gp::g_use_mu);   // a cuBLAS handle must not be driven by two host threads at once
@@ -338,10 +405,19 @@ int gemm_path_forward(const Geo& g, int operand, const void* x, const float* off
   if (gp::g_api.SetWorkspace) gp::g_api.SetWorkspace(h, cws, gp::kCublasWs);
   // row-major out_b[O, HW] += Wm[O, K] * A_b^T  <=>  column-major C'[HW, O] = op_T(A'[K, HW]) * B'[K, O]
   KernelScope scope("cublas_gemm_fwd", st);
-  cs = gp::g_api.GemmStridedBatchedEx(h, CUBLAS_OP_T, CUBLAS_OP_N, g.HW, g.O, g.K, &one, S, dt, g.K, (long long)g.C * g.P, wt,
-                                      dt, g.K, 0, &one, out, CUDA_R_32F, g.HW, (long long)g.Oimg * g.HW, g.B,
-                                      CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
-  count_launch();
+  auto gemm = [&](const void* Sm, const void* Wm) {
+    count_launch();
+    return gp::g_api.GemmStridedBatchedEx(h, CUBLAS_OP_T, CUBLAS_OP_N, g.HW, g.O, g.K, &one, Sm, dt, g.K, (long long)g.C * g.P,
+                                          Wm, dt, g.K, 0, &one, out, CUDA_R_32F, g.HW, (long long)g.Oimg * g.HW, g.B,
+                                          CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
+  };
+  if (split) {
+    const __nv_bfloat16 *s_hi = (const __nv_bfloat16*)S, *s_lo = s_hi + nS;
+    if ((cs = gemm(s_lo, w_hi)) == CUBLAS_STATUS_SUCCESS && (cs = gemm(s_hi, w_lo)) == CUBLAS_STATUS_SUCCESS)
+      cs = gemm(s_hi, w_hi);
+  } else {
+    cs = gemm(S, wt);
+  }
   if (cs != CUBLAS_STATUS_SUCCESS) return gp_cublas_fail(cs, "cublasGemmStridedBatchedEx(forward)");
   return DCN_OK;
 }
@@ -359,10 +435,27 @@ int gemm_path_backward(const Geo& g, int operand, int flags, const void* x, cons
   uint8_t* gS = (uint8_t*)S + gp_S_bytes(g, operand);
   float* gxt = (float*)(gS + gp_S_bytes(g, operand));
   uint8_t* goutT = (uint8_t*)gxt + umma_xt_bytes(g, DCN_OPERAND_FP32);
-  uint8_t* cws = goutT + align_up(gp_esz(operand) * (size_t)g.B * g.O * g.HW, 1024);
+  const bool split = gp_split(operand);
+  uint8_t* ghl = goutT + gp_gout_bytes(g, operand);                       // split mode: compact grad_out, hi | lo
+  uint8_t* whl = ghl + (split ? gp_gout_bytes(g, operand) : 0);
+  uint8_t* cws = whl + gp_W_bytes(g, operand);
   const bool want_gx = !(flags & DCN_FLAG_NO_GRAD_X) && gx != nullptr;
-  const cudaDataType dt = operand == DCN_OPERAND_BF16 ? CUDA_R_16BF : CUDA_R_32F;
+  const cudaDataType dt = operand == DCN_OPERAND_FP32 && !split ? CUDA_R_32F : CUDA_R_16BF;
+  const cudaDataType dt_gs = operand == DCN_OPERAND_BF16 ? CUDA_R_16BF : CUDA_R_32F;   // gS feeds the scatter kernel
   const float one = 1.f, zero = 0.f;
+  const size_t nS = (size_t)g.B * g.C * g.P, nW = (size_t)g.O * g.K, nG = (size_t)g.B * g.O * g.HW;
+  __nv_bfloat16 *w_hi = (__nv_bfloat16*)whl, *w_lo = w_hi + nW;
+  __nv_bfloat16 *g_hi = (__nv_bfloat16*)ghl, *g_lo = g_hi + nG;
+  __nv_bfloat16 *gT_hi = (__nv_bfloat16*)goutT, *gT_lo = gT_hi + nG;
+  const __nv_bfloat16 *s_hi = (const __nv_bfloat16*)S, *s_lo = s_hi + nS;
+  if (split) {
+    KernelScope scope("gemm_split_kernel", st);
+    gp::split_flat_kernel<<<256, 256, 0, st>>>(nW, (const float*)wt, w_hi, w_lo);
+    gp::gout_split_kernel<<<dim3((unsigned)g.O, (unsigned)g.B), 256, 0, st>>>(g.B, g.O, g.Oimg, g.HW, (const float*)gout,
+                                                                               g_hi, g_lo, gT_hi, gT_lo);
+    count_launch();
+    DCN_KERNEL_CHECK("gemm_split_kernel");
+  }
   cublasStatus_t cs;
   std::lock_guard<std::mutex> use(gp::g_use_mu);   // see gemm_path_forward
   if ((cs = gp::g_api.SetStream(h, st)) != CUBLAS_STATUS_SUCCESS) return gp_cublas_fail(cs, "cublasSetStream");
@@ -370,10 +463,20 @@ int gemm_path_backward(const Geo& g, int operand, int flags, const void* x, cons
   // row-major gS_b[HW, K] = gout_b^T[HW, O] * Wm[O, K]  <=>  column-major C'[K, HW] = B'[K, O] * op_T(gout'[HW, O])
   {
     KernelScope scope("cublas_gemm_bwd_data", st);
-    cs = gp::g_api.GemmStridedBatchedEx(h, CUBLAS_OP_N, CUBLAS_OP_T, g.K, g.HW, g.O, &one, wt, dt, g.K, 0, gout, dt, g.HW,
-                                        (long long)g.Oimg * g.HW, &zero, gS, dt, g.K, (long long)g.C * g.P, g.B,
-                                        CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
-    count_launch();
+    auto gemm = [&](const void* Wm, const void* Gm, long long gstride, const float* beta) {
+      count_launch();
+      return gp::g_api.GemmStridedBatchedEx(h, CUBLAS_OP_N, CUBLAS_OP_T, g.K, g.HW, g.O, &one, Wm, dt, g.K, 0, Gm, dt, g.HW,
+                                            gstride, beta, gS, dt_gs, g.K, (long long)g.C * g.P, g.B, CUBLAS_COMPUTE_32F,
+                                            CUBLAS_GEMM_DEFAULT);
+    };
+    if (split) {
+      const long long gs = (long long)g.O * g.HW;
+      if ((cs = gemm(w_lo, g_hi, gs, &zero)) == CUBLAS_STATUS_SUCCESS &&
+          (cs = gemm(w_hi, g_lo, gs, &one)) == CUBLAS_STATUS_SUCCESS)
+        cs = gemm(w_hi, g_hi, gs, &one);
+    } else {
+      cs = gemm(wt, gout, (long long)g.Oimg * g.HW, &zero);
+    }
     if (cs != CUBLAS_STATUS_SUCCESS) return gp_cublas_fail(cs, "cublasGemmStridedBatchedEx(data gradient)");
   }
   if (want_gx) DCN_CUDA_TRY(cudaMemsetAsync(gxt, 0, sizeof(float) * (size_t)g.B * xt_image_stride(g), st));
@@ -397,7 +500,7 @@ int gemm_path_backward(const Geo& g, int operand, int flags, const void* x, cons
     if ((rc = launch_nhwc_to_nchw_add(g, t, gxt, gx, (flags & DCN_FLAG_ACCUM_GRAD_X) ? 1 : 0, st))) return rc;
   }
   // weight gradient: row-major gW[O, K] = goutT[O, B*HW] * A[B*HW, K]  <=>  column-major C'[K, O] = A'[K, BHW] * G'[BHW, O]
-  {
+  if (!split) {
     KernelScope scope("gemm_gout_rows_kernel", st);
     const dim3 grid((unsigned)g.O, (unsigned)g.B);
     if (operand == DCN_OPERAND_BF16)
@@ -410,9 +513,17 @@ int gemm_path_backward(const Geo& g, int operand, int flags, const void* x, cons
   {
     KernelScope scope("cublas_gemm_bwd_weight", st);
     const int bhw = g.B * g.HW;
-    cs = gp::g_api.GemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, g.K, g.O, bhw, &one, S, dt, g.K, goutT, dt, bhw, &zero, gw, CUDA_R_32F,
-                          g.K, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
-    count_launch();
+    auto gemm = [&](const void* Sm, const void* Gm, const float* beta) {
+      count_launch();
+      return gp::g_api.GemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, g.K, g.O, bhw, &one, Sm, dt, g.K, Gm, dt, bhw, beta, gw, CUDA_R_32F,
+                              g.K, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
+    };
+    if (split) {
+      if ((cs = gemm(s_lo, gT_hi, &zero)) == CUBLAS_STATUS_SUCCESS && (cs = gemm(s_hi, gT_lo, &one)) == CUBLAS_STATUS_SUCCESS)
+        cs = gemm(s_hi, gT_hi, &one);
+    } else {
+      cs = gemm(S, goutT, &zero);
+    }
     if (cs != CUBLAS_STATUS_SUCCESS) return gp_cublas_fail(cs, "cublasGemmEx(weight gradient)");
   }
   if (gb && (rc = launch_bias_grad(g, gout, operand, gb, st))) return rc;
