@@ -260,9 +260,8 @@ struct Knobs {
   int conv_wstream;     // DCN_CONV_WSTREAM     shifted-view conv: stream the weight tap images per K step even when they fit
   int conv_debug;       // DCN_CONV_DEBUG       shifted-view conv: print per-role wait / work cycle counters of CTA 0
   int conv_small_c;     // DCN_CONV_SMALL_C     shifted-view conv also for 16 / 32 input channels (slower; for A/B runs)
-  int conv_small_off;   // DCN_CONV_SMALL_OFF   companion offset conv of layers with < 64 input channels (and the stride-2
-                        //                      data gradient of wider ones): plain mode of the DCN kernels instead of
-                        //                      the warp-MMA kernels (dcn_conv_small.cu)
+  int conv_small_off;   // DCN_CONV_SMALL_OFF   companion offset conv of layers with < 64 input channels: plain mode of the
+                        //                      DCN kernels instead of the warp-MMA kernels (dcn_conv_small.cu)
   int gemm_sgemm;       // DCN_GEMM_SGEMM       GEMM path, fp32 operands: true-fp32 cuBLAS GEMMs instead of three bf16 tensor-core
                         //                      GEMMs over (hi, lo) splits
   int gemm_off;         // DCN_GEMM_OFF         Torch layout with gcd(HoWo, C) % 16 != 0: generic kernels instead of the

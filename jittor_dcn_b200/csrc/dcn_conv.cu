@@ -745,7 +745,8 @@ static bool conv_params(const Geo& g, int mode, cv::Params* Pp) {
   if (g.ph > 1 || kh > 3 || g.kw > 3) return false;
   // K of one MMA row is the channels of ONE pixel: with fewer than 64 channels the per-tile MMA count (fixed: taps x
   // 16-column steps x hi/lo terms) dominates and the plain mode of the DCN kernels, which packs (tap, channel) pairs
-  // into its K blocks, is faster (measured on the detector's 16- and 32-channel layers: backward 6.6 vs 2.8 ms)
+  // into its K blocks, is faster (measured on the detector's 16- and 32-channel layers: backward 6.6 vs 2.8 ms).  Those
+  // layers run on the warp-MMA kernels of dcn_conv_small.cu instead (conv_offset_*_supported below).
   if (g.C % 64 != 0 && !knobs().conv_small_c) return false;
   if (!(g.C == 16 || g.C == 32 || g.C % 64 == 0)) return false;
   const int O = 2 * g.N;

@@ -1,19 +1,24 @@
 // dcn_conv_small.cu — the companion offset convolution (deform_conv.py:16-21,58; train.py:80-85,98) for layers the
 // shifted-view tcgen05 kernels of dcn_conv.cu do not take: fewer than 64 input channels (the detector's 16- and
 // 32-channel layers, where a K step of one pixel's channels leaves 3/4 or 1/2 of a 128-byte operand row empty), and the
-// stride-2 data gradient of wider layers (four parity accumulators do not fit in TMEM).
+// forward pass of other channel counts that are a multiple of 16 but not of 64.
 //
 // These layers are small GEMMs with tiny N (2N = 18 outputs) on a lot of pixels: HBM-bound by far (conv2 of the
-// detector at batch 1024: 21.7 GFLOP over 570 MB).  The plain mode of the DCN kernels ran them at 1.2 ms forward and
+// detector at batch 1024: 21.7 GFLOP over 1.4 GB).  The plain mode of the DCN kernels ran them at 1.2 ms forward and
 // 1.8 ms backward because it pays the sampling machinery (plan entries, four-corner blends) for integer taps.  Here
 // they are warp-level tensor-core kernels — mma.sync.m16n8k16 bf16 with the same hi/lo 3-term split as everywhere else
-// (fp32-class result), operands converted in registers straight from the framed channels-last copy of x, no shared
-// memory, no barriers:
+// (fp32-class result), operands converted in registers straight from the framed channels-last copy of x, no operand
+// staging in shared memory, no barriers in the main loops:
 //   forward   D[pixel, o]      = sum_{tap, c} x[pixel @ tap, c] * W[o, c, tap]        warp = 32 output pixels
 //   dgrad     E[pixel, tap, c] = sum_o goff[pixel, o] * W[o, c, tap], red.global.add.v4 into the framed channels-last
 //             gradient accumulator the DCN data gradient also adds into            warp = 16 output pixels
-//   wgrad     gW[c, o | tap]  += sum_pixel x[pixel @ tap, c] * goff[pixel, o]         warp = (kernel row, 16 channels),
-//             accumulators live in registers over the warp's whole pixel stream, one atomicAdd per entry at the end
+//   wgrad     gW[c, o | tap]  += sum_pixel x[pixel @ tap, c] * goff[pixel, o]         block = (kernel row, 16 channels),
+//             accumulators live in registers over each warp's whole pixel stream (next chunk's loads issued before the
+//             current one is converted), shared-memory block reduction, one atomicAdd per block and entry
+// Measured on detector conv2 (batch 1024): 0.375 / 0.66 / 0.45 ms — forward and data gradient at 58 % of the HBM copy
+// peak (profiles/r2_ncu_conv_small.txt); HMMA.16816 issues every 8 cycles per sub-partition (tools/hmma_probe.cu), far
+// above what N = 18 needs.  The backward pair is used below 64 channels only: at 64 / 128 channels the plain mode of the
+// fused DCN backward kernel is faster (dcn_conv.cu:conv_offset_bwd_supported).
 // 3 x 3 kernels, padding 1, stride 1 or 2, C % 16 == 0, 2N <= 32.
 #include <cuda_runtime.h>
 
